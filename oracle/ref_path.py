@@ -1,0 +1,249 @@
+"""numpy restatement of the reference's Python-level hot path.
+
+TEST INFRASTRUCTURE ONLY - see oracle/__init__.py.  /root/reference cannot travel
+to the GPU box, so the host-level algorithm of
+    /root/reference/src/figaroh/tools/regressor.py        (assembly, elimination)
+    /root/reference/src/figaroh/tools/qrdecomposition.py  (QR base parameters, OLS)
+    /root/reference/src/figaroh/tools/robot.py:76-155     (parameter naming)
+    /root/reference/src/figaroh/identification/identification_tools.py:204-234 (relative_stdev)
+is restated here on top of oracle/fg_oracle.c.  In this container
+tests/test_oracle_vs_reference.py checks every function against the unmodified
+reference files (imported by path through oracle/pinshim.py) on the same inputs.
+"""
+import numpy as np
+
+from . import kernels
+
+TOL_QR = 1e-8
+_INERTIAL = ("Ixx", "Ixy", "Ixz", "Iyy", "Iyz", "Izz", "mx", "my", "mz", "m")
+# position of pinocchio's [m, mx, my, mz, Ixx, Ixy, Iyy, Ixz, Iyz, Izz] inside FIGAROH's 10-block
+_PIN_TO_FIG = np.array([9, 6, 7, 8, 0, 1, 3, 2, 4, 5])
+
+
+def standard_parameters(om, param):
+    """robot.py:76-155 - ordered name->value dict that defines the column order."""
+    out = {}
+    dyn = om.dynamic_parameters()
+    for i in range(1, om.njoints):
+        blk = np.empty(10)
+        blk[_PIN_TO_FIG] = dyn[i - 1]
+        for nm, val in zip(_INERTIAL, blk):
+            out[f"{nm}{i}"] = val
+
+        def pick(flag, key):
+            if not param[flag]:
+                return 0
+            try:
+                return param[key][i - 1]
+            except Exception:
+                return 0
+        out[f"Ia{i}"] = pick("has_actuator_inertia", "Ia")
+        if param["has_friction"]:
+            try:
+                fv, fs = param["fv"][i - 1], param["fs"][i - 1]
+            except Exception:
+                fv, fs = 0, 0
+        else:
+            fv, fs = 0, 0
+        out[f"fv{i}"] = fv
+        out[f"fs{i}"] = fs
+        out[f"off{i}"] = pick("has_joint_offset", "off")
+    return out
+
+
+_FT_ROW = {"Fx": 0, "Fy": 1, "Fz": 2, "Mx": 3, "My": 4, "Mz": 5}
+
+
+def build_regressor_basic(om, q, v, a, param, per_sample=True):
+    """regressor.py:20-194.  per_sample=True keeps the reference's one-call-per-sample
+    loop (used for the timed CPU baseline); False does the whole batch in one C call."""
+    q = np.asarray(q, dtype=np.float64)
+    v = np.asarray(v, dtype=np.float64)
+    a = np.asarray(a, dtype=np.float64)
+    N = len(q)
+    nb, nv = om.njoints - 1, om.nv
+    flags = (1 if param["has_friction"] else 0) | (2 if param["has_actuator_inertia"] else 0) | \
+            (4 if param["has_joint_offset"] else 0)
+    if param["is_joint_torques"]:
+        mode, mask = 0, 0x3F
+    elif param["is_external_wrench"]:
+        mode, mask = 1, 0
+        for ft in param["force_torque"]:
+            if ft == "All":
+                mask |= 0x3F
+            elif ft in _FT_ROW:
+                mask |= 1 << _FT_ROW[ft]
+            else:
+                raise ValueError("Please enter valid parameters")
+    else:
+        raise UnboundLocalError("cannot access local variable 'W_mod' where it is not associated with a value")
+    if not per_sample:
+        return kernels.build_regressor_basic_c(om, q, v, a, mode, flags, mask)
+    if mode == 0 and nv != nb:
+        raise ValueError(f"could not broadcast input array from shape ({10 * nb},) into shape ({10 * nv},)")
+    nblk = nv if mode == 0 else 6
+    W = np.zeros((nblk * N, 14 * nb))
+    body_cols = (14 * np.arange(nb)[:, None] + _PIN_TO_FIG[None, :]).reshape(-1)
+    has_mass = om.mass[1:] != 0.0
+    ew_cols = (14 * np.nonzero(has_mass)[0][:, None] + _PIN_TO_FIG[None, :]).reshape(-1)
+    ew_src = (10 * np.nonzero(has_mass)[0][:, None] + np.arange(10)[None, :]).reshape(-1)
+    rows = np.arange(nblk) * N
+    for i in range(N):
+        Wt = kernels.joint_torque_regressor(om, q[i], v[i], a[i])
+        if mode == 0:
+            W[np.ix_(rows + i, body_cols)] = Wt
+            jj = np.arange(nv)
+            if flags & 1:
+                W[rows + i, 14 * jj + 11] = v[i]
+                W[rows + i, 14 * jj + 12] = np.sign(v[i])
+            if flags & 2:
+                W[rows + i, 14 * jj + 10] = a[i]
+            if flags & 4:
+                W[rows + i, 14 * jj + 13] = 1.0
+        else:
+            sel = [j for j in range(6) if (mask >> j) & 1]
+            W[np.ix_(rows[sel] + i, ew_cols)] = Wt[np.ix_(sel, ew_src)]
+            bb = np.arange(nb)
+            if flags & 1:
+                W[np.ix_(rows + i, 14 * bb + 11)] = v[i, :nb]
+                W[np.ix_(rows + i, 14 * bb + 12)] = np.sign(v[i, :nb])
+            if flags & 2:
+                W[np.ix_(rows + i, 14 * bb + 10)] = a[i, :nb]
+            if flags & 4:
+                W[np.ix_(rows + i, 14 * bb + 13)] = 1.0
+    return W
+
+
+def add_coupling_TX40(W, N, v, a):
+    """regressor.py:198-227 - three wrist-coupling columns on the rows of joints 5 and 6."""
+    v = np.asarray(v)
+    a = np.asarray(a)
+    out = np.hstack([W, np.zeros((W.shape[0], 3))])
+    sg = np.sign(v[:N, 4] + v[:N, 5])
+    out[4 * N:5 * N, -3:] = np.stack([a[:N, 5], v[:N, 5], sg], axis=1)
+    out[5 * N:6 * N, -3:] = np.stack([a[:N, 4], v[:N, 4], sg], axis=1)
+    return out
+
+
+def get_index_eliminate(W, params_std, tol_e=1e-6):
+    """regressor.py:258-279 - squared column norm below an absolute tolerance."""
+    sq = np.diag(np.dot(W.T, W))
+    names = list(params_std.keys())
+    idx_e = [i for i in range(sq.shape[0]) if sq[i] < tol_e]
+    params_r = [names[i] for i in range(sq.shape[0]) if not sq[i] < tol_e]
+    return idx_e, params_r
+
+
+def eliminate_non_dynaffect(W, params_std, tol_e=1e-6):
+    idx_e, params_r = get_index_eliminate(W, params_std, tol_e)
+    return np.delete(W, tuple(idx_e), 1), params_r
+
+
+def build_regressor_reduced(W, idx_e):
+    return np.delete(W, idx_e, 1)
+
+
+def _split_by_diag(W_e, params_r, tol_qr):
+    R = np.linalg.qr(W_e, mode="r")
+    d = np.abs(np.diag(R))
+    assert d.shape[0] == len(params_r), "params_r does not have same length with R"
+    base = [i for i in range(len(params_r)) if d[i] > tol_qr]
+    regroup = [i for i in range(len(params_r)) if not d[i] > tol_qr]
+    return base, regroup
+
+
+def get_baseIndex(W_e, params_r, tol_qr=TOL_QR):
+    """qrdecomposition.py:274-296."""
+    base, _ = _split_by_diag(W_e, params_r, tol_qr)
+    return tuple(base)
+
+
+def _expressions(names_base, names_regroup, beta):
+    """qrdecomposition.py:160-183 - 'name + |b|*other' strings for |b| >= 1e-6."""
+    out = list(names_base)
+    for i in range(len(out)):
+        for j in range(beta.shape[1]):
+            b = beta[i, j]
+            if abs(b) < 1e-6:
+                continue
+            out[i] = out[i] + (" - " if b < -1e-6 else " + ") + str(abs(b)) + "*" + str(names_regroup[j])
+    return out
+
+
+def _regrouped_qr(W_e, params_r, tol_qr):
+    base, regroup = _split_by_diag(W_e, params_r, tol_qr)
+    r = len(base)
+    W1 = W_e[:, base]
+    Wg = np.concatenate([W1, W_e[:, regroup]], axis=1)
+    Q, R = np.linalg.qr(Wg)
+    R1, R2, Q1 = R[:r, :r], R[:r, r:], Q[:, :r]
+    beta = np.around(np.dot(np.linalg.inv(R1), R2), 6)
+    return base, regroup, W1, Q1, R1, beta
+
+
+def get_baseParams(W_e, params_r, params_std=None, tol_qr=TOL_QR):
+    """qrdecomposition.py:190-271."""
+    base, regroup, W1, Q1, R1, beta = _regrouped_qr(W_e, params_r, tol_qr)
+    names = _expressions([params_r[i] for i in base], [params_r[i] for i in regroup], beta)
+    W_b = np.dot(Q1, R1)
+    assert np.allclose(W1, W_b), "base regressors is wrongly calculated!"
+    return W_b, names, base
+
+
+def double_QR(tau, W_e, params_r, params_std=None, tol_qr=TOL_QR):
+    """qrdecomposition.py:89-187."""
+    base, regroup, W1, Q1, R1, beta = _regrouped_qr(W_e, params_r, tol_qr)
+    phi_b = np.round(np.dot(np.linalg.inv(R1), np.dot(Q1.T, tau)), 6)
+    W_b = np.dot(Q1, R1)
+    assert np.allclose(W1, W_b), "base regressors is wrongly calculated!"
+    nb_, ng_ = [params_r[i] for i in base], [params_r[i] for i in regroup]
+    phi_std = None
+    if params_std is not None:
+        phi_std = [params_std[x] for x in nb_]
+        for i in range(len(base)):
+            for j in range(beta.shape[1]):
+                phi_std[i] = phi_std[i] + beta[i, j] * params_std[ng_[j]]
+        phi_std = np.around(phi_std, 5)
+    names = _expressions(nb_, ng_, beta)
+    bp = dict(zip(names, phi_b))
+    if params_std is not None:
+        return W_b, bp, names, phi_b, phi_std
+    return W_b, bp, names, phi_b
+
+
+def QR_pivoting(tau, W_e, params_r, tol_qr=TOL_QR):
+    """qrdecomposition.py:24-86 (full Q: only usable for small row counts)."""
+    from scipy import linalg
+    Q, R, P = linalg.qr(W_e, pivoting=True)
+    sorted_names = [params_r[P[i]] for i in range(P.shape[0])]
+    d = np.abs(np.diag(R))
+    rank = 0
+    for i in range(d.shape[0]):
+        if not d[i] > tol_qr:
+            rank = i
+            break
+    R1, Q1, R2 = R[:rank, :rank], Q[:, :rank], R[:rank, rank:]
+    beta = np.around(np.dot(np.linalg.inv(R1), R2), 6)
+    phi_b = np.round(np.dot(np.linalg.inv(R1), np.dot(Q1.T, tau)), 6)
+    W_b = np.dot(Q1, R1)
+    names = _expressions(sorted_names[:rank], sorted_names[rank:], beta)
+    return W_b, dict(zip(names, phi_b))
+
+
+def build_baseRegressor(W_e, idx_base):
+    return np.ascontiguousarray(W_e[:, list(idx_base)])
+
+
+def cond_num(W_b, norm_type=None):
+    if norm_type == "fro":
+        return np.linalg.cond(W_b, "fro")
+    if norm_type == "max_over_min_sigma":
+        return np.linalg.cond(W_b, 2) / np.linalg.cond(W_b, -2)
+    return np.linalg.cond(W_b)
+
+
+def relative_stdev(W_b, phi_b, tau):
+    """identification_tools.py:204-234."""
+    sig2 = np.linalg.norm(tau - np.dot(W_b, phi_b)) ** 2 / (W_b.shape[0] - phi_b.shape[0])
+    C = sig2 * np.linalg.inv(np.dot(W_b.T, W_b))
+    return np.round(100 * np.sqrt(np.diag(C)) / np.abs(phi_b), 2)
