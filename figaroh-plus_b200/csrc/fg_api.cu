@@ -1,0 +1,818 @@
+// fg_api.cu - host side of libfigaroh_b200.so: model upload, regressor plans, kernel
+// dispatch, TSQR state management and the extern "C" ABI declared in include/figaroh_b200.h.
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/figaroh_b200.h"
+#include "fg_kernels.cuh"
+
+using namespace fg;
+
+// ------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static int set_err(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define FG_CUDA(x)                                                                                   \
+  do {                                                                                               \
+    cudaError_t e_ = (x);                                                                            \
+    if (e_ != cudaSuccess)                                                                           \
+      return set_err(FG_ERR_CUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+// number of kernels this library has launched (diagnostic: bench.py reports it as gpu_launches)
+static std::atomic<long long> g_launches{0};
+#define FG_LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
+
+// ------------------------------------------------------------------------------------ objects
+struct DevPlan {
+  Plan P;
+  std::vector<ColDesc> cols;
+  std::vector<RowDesc> rows;
+  std::vector<int> nact, fullcol;
+  void* d_blob = nullptr;  // one allocation holding everything
+  DevPlanPtrs ptrs{};
+  ~DevPlan() { if (d_blob) cudaFree(d_blob); }
+};
+
+struct fg_model {
+  int njoints = 0, nq = 0, nv = 0;
+  std::vector<DevJoint> joints;
+  std::vector<double> mass;
+  double gravity[3] = {0, 0, -9.81};
+  DevJoint* d_joints = nullptr;
+  std::map<std::string, std::unique_ptr<DevPlan>> plans;
+  int sm_count = 148;
+  int max_smem = 227 * 1024;
+};
+
+struct fg_state {
+  int p = 0, p1 = 0;
+  int64_t rows = 0;
+  bool empty = true;
+  double* d_part = nullptr;     // merged factor: packed triangle + norms   [part_doubles(p1)]
+  double* d_parts = nullptr;    // scratch partial factors
+  int64_t parts_cap = 0;        // in parts
+  double* d_gR = nullptr;       // per-warp factors in HBM (only when they do not fit shared memory)
+  int64_t gR_cap = 0;           // in doubles
+  double* d_A = nullptr;        // (p1 x p1) dense scratch of the small stage
+  double* d_Re = nullptr;       // reduced factor (dense, (nk+1)^2)
+  double* d_X = nullptr;        // solve output
+  int* d_idx = nullptr;         // 2*p1 ints: column map + extents
+  int nk = -1;                  // columns kept by the last fg_state_reduce
+  std::vector<int> keep;
+  // staging for the host-buffer path
+  double* d_stage = nullptr;
+  int64_t stage_cap = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  // optional timing of the dominant (fold) kernel
+  bool timing = false;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  double main_ms_sum = 0.0;
+  long long main_launches = 0;
+  bool t_pending = false;
+};
+
+static int timing_begin(fg_state* s, cudaStream_t st) {
+  if (!s->timing) return FG_OK;
+  if (s->t_pending) {  // collect the previous launch first
+    FG_CUDA(cudaEventSynchronize(s->t1));
+    float ms = 0;
+    FG_CUDA(cudaEventElapsedTime(&ms, s->t0, s->t1));
+    s->main_ms_sum += ms; s->main_launches += 1; s->t_pending = false;
+  }
+  FG_CUDA(cudaEventRecord(s->t0, st));
+  return FG_OK;
+}
+static int timing_end(fg_state* s, cudaStream_t st) {
+  if (!s->timing) return FG_OK;
+  FG_CUDA(cudaEventRecord(s->t1, st));
+  s->t_pending = true;
+  return FG_OK;
+}
+
+static const int FIG2PIN[10] = {4, 5, 7, 6, 8, 9, 1, 2, 3, 0};  // figaroh slot -> pinocchio parameter
+
+// ------------------------------------------------------------------------------------ model
+extern "C" const char* fg_last_error(void) { return g_err; }
+extern "C" int fg_abi_version(void) { return FG_ABI_VERSION; }
+
+extern "C" int fg_model_create(const fg_model_desc* d, fg_model** out) {
+  if (!d || !out) return set_err(FG_ERR_INVALID, "fg_model_create: null argument");
+  if (d->njoints < 2 || d->njoints > kMaxJoints)
+    return set_err(FG_ERR_UNSUPPORTED, "fg_model_create: njoints=%d outside [2,%d]", d->njoints, kMaxJoints);
+  std::unique_ptr<fg_model> m(new fg_model);
+  m->njoints = d->njoints; m->nq = d->nq; m->nv = d->nv;
+  m->joints.resize(d->njoints);
+  m->mass.assign(d->njoints, 1.0);
+  int nq = 0, nv = 0;
+  for (int i = 0; i < d->njoints; ++i) {
+    DevJoint& j = m->joints[i];
+    memset(&j, 0, sizeof j);
+    for (int k = 0; k < 9; ++k) j.plcR[k] = i == 0 ? (k % 4 == 0 ? 1.0 : 0.0) : d->plc_R[9 * i + k];
+    for (int k = 0; k < 3; ++k) { j.plcp[k] = i == 0 ? 0.0 : d->plc_p[3 * i + k]; j.axis[k] = d->axis[3 * i + k]; }
+    j.parent = d->parent[i]; j.jtype = d->jtype[i]; j.idx_q = d->idx_q[i]; j.idx_v = d->idx_v[i];
+    if (d->mass) m->mass[i] = d->mass[i];
+    if (i == 0) continue;
+    if (j.parent < 0 || j.parent >= i) return set_err(FG_ERR_INVALID, "joint %d: parent %d not before it", i, j.parent);
+    int jq, jv;
+    switch (j.jtype) {
+      case FG_JT_REVOLUTE: jq = 1; jv = 1; break;
+      case FG_JT_REVOLUTE_UNB: jq = 2; jv = 1; break;
+      case FG_JT_PRISMATIC: jq = 1; jv = 1; break;
+      case FG_JT_FREEFLYER: jq = 7; jv = 6; break;
+      default: return set_err(FG_ERR_UNSUPPORTED, "joint %d: unsupported joint type %d", i, j.jtype);
+    }
+    if (j.idx_q != nq || j.idx_v != nv) return set_err(FG_ERR_INVALID, "joint %d: idx_q/idx_v not contiguous", i);
+    nq += jq; nv += jv;
+  }
+  if (nq != d->nq || nv != d->nv) return set_err(FG_ERR_INVALID, "nq/nv (%d,%d) do not match joints (%d,%d)", d->nq, d->nv, nq, nv);
+  if (d->gravity) for (int k = 0; k < 3; ++k) m->gravity[k] = d->gravity[k];
+  FG_CUDA(cudaMalloc(&m->d_joints, sizeof(DevJoint) * d->njoints));
+  FG_CUDA(cudaMemcpy(m->d_joints, m->joints.data(), sizeof(DevJoint) * d->njoints, cudaMemcpyHostToDevice));
+  int dev = 0;
+  FG_CUDA(cudaGetDevice(&dev));
+  FG_CUDA(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, dev));
+  FG_CUDA(cudaDeviceGetAttribute(&m->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  *out = m.release();
+  return FG_OK;
+}
+
+extern "C" void fg_model_destroy(fg_model* m) {
+  if (!m) return;
+  if (m->d_joints) cudaFree(m->d_joints);
+  delete m;
+}
+
+static int joint_of_vidx(const fg_model* m, int vi, int* local) {
+  for (int i = 1; i < m->njoints; ++i) {
+    const int nvj = m->joints[i].jtype == FG_JT_FREEFLYER ? 6 : 1;
+    if (vi >= m->joints[i].idx_v && vi < m->joints[i].idx_v + nvj) { *local = vi - m->joints[i].idx_v; return i; }
+  }
+  return -1;
+}
+
+static int check_cfg(const fg_model* m, const fg_regressor_cfg* cfg) {
+  if (!m || !cfg) return set_err(FG_ERR_INVALID, "null model or cfg");
+  const int nb = m->njoints - 1;
+  if (cfg->mode == FG_MODE_JOINT_TORQUES) {
+    if (m->nv != nb)
+      return set_err(FG_ERR_UNSUPPORTED,
+                     "joint-torque mode needs nv == njoints-1 (got nv=%d, bodies=%d): the reference cannot "
+                     "broadcast a %d-wide regressor row into %d columns (regressor.py:53)", m->nv, nb, 10 * nb, 10 * m->nv);
+  } else if (cfg->mode == FG_MODE_EXTERNAL_WRENCH) {
+    if (m->nv < 6) return set_err(FG_ERR_UNSUPPORTED, "external-wrench mode needs nv >= 6");
+    if (cfg->flags & FG_FLAG_TX40_COUPLING) return set_err(FG_ERR_UNSUPPORTED, "TX40 coupling is a joint-torque feature");
+  } else {
+    return set_err(FG_ERR_INVALID, "unknown mode %d", cfg->mode);
+  }
+  if ((cfg->flags & FG_FLAG_TX40_COUPLING) && m->nv < 6) return set_err(FG_ERR_UNSUPPORTED, "TX40 coupling needs 6 joints");
+  return FG_OK;
+}
+
+extern "C" int fg_regressor_shape(const fg_model* m, const fg_regressor_cfg* cfg, int32_t* rps, int32_t* cols) {
+  int rc = check_cfg(m, cfg);
+  if (rc) return rc;
+  if (rps) *rps = cfg->mode == FG_MODE_JOINT_TORQUES ? (cfg->n_row_sel > 0 ? cfg->n_row_sel : m->nv) : 6;
+  if (cols) *cols = 14 * (m->njoints - 1) + ((cfg->flags & FG_FLAG_TX40_COUPLING) ? 3 : 0);
+  return FG_OK;
+}
+
+// Build (or fetch) the device plan of (model, cfg, column selection).
+static int get_plan(fg_model* m, const fg_regressor_cfg* cfg, const int32_t* col_sel, int n_col_sel, DevPlan** out) {
+  int rc = check_cfg(m, cfg);
+  if (rc) return rc;
+  std::string key = std::to_string(cfg->mode) + ":" + std::to_string(cfg->flags) + ":" + std::to_string(cfg->ft_mask) + ":";
+  for (int i = 0; i < cfg->n_row_sel; ++i) key += std::to_string(cfg->row_sel[i]) + ",";
+  key += ":";
+  for (int i = 0; i < n_col_sel; ++i) key += std::to_string(col_sel[i]) + ",";
+  auto it = m->plans.find(key);
+  if (it != m->plans.end()) { *out = it->second.get(); return FG_OK; }
+
+  const int nb = m->njoints - 1;
+  const int ncols_full = 14 * nb + ((cfg->flags & FG_FLAG_TX40_COUPLING) ? 3 : 0);
+  std::unique_ptr<DevPlan> pl(new DevPlan);
+  // ---- rows
+  std::vector<int> vsel;
+  if (cfg->mode == FG_MODE_JOINT_TORQUES) {
+    if (cfg->n_row_sel > 0) {
+      for (int i = 0; i < cfg->n_row_sel; ++i) {
+        const int v = cfg->row_sel[i];
+        if (v < 0 || v >= m->nv || (i > 0 && v <= cfg->row_sel[i - 1]))
+          return set_err(FG_ERR_INVALID, "row_sel must be ascending velocity indices in [0,%d)", m->nv);
+        vsel.push_back(v);
+      }
+    } else {
+      for (int v = 0; v < m->nv; ++v) vsel.push_back(v);
+    }
+  } else {
+    for (int v = 0; v < 6; ++v) vsel.push_back(v);
+  }
+  if ((int)vsel.size() > kMaxRowGroups) return set_err(FG_ERR_UNSUPPORTED, "more than %d row blocks", kMaxRowGroups);
+  for (size_t g = 0; g < vsel.size(); ++g) {
+    int local = 0;
+    const int j = joint_of_vidx(m, vsel[g], &local);
+    if (j < 0) return set_err(FG_ERR_INVALID, "no joint owns velocity index %d", vsel[g]);
+    RowDesc rd;
+    memset(&rd, 0, sizeof rd);
+    const DevJoint& J = m->joints[j];
+    const bool enabled = cfg->mode == FG_MODE_JOINT_TORQUES || ((cfg->ft_mask >> g) & 1);
+    if (enabled) {
+      if (J.jtype == FG_JT_REVOLUTE || J.jtype == FG_JT_REVOLUTE_UNB) for (int k = 0; k < 3; ++k) rd.S[3 + k] = J.axis[k];
+      else if (J.jtype == FG_JT_PRISMATIC) for (int k = 0; k < 3; ++k) rd.S[k] = J.axis[k];
+      else rd.S[local] = 1.0;
+    }
+    rd.joint = j;
+    rd.rowblock = cfg->mode == FG_MODE_JOINT_TORQUES ? vsel[g] : (int)g;
+    rd.start_col = 14 * (j - 1);
+    pl->rows.push_back(rd);
+  }
+  // ---- columns (full reference numbering first)
+  std::vector<ColDesc> full(ncols_full);
+  for (auto& c : full) { memset(&c, 0, sizeof c); c.kind = COL_ZERO; c.grp = -2; }
+  auto grp_of_rowblock = [&](int rb) {
+    for (size_t g = 0; g < pl->rows.size(); ++g) if (pl->rows[g].rowblock == rb) return (int)g;
+    return -2;
+  };
+  for (int b = 0; b < nb; ++b) {
+    const int body = b + 1;
+    uint64_t anc = 0;
+    for (size_t g = 0; g < pl->rows.size(); ++g) {
+      int j = body;
+      while (j > pl->rows[g].joint) j = m->joints[j].parent;
+      if (j == pl->rows[g].joint) anc |= 1ull << g;
+    }
+    const bool massless = cfg->mode == FG_MODE_EXTERNAL_WRENCH && m->mass[body] == 0.0;
+    for (int f = 0; f < 10; ++f) {
+      ColDesc& c = full[14 * b + f];
+      if (massless) continue;
+      c.kind = COL_INERTIAL; c.body = body; c.k = FIG2PIN[f];
+      c.anc_lo = (unsigned)(anc & 0xffffffffu); c.anc_hi = (unsigned)(anc >> 32);
+    }
+    const int grp = cfg->mode == FG_MODE_JOINT_TORQUES ? grp_of_rowblock(b) : -1;
+    const bool src_ok = b < m->nv;  // the reference indexes v[i, b] (regressor.py:145-158)
+    auto extra = [&](int slot, int src) {
+      ColDesc& c = full[14 * b + slot];
+      if (!src_ok || grp == -2) return;
+      c.kind = COL_EXTRA; c.k = src; c.vidx = b; c.grp = grp;
+    };
+    if (cfg->flags & FG_FLAG_ACTUATOR_INERTIA) extra(10, SRC_QDD);
+    if (cfg->flags & FG_FLAG_FRICTION) { extra(11, SRC_QD); extra(12, SRC_SIGN_QD); }
+    if (cfg->flags & FG_FLAG_JOINT_OFFSET) extra(13, SRC_ONE);
+  }
+  if (cfg->flags & FG_FLAG_TX40_COUPLING)
+    for (int k = 0; k < 3; ++k) { ColDesc& c = full[14 * nb + k]; c.kind = COL_COUPLING; c.k = k; }
+  // ---- column selection
+  std::vector<int> sel;
+  if (n_col_sel > 0) {
+    for (int i = 0; i < n_col_sel; ++i) {
+      if (col_sel[i] < 0 || col_sel[i] >= ncols_full || (i > 0 && col_sel[i] <= col_sel[i - 1]))
+        return set_err(FG_ERR_INVALID, "col_sel must be ascending column indices in [0,%d)", ncols_full);
+      sel.push_back(col_sel[i]);
+    }
+  } else {
+    for (int c = 0; c < ncols_full; ++c) sel.push_back(c);
+  }
+  const int ncols = (int)sel.size(), p1 = ncols + 1;
+  pl->cols.resize(p1);
+  pl->fullcol.resize(p1);
+  pl->nact.resize(p1);
+  for (int c = 0; c < ncols; ++c) { pl->cols[c] = full[sel[c]]; pl->fullcol[c] = sel[c]; }
+  memset(&pl->cols[ncols], 0, sizeof(ColDesc));
+  pl->cols[ncols].kind = COL_RHS; pl->cols[ncols].grp = -1;
+  pl->fullcol[ncols] = -1;
+  for (int c = 0; c < p1; ++c) {
+    int na = 0;
+    const int fc = c < ncols ? sel[c] : ncols_full;
+    for (auto& r : pl->rows) if (r.start_col <= fc) ++na;
+    pl->nact[c] = na;
+  }
+  Plan& P = pl->P;
+  memset(&P, 0, sizeof P);
+  P.nj = m->njoints; P.nq = m->nq; P.nv = m->nv; P.ms = (int)pl->rows.size();
+  P.ncols = ncols; P.p1 = p1; P.mode = cfg->mode; P.flags = cfg->flags;
+  for (int k = 0; k < 3; ++k) P.gravity[k] = m->gravity[k];
+  // ---- upload as one blob
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t o_plan = 0, o_rows = al(sizeof(Plan)), o_cols = o_rows + al(sizeof(RowDesc) * pl->rows.size());
+  const size_t o_nact = o_cols + al(sizeof(ColDesc) * p1), o_full = o_nact + al(sizeof(int) * p1);
+  const size_t total = o_full + al(sizeof(int) * p1);
+  std::vector<unsigned char> blob(total, 0);
+  memcpy(&blob[o_plan], &P, sizeof P);
+  memcpy(&blob[o_rows], pl->rows.data(), sizeof(RowDesc) * pl->rows.size());
+  memcpy(&blob[o_cols], pl->cols.data(), sizeof(ColDesc) * p1);
+  memcpy(&blob[o_nact], pl->nact.data(), sizeof(int) * p1);
+  memcpy(&blob[o_full], pl->fullcol.data(), sizeof(int) * p1);
+  FG_CUDA(cudaMalloc(&pl->d_blob, total));
+  FG_CUDA(cudaMemcpy(pl->d_blob, blob.data(), total, cudaMemcpyHostToDevice));
+  unsigned char* db = (unsigned char*)pl->d_blob;
+  pl->ptrs.plan = (const Plan*)(db + o_plan);
+  pl->ptrs.joints = m->d_joints;
+  pl->ptrs.rows = (const RowDesc*)(db + o_rows);
+  pl->ptrs.cols = (const ColDesc*)(db + o_cols);
+  pl->ptrs.nact = (const int*)(db + o_nact);
+  pl->ptrs.fullcol = (const int*)(db + o_full);
+  *out = pl.get();
+  m->plans[key] = std::move(pl);
+  return FG_OK;
+}
+
+// ------------------------------------------------------------------------------------ materialise
+template <int MSMAX, int S>
+static int launch_materialize(fg_model* m, DevPlan* pl, const double* q, const double* v, const double* a, int64_t N,
+                              double* W, int64_t ldw, cudaStream_t st) {
+  int nwarps = 8;
+  while (nwarps > 1 &&
+         make_layout(pl->P.nj, pl->P.ms, pl->P.p1, pl->P.nv, S, MSMAX * S, nwarps, false, true).total > m->max_smem / 2)
+    nwarps /= 2;  // aim for two CTAs per SM
+  const SmemLayout L = make_layout(pl->P.nj, pl->P.ms, pl->P.p1, pl->P.nv, S, MSMAX * S, nwarps, false, true);
+  if (L.total > m->max_smem) return set_err(FG_ERR_UNSUPPORTED, "materialise: %d bytes of shared memory needed", L.total);
+  auto kern = regressor_materialize_kernel<MSMAX, S>;
+  FG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+  const int64_t ntiles = (N + S - 1) / S;
+  int64_t grid = std::min<int64_t>((ntiles + nwarps - 1) / nwarps, (int64_t)m->sm_count * 16);
+  if (grid < 1) grid = 1;
+  kern<<<(unsigned)grid, nwarps * 32, L.total, st>>>(pl->ptrs, q, v, a, N, W, ldw);
+  FG_CUDA(cudaGetLastError());
+  FG_LAUNCHED();
+  return FG_OK;
+}
+
+extern "C" int fg_regressor_materialize(const fg_model* mc, const fg_regressor_cfg* cfg, const double* q,
+                                        const double* v, const double* a, int64_t N, double* W, int64_t ldw,
+                                        void* stream) {
+  fg_model* m = const_cast<fg_model*>(mc);
+  DevPlan* pl = nullptr;
+  fg_regressor_cfg c2 = *cfg;
+  c2.n_row_sel = 0; c2.row_sel = nullptr;  // the materialised matrix always has every row block
+  c2.n_col_sel = 0; c2.col_sel = nullptr;  // ... and every column
+  int rc = get_plan(m, &c2, nullptr, 0, &pl);
+  if (rc) return rc;
+  if (N <= 0) return FG_OK;
+  if (ldw < pl->P.ncols) return set_err(FG_ERR_INVALID, "ldw=%lld smaller than %d columns", (long long)ldw, pl->P.ncols);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ms = pl->P.ms;
+  if (ms <= 8) return launch_materialize<8, 4>(m, pl, q, v, a, N, W, ldw, st);
+  if (ms <= 24) return launch_materialize<24, 1>(m, pl, q, v, a, N, W, ldw, st);
+  if (ms <= 48) return launch_materialize<48, 1>(m, pl, q, v, a, N, W, ldw, st);
+  return set_err(FG_ERR_UNSUPPORTED, "materialise: %d row blocks per sample not supported", ms);
+}
+
+// ------------------------------------------------------------------------------------ state
+extern "C" int64_t fg_state_packed_doubles(int32_t p) { return (int64_t)(p + 1) * (p + 1) + (p + 1) + 1; }
+extern "C" int fg_state_p(const fg_state* s) { return s ? s->p : -1; }
+extern "C" int64_t fg_state_rows(const fg_state* s) { return s ? s->rows : -1; }
+
+extern "C" int fg_state_create(int32_t p, fg_state** out) {
+  if (p < 1 || p > 479 || !out) return set_err(FG_ERR_INVALID, "fg_state_create: p=%d outside [1,479]", p);
+  std::unique_ptr<fg_state> s(new fg_state);
+  s->p = p; s->p1 = p + 1;
+  const int p1 = s->p1;
+  FG_CUDA(cudaMalloc(&s->d_part, sizeof(double) * part_doubles(p1)));
+  FG_CUDA(cudaMemset(s->d_part, 0, sizeof(double) * part_doubles(p1)));
+  FG_CUDA(cudaMalloc(&s->d_A, sizeof(double) * p1 * p1));
+  FG_CUDA(cudaMalloc(&s->d_Re, sizeof(double) * p1 * p1));
+  FG_CUDA(cudaMalloc(&s->d_X, sizeof(double) * p1 * p1));
+  FG_CUDA(cudaMalloc(&s->d_idx, sizeof(int) * 2 * p1));
+  *out = s.release();
+  return FG_OK;
+}
+
+extern "C" void fg_state_destroy(fg_state* s) {
+  if (!s) return;
+  cudaFree(s->d_part); cudaFree(s->d_parts); cudaFree(s->d_gR); cudaFree(s->d_A); cudaFree(s->d_Re);
+  cudaFree(s->d_X); cudaFree(s->d_idx); cudaFree(s->d_stage);
+  if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+  for (auto& e : s->ev) if (e) cudaEventDestroy(e);
+  if (s->t0) cudaEventDestroy(s->t0);
+  if (s->t1) cudaEventDestroy(s->t1);
+  delete s;
+}
+
+extern "C" long long fg_launch_count(void) { return g_launches.load(); }
+
+extern "C" int fg_state_set_timing(fg_state* s, int on) {
+  if (!s) return set_err(FG_ERR_INVALID, "null state");
+  if (on && !s->t0) {
+    FG_CUDA(cudaEventCreate(&s->t0));
+    FG_CUDA(cudaEventCreate(&s->t1));
+  }
+  s->timing = on != 0;
+  s->main_ms_sum = 0.0; s->main_launches = 0; s->t_pending = false;
+  return FG_OK;
+}
+
+extern "C" int fg_state_get_timing(fg_state* s, double* total_ms, long long* launches) {
+  if (!s) return set_err(FG_ERR_INVALID, "null state");
+  if (s->t_pending) {
+    FG_CUDA(cudaEventSynchronize(s->t1));
+    float ms = 0;
+    FG_CUDA(cudaEventElapsedTime(&ms, s->t0, s->t1));
+    s->main_ms_sum += ms; s->main_launches += 1; s->t_pending = false;
+  }
+  if (total_ms) *total_ms = s->main_ms_sum;
+  if (launches) *launches = s->main_launches;
+  return FG_OK;
+}
+
+extern "C" int fg_state_reset(fg_state* s, void* stream) {
+  if (!s) return set_err(FG_ERR_INVALID, "null state");
+  FG_CUDA(cudaMemsetAsync(s->d_part, 0, sizeof(double) * part_doubles(s->p1), (cudaStream_t)stream));
+  s->rows = 0; s->empty = true; s->nk = -1;
+  return FG_OK;
+}
+
+static int ensure_parts(fg_state* s, int64_t nparts) {
+  if (nparts <= s->parts_cap) return FG_OK;
+  if (s->d_parts) cudaFree(s->d_parts);
+  s->d_parts = nullptr; s->parts_cap = 0;
+  FG_CUDA(cudaMalloc(&s->d_parts, sizeof(double) * part_doubles(s->p1) * nparts));
+  s->parts_cap = nparts;
+  return FG_OK;
+}
+static int ensure_gR(fg_state* s, int64_t doubles) {
+  if (doubles <= s->gR_cap) return FG_OK;
+  if (s->d_gR) cudaFree(s->d_gR);
+  s->d_gR = nullptr; s->gR_cap = 0;
+  FG_CUDA(cudaMalloc(&s->d_gR, sizeof(double) * doubles));
+  s->gR_cap = doubles;
+  return FG_OK;
+}
+
+
+template <int NSLOT, int TR>
+static int launch_merge_level(double* parts, int nparts, int stride, int p1, int max_smem, cudaStream_t st) {
+  const int pairs = (nparts + 2 * stride - 1) / (2 * stride);
+  const int ntri = p1 * (p1 + 1) / 2;
+  const int xs_bytes = align16(2 * (TR + 2) * 8);
+  int smem = xs_bytes + ntri * 8;
+  int use_smem = 1;
+  if (smem > max_smem) { smem = xs_bytes; use_smem = 0; }
+  auto kern = merge_pairs_kernel<NSLOT, TR>;
+  FG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kern<<<pairs, 32, smem, st>>>(parts, nparts, stride, p1, use_smem);
+  FG_CUDA(cudaGetLastError());
+  FG_LAUNCHED();
+  return FG_OK;
+}
+
+static int merge_level(double* parts, int nparts, int stride, int p1, int max_smem, cudaStream_t st) {
+  const int nslot = (p1 + 31) / 32;
+  if (nslot <= 1) return launch_merge_level<1, 24>(parts, nparts, stride, p1, max_smem, st);
+  if (nslot <= 2) return launch_merge_level<2, 24>(parts, nparts, stride, p1, max_smem, st);
+  if (nslot <= 3) return launch_merge_level<3, 24>(parts, nparts, stride, p1, max_smem, st);
+  if (nslot <= 5) return launch_merge_level<5, 16>(parts, nparts, stride, p1, max_smem, st);
+  if (nslot <= 8) return launch_merge_level<8, 12>(parts, nparts, stride, p1, max_smem, st);
+  if (nslot <= 11) return launch_merge_level<11, 8>(parts, nparts, stride, p1, max_smem, st);
+  return launch_merge_level<15, 8>(parts, nparts, stride, p1, max_smem, st);
+}
+
+// Tree-merge parts[0..nparts) (slot `nparts` may hold the state's current factor) into s->d_part.
+static int merge_parts_into_state(fg_state* s, int nparts, int max_smem, cudaStream_t st) {
+  const int64_t pd = part_doubles(s->p1);
+  int total = nparts;
+  if (!s->empty) {  // the existing factor is one more part (placed last: deterministic order)
+    FG_CUDA(cudaMemcpyAsync(s->d_parts + pd * nparts, s->d_part, sizeof(double) * pd, cudaMemcpyDeviceToDevice, st));
+    total = nparts + 1;
+  }
+  for (int stride = 1; stride < total; stride *= 2) {
+    int rc = merge_level(s->d_parts, total, stride, s->p1, max_smem, st);
+    if (rc) return rc;
+  }
+  FG_CUDA(cudaMemcpyAsync(s->d_part, s->d_parts, sizeof(double) * pd, cudaMemcpyDeviceToDevice, st));
+  s->empty = false;
+  s->nk = -1;
+  return FG_OK;
+}
+
+static int device_limits(int* sm_count, int* max_smem) {
+  int dev = 0;
+  FG_CUDA(cudaGetDevice(&dev));
+  FG_CUDA(cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, dev));
+  FG_CUDA(cudaDeviceGetAttribute(max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  return FG_OK;
+}
+
+// ---- dense accumulate
+template <int NSLOT, int TR>
+static int launch_dense(fg_state* s, const double* W, int64_t ldw, const double* tau, int64_t rows, cudaStream_t st) {
+  int sm_count, max_smem;
+  int rc = device_limits(&sm_count, &max_smem);
+  if (rc) return rc;
+  const int p1 = s->p1, ntri = p1 * (p1 + 1) / 2;
+  const int xs_bytes = align16(2 * (TR + 2) * 8);
+  const int static_smem = 8 * 32 * NSLOT * 8 + 64;
+  int nwarps = 8;
+  bool in_smem = true;
+  while (nwarps > 1 && nwarps * (xs_bytes + align16(ntri * 8)) + static_smem > max_smem) --nwarps;
+  if (nwarps * (xs_bytes + align16(ntri * 8)) + static_smem > max_smem || nwarps < 4) { in_smem = false; nwarps = 8; }
+  const int64_t ntiles = (rows + TR - 1) / TR;
+  int grid = (int)std::min<int64_t>((ntiles + nwarps - 1) / nwarps, sm_count);
+  if (grid < 1) grid = 1;
+  if (!in_smem) {  // factors live in HBM/L2: keep the footprint well inside L2
+    const int64_t cap = std::max<int64_t>(1, (64ll << 20) / ((int64_t)ntri * 8 * nwarps));
+    grid = (int)std::min<int64_t>(grid, cap);
+    rc = ensure_gR(s, (int64_t)grid * nwarps * ntri);
+    if (rc) return rc;
+  }
+  rc = ensure_parts(s, grid + 1);
+  if (rc) return rc;
+  const int smem = in_smem ? nwarps * (xs_bytes + align16(ntri * 8)) : nwarps * xs_bytes;
+  auto kern = accumulate_dense_kernel<NSLOT, TR>;
+  FG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  rc = timing_begin(s, st);
+  if (rc) return rc;
+  kern<<<grid, nwarps * 32, smem, st>>>(W, ldw, tau, rows, p1, s->d_parts, in_smem ? nullptr : s->d_gR);
+  rc = timing_end(s, st);
+  if (rc) return rc;
+  FG_CUDA(cudaGetLastError());
+  FG_LAUNCHED();
+  rc = merge_parts_into_state(s, grid, max_smem, st);
+  if (rc) return rc;
+  s->rows += rows;
+  return FG_OK;
+}
+
+extern "C" int fg_state_accumulate_dense(fg_state* s, const double* W, int64_t ldw, const double* tau, int64_t rows,
+                                         void* stream) {
+  if (!s || (!W && rows > 0)) return set_err(FG_ERR_INVALID, "fg_state_accumulate_dense: null argument");
+  if (rows <= 0) return FG_OK;
+  if (ldw < s->p) return set_err(FG_ERR_INVALID, "ldw=%lld smaller than p=%d", (long long)ldw, s->p);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nslot = (s->p1 + 31) / 32;
+  if (nslot <= 1) return launch_dense<1, 24>(s, W, ldw, tau, rows, st);
+  if (nslot <= 2) return launch_dense<2, 24>(s, W, ldw, tau, rows, st);
+  if (nslot <= 3) return launch_dense<3, 24>(s, W, ldw, tau, rows, st);
+  if (nslot <= 5) return launch_dense<5, 16>(s, W, ldw, tau, rows, st);
+  if (nslot <= 8) return launch_dense<8, 12>(s, W, ldw, tau, rows, st);
+  if (nslot <= 11) return launch_dense<11, 8>(s, W, ldw, tau, rows, st);
+  return launch_dense<15, 8>(s, W, ldw, tau, rows, st);
+}
+
+// ---- fused accumulate
+template <int NSLOT, int MS, int S>
+static int launch_fused(fg_state* s, fg_model* m, DevPlan* pl, const double* q, const double* v, const double* a,
+                        const double* tau, int64_t ld_tau, int64_t N, cudaStream_t st) {
+  constexpr int TR = MS * S;
+  constexpr int TRM = TR >= 8 ? TR : 8;
+  static_assert(TRM == TR || true, "");
+  const int p1 = s->p1, ntri = p1 * (p1 + 1) / 2;
+  const int static_smem = 8 * 32 * NSLOT * 8 + 64;
+  int nwarps = 8;
+  bool in_smem = true;
+  while (nwarps > 1 &&
+         make_layout(pl->P.nj, pl->P.ms, p1, pl->P.nv, S, TRM, nwarps, true, true).total + static_smem > m->max_smem)
+    --nwarps;
+  if (make_layout(pl->P.nj, pl->P.ms, p1, pl->P.nv, S, TRM, nwarps, true, true).total + static_smem > m->max_smem ||
+      nwarps < 4) {
+    in_smem = false;
+    nwarps = 8;
+  }
+  const SmemLayout L = make_layout(pl->P.nj, pl->P.ms, p1, pl->P.nv, S, TRM, nwarps, in_smem, true);
+  if (L.total + static_smem > m->max_smem) return set_err(FG_ERR_UNSUPPORTED, "fused kernel needs %d bytes of shared memory", L.total);
+  const int64_t ntiles = (N + S - 1) / S;
+  int grid = (int)std::min<int64_t>((ntiles + nwarps - 1) / nwarps, m->sm_count);
+  if (grid < 1) grid = 1;
+  int rc;
+  if (!in_smem) {
+    const int64_t cap = std::max<int64_t>(1, (64ll << 20) / ((int64_t)ntri * 8 * nwarps));
+    grid = (int)std::min<int64_t>(grid, cap);
+    rc = ensure_gR(s, (int64_t)grid * nwarps * ntri);
+    if (rc) return rc;
+  }
+  rc = ensure_parts(s, grid + 1);
+  if (rc) return rc;
+  auto kern = accumulate_samples_kernel<NSLOT, MS, S>;
+  FG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+  rc = timing_begin(s, st);
+  if (rc) return rc;
+  kern<<<grid, nwarps * 32, L.total, st>>>(pl->ptrs, q, v, a, tau, ld_tau, N, s->d_parts,
+                                           in_smem ? nullptr : s->d_gR, 1);
+  rc = timing_end(s, st);
+  if (rc) return rc;
+  FG_CUDA(cudaGetLastError());
+  FG_LAUNCHED();
+  rc = merge_parts_into_state(s, grid, m->max_smem, st);
+  if (rc) return rc;
+  s->rows += N * pl->P.ms;
+  return FG_OK;
+}
+
+static int accumulate_samples_dev(fg_state* s, fg_model* m, const fg_regressor_cfg* cfg, const double* q,
+                                  const double* v, const double* a, const double* tau, int64_t ld_tau, int64_t N,
+                                  cudaStream_t st) {
+  DevPlan* pl = nullptr;
+  int rc = get_plan(m, cfg, cfg->col_sel, cfg->n_col_sel, &pl);
+  if (rc) return rc;
+  if (pl->P.ncols != s->p)
+    return set_err(FG_ERR_INVALID, "state has p=%d but the regressor has %d columns", s->p, pl->P.ncols);
+  if (N <= 0) return FG_OK;
+  if (tau && ld_tau < N) return set_err(FG_ERR_INVALID, "ld_tau=%lld smaller than N=%lld", (long long)ld_tau, (long long)N);
+  const int ms = pl->P.ms, nslot = (pl->P.p1 + 31) / 32;
+  if (ms == 6 && nslot <= 3) return launch_fused<3, 6, 4>(s, m, pl, q, v, a, tau, ld_tau, N, st);
+  if (ms == 6 && nslot <= 11) return launch_fused<11, 6, 1>(s, m, pl, q, v, a, tau, ld_tau, N, st);
+  if (ms == 6 && nslot <= 15) return launch_fused<15, 6, 1>(s, m, pl, q, v, a, tau, ld_tau, N, st);
+  if (ms == 8 && nslot <= 5) return launch_fused<5, 8, 2>(s, m, pl, q, v, a, tau, ld_tau, N, st);
+  if (ms == 8 && nslot <= 11) return launch_fused<11, 8, 1>(s, m, pl, q, v, a, tau, ld_tau, N, st);
+  return set_err(FG_ERR_UNSUPPORTED,
+                 "no fused kernel for %d row blocks x %d columns; materialise W and use fg_state_accumulate_dense",
+                 ms, pl->P.ncols);
+}
+
+extern "C" int fg_state_accumulate_samples(fg_state* s, const fg_model* m, const fg_regressor_cfg* cfg,
+                                           const double* q, const double* v, const double* a, const double* tau,
+                                           int64_t ld_tau, int64_t N, void* stream) {
+  if (!s || !m || !cfg) return set_err(FG_ERR_INVALID, "fg_state_accumulate_samples: null argument");
+  return accumulate_samples_dev(s, const_cast<fg_model*>(m), cfg, q, v, a, tau, ld_tau, N, (cudaStream_t)stream);
+}
+
+// ---- host-buffer path: chunked H2D staging overlapped with the fused kernel
+extern "C" int fg_state_accumulate_samples_host(fg_state* s, const fg_model* mc, const fg_regressor_cfg* cfg,
+                                                const double* q, const double* v, const double* a, const double* tau,
+                                                int64_t ld_tau, int64_t N, void* stream) {
+  if (!s || !mc || !cfg) return set_err(FG_ERR_INVALID, "fg_state_accumulate_samples_host: null argument");
+  fg_model* m = const_cast<fg_model*>(mc);
+  int32_t ms = 0, cols = 0;
+  int rc = fg_regressor_shape(m, cfg, &ms, &cols);
+  if (rc) return rc;
+  if (N <= 0) return FG_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t chunk = std::min<int64_t>(N, 1 << 18);
+  const int64_t per_sample = m->nq + 2 * m->nv + ms;
+  const int64_t need = 2 * chunk * per_sample;
+  if (need > s->stage_cap) {
+    if (s->d_stage) cudaFree(s->d_stage);
+    s->d_stage = nullptr; s->stage_cap = 0;
+    FG_CUDA(cudaMalloc(&s->d_stage, sizeof(double) * need));
+    s->stage_cap = need;
+  }
+  if (!s->copy_stream) FG_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+  for (auto& e : s->ev) if (!e) FG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  // ev[b]: copies into buffer b done; ev[2+b]: compute on buffer b done
+  FG_CUDA(cudaEventRecord(s->ev[2], st));
+  FG_CUDA(cudaEventRecord(s->ev[3], st));
+  int b = 0;
+  for (int64_t i0 = 0; i0 < N; i0 += chunk, b ^= 1) {
+    const int64_t n = std::min(chunk, N - i0);
+    double* base = s->d_stage + (int64_t)b * chunk * per_sample;
+    double* dq = base;
+    double* dv = dq + chunk * m->nq;
+    double* da = dv + chunk * m->nv;
+    double* dt = da + chunk * m->nv;
+    FG_CUDA(cudaStreamWaitEvent(s->copy_stream, s->ev[2 + b], 0));
+    FG_CUDA(cudaMemcpyAsync(dq, q + i0 * m->nq, sizeof(double) * n * m->nq, cudaMemcpyHostToDevice, s->copy_stream));
+    FG_CUDA(cudaMemcpyAsync(dv, v + i0 * m->nv, sizeof(double) * n * m->nv, cudaMemcpyHostToDevice, s->copy_stream));
+    FG_CUDA(cudaMemcpyAsync(da, a + i0 * m->nv, sizeof(double) * n * m->nv, cudaMemcpyHostToDevice, s->copy_stream));
+    if (tau)
+      FG_CUDA(cudaMemcpy2DAsync(dt, sizeof(double) * chunk, tau + i0, sizeof(double) * ld_tau, sizeof(double) * n, ms,
+                                cudaMemcpyHostToDevice, s->copy_stream));
+    FG_CUDA(cudaEventRecord(s->ev[b], s->copy_stream));
+    FG_CUDA(cudaStreamWaitEvent(st, s->ev[b], 0));
+    rc = accumulate_samples_dev(s, m, cfg, dq, dv, da, tau ? dt : nullptr, chunk, n, st);
+    if (rc) return rc;
+    FG_CUDA(cudaEventRecord(s->ev[2 + b], st));
+  }
+  return FG_OK;
+}
+
+// ---- export / merge (multi-GPU exchange)
+extern "C" int fg_state_export(const fg_state* s, double* packed, void* stream) {
+  if (!s || !packed) return set_err(FG_ERR_INVALID, "fg_state_export: null argument");
+  tri_to_dense_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(s->d_part, s->p1, packed, (double)s->rows);
+  FG_CUDA(cudaGetLastError());
+  FG_LAUNCHED();
+  return FG_OK;
+}
+
+extern "C" int fg_state_merge_packed(fg_state* s, const double* packed, int32_t n, void* stream) {
+  if (!s || !packed || n < 1) return set_err(FG_ERR_INVALID, "fg_state_merge_packed: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int sm_count, max_smem;
+  int rc = device_limits(&sm_count, &max_smem);
+  if (rc) return rc;
+  rc = ensure_parts(s, n + 1);
+  if (rc) return rc;
+  dense_to_tri_kernel<<<dim3(16, n), 256, 0, st>>>(packed, n, s->p1, s->d_parts);
+  FG_CUDA(cudaGetLastError());
+  FG_LAUNCHED();
+  // row counts travel in the last packed double
+  const int64_t pk = fg_state_packed_doubles(s->p);
+  std::vector<double> cnt(n);
+  FG_CUDA(cudaMemcpy2DAsync(cnt.data(), sizeof(double), packed + pk - 1, sizeof(double) * pk, sizeof(double), n,
+                            cudaMemcpyDeviceToHost, st));
+  FG_CUDA(cudaStreamSynchronize(st));
+  rc = merge_parts_into_state(s, n, max_smem, st);
+  if (rc) return rc;
+  for (double c : cnt) s->rows += (int64_t)c;
+  return FG_OK;
+}
+
+// ------------------------------------------------------------------------------------ small stage
+extern "C" int fg_state_colsq(fg_state* s, double* out, void* stream) {
+  if (!s || !out) return set_err(FG_ERR_INVALID, "fg_state_colsq: null argument");
+  const int ntri = s->p1 * (s->p1 + 1) / 2;
+  FG_CUDA(cudaMemcpyAsync(out, s->d_part + ntri, sizeof(double) * s->p1, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  FG_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return FG_OK;
+}
+
+static int run_small_qr(double* A, int mrows, int n, const int* d_ext, cudaStream_t st) {
+  int sm_count, max_smem;
+  int rc = device_limits(&sm_count, &max_smem);
+  if (rc) return rc;
+  int smem = (mrows * n + n) * 8, use_smem = 1;
+  if (smem > max_smem) { smem = n * 8; use_smem = 0; }
+  FG_CUDA(cudaFuncSetAttribute(small_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int threads = n <= 128 ? 128 : (n <= 256 ? 256 : 512);
+  small_qr_kernel<<<1, threads, smem, st>>>(A, mrows, n, d_ext, use_smem);
+  FG_CUDA(cudaGetLastError());
+  FG_LAUNCHED();
+  return FG_OK;
+}
+
+extern "C" int fg_state_reduce(fg_state* s, const int32_t* keep, int32_t nk, double* diag, void* stream) {
+  if (!s || !keep || nk < 1 || nk > s->p || !diag) return set_err(FG_ERR_INVALID, "fg_state_reduce: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int p1 = s->p1, n = nk + 1;
+  std::vector<int> idx(2 * n);
+  for (int j = 0; j < nk; ++j) {
+    if (keep[j] < 0 || keep[j] >= s->p || (j > 0 && keep[j] <= keep[j - 1]))
+      return set_err(FG_ERR_INVALID, "fg_state_reduce: keep must be ascending indices in [0,%d)", s->p);
+    idx[j] = keep[j];
+    idx[n + j] = keep[j] + 1;
+  }
+  idx[nk] = s->p;       // rhs column
+  idx[n + nk] = p1;
+  FG_CUDA(cudaMemcpyAsync(s->d_idx, idx.data(), sizeof(int) * 2 * n, cudaMemcpyHostToDevice, st));
+  gather_cols_kernel<<<64, 256, 0, st>>>(s->d_part, p1, 1, s->d_idx, p1, n, s->d_A);
+  FG_CUDA(cudaGetLastError());
+  FG_LAUNCHED();
+  int rc = run_small_qr(s->d_A, p1, n, s->d_idx + n, st);
+  if (rc) return rc;
+  // keep the leading n x n block as the reduced factor (dense, ld = n)
+  FG_CUDA(cudaMemcpyAsync(s->d_Re, s->d_A, sizeof(double) * n * n, cudaMemcpyDeviceToDevice, st));
+  std::vector<double> Rh((size_t)n * n);
+  FG_CUDA(cudaMemcpyAsync(Rh.data(), s->d_Re, sizeof(double) * n * n, cudaMemcpyDeviceToHost, st));
+  FG_CUDA(cudaStreamSynchronize(st));
+  for (int j = 0; j < n; ++j) diag[j] = std::abs(Rh[(size_t)j * n + j]);
+  s->nk = nk;
+  s->keep.assign(keep, keep + nk);
+  return FG_OK;
+}
+
+extern "C" int fg_state_regroup_solve(fg_state* s, const int32_t* base, int32_t nb, const int32_t* regroup, int32_t ng,
+                                      double* beta, double* phi, double* R1, double* resid2, void* stream) {
+  if (!s || s->nk < 0) return set_err(FG_ERR_INVALID, "fg_state_regroup_solve: call fg_state_reduce first");
+  if (nb < 1 || nb + ng != s->nk || !base || (ng > 0 && !regroup))
+    return set_err(FG_ERR_INVALID, "fg_state_regroup_solve: base (%d) + regroup (%d) must cover the %d kept columns", nb, ng, s->nk);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = s->nk + 1;
+  std::vector<int> idx(2 * n);
+  std::vector<char> seen(s->nk, 0);
+  for (int j = 0; j < nb + ng; ++j) {
+    const int c = j < nb ? base[j] : regroup[j - nb];
+    if (c < 0 || c >= s->nk || seen[c]) return set_err(FG_ERR_INVALID, "fg_state_regroup_solve: bad column index %d", c);
+    seen[c] = 1;
+    idx[j] = c;
+    idx[n + j] = c + 1;
+  }
+  idx[n - 1] = s->nk;
+  idx[2 * n - 1] = n;
+  FG_CUDA(cudaMemcpyAsync(s->d_idx, idx.data(), sizeof(int) * 2 * n, cudaMemcpyHostToDevice, st));
+  gather_cols_kernel<<<64, 256, 0, st>>>(s->d_Re, n, 0, s->d_idx, n, n, s->d_A);
+  FG_CUDA(cudaGetLastError());
+  FG_LAUNCHED();
+  int rc = run_small_qr(s->d_A, n, n, s->d_idx + n, st);
+  if (rc) return rc;
+  const int nrhs = ng + 1;
+  upper_solve_kernel<<<(nrhs + 63) / 64, 64, 0, st>>>(s->d_A, n, nb, nrhs, s->d_X);
+  FG_CUDA(cudaGetLastError());
+  FG_LAUNCHED();
+  std::vector<double> X((size_t)nb * nrhs), Rg((size_t)n * n);
+  FG_CUDA(cudaMemcpyAsync(X.data(), s->d_X, sizeof(double) * nb * nrhs, cudaMemcpyDeviceToHost, st));
+  FG_CUDA(cudaMemcpyAsync(Rg.data(), s->d_A, sizeof(double) * n * n, cudaMemcpyDeviceToHost, st));
+  FG_CUDA(cudaStreamSynchronize(st));
+  for (int i = 0; i < nb; ++i) {
+    if (beta) for (int j = 0; j < ng; ++j) beta[(size_t)i * ng + j] = X[(size_t)i * nrhs + j];
+    if (phi) phi[i] = X[(size_t)i * nrhs + ng];
+    if (R1) for (int j = 0; j < nb; ++j) R1[(size_t)i * nb + j] = Rg[(size_t)i * n + j];
+  }
+  if (resid2) {
+    double r2 = 0.0;
+    for (int i = nb; i < n; ++i) r2 += Rg[(size_t)i * n + (n - 1)] * Rg[(size_t)i * n + (n - 1)];
+    *resid2 = r2;
+  }
+  return FG_OK;
+}

@@ -1,0 +1,474 @@
+// fg_kernels.cuh - the __global__ kernels of the identification path (sm_100a, fp64).
+//
+//   regressor_materialize_kernel : kernel (1) alone, W written to HBM in the reference layout
+//   accumulate_samples_kernel    : kernel (1) fused into the TSQR fold (W never leaves registers)
+//   accumulate_dense_kernel      : TSQR fold of a dense matrix already in HBM
+//   merge_pairs_kernel           : pairwise merge of partial R factors (tree reduction step)
+//   small_qr_kernel / solve      : kernel (3), the N-independent stage on the (p+1)^2 factor
+#pragma once
+#include "fg_device.cuh"
+
+namespace fg {
+
+// ------------------------------------------------------------------ shared memory carving
+struct SmemLayout {
+  int off_plan, off_joints, off_rows, off_nact, off_warp0;  // byte offsets
+  int warp_stride;                                          // bytes per warp
+  int w_R, w_fw, w_vs, w_as, w_xs;                          // byte offsets inside a warp block
+  int total;
+};
+
+__host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
+
+__host__ __device__ inline SmemLayout make_layout(int nj, int ms, int p1, int nv, int S, int TR, int nwarps,
+                                                  bool R_in_smem, bool need_fw) {
+  SmemLayout L;
+  int o = 0;
+  L.off_plan = o;   o = align16(o + (int)sizeof(Plan));
+  L.off_joints = o; o = align16(o + nj * (int)sizeof(DevJoint));
+  L.off_rows = o;   o = align16(o + ms * (int)sizeof(RowDesc));
+  L.off_nact = o;   o = align16(o + p1 * (int)sizeof(int));
+  L.off_warp0 = o;
+  int w = 0;
+  L.w_R = w;  w = align16(w + (R_in_smem ? (p1 * (p1 + 1) / 2) * 8 : 0));
+  L.w_fw = w; w = align16(w + (need_fw ? S * nj * FW_STRIDE * 8 : 0));
+  L.w_vs = w; w = align16(w + (need_fw ? S * nv * 8 : 0));
+  L.w_as = w; w = align16(w + (need_fw ? S * nv * 8 : 0));
+  L.w_xs = w; w = align16(w + 2 * (TR + 2) * 8);
+  L.warp_stride = w;
+  L.total = o + nwarps * w;
+  return L;
+}
+
+struct DevPlanPtrs {
+  const Plan* plan;
+  const DevJoint* joints;
+  const RowDesc* rows;
+  const ColDesc* cols;  // [p1] (last = rhs)
+  const int* nact;      // [p1]
+  const int* fullcol;   // [p1] full (reference) column index of each compact column, -1 for rhs
+};
+
+__device__ inline void load_plan_to_smem(unsigned char* smem, const SmemLayout& L, const DevPlanPtrs& pp) {
+  const Plan P = *pp.plan;
+  if (threadIdx.x == 0) *reinterpret_cast<Plan*>(smem + L.off_plan) = P;
+  DevJoint* J = reinterpret_cast<DevJoint*>(smem + L.off_joints);
+  for (int i = threadIdx.x; i < P.nj * (int)(sizeof(DevJoint) / 8); i += blockDim.x)
+    reinterpret_cast<double*>(J)[i] = reinterpret_cast<const double*>(pp.joints)[i];
+  RowDesc* Rw = reinterpret_cast<RowDesc*>(smem + L.off_rows);
+  for (int i = threadIdx.x; i < P.ms * (int)(sizeof(RowDesc) / 8); i += blockDim.x)
+    reinterpret_cast<double*>(Rw)[i] = reinterpret_cast<const double*>(pp.rows)[i];
+  int* na = reinterpret_cast<int*>(smem + L.off_nact);
+  for (int i = threadIdx.x; i < P.p1; i += blockDim.x) na[i] = pp.nact[i];
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------ kernel (1): materialise W
+// One warp handles S consecutive samples at a time: lanes 0..S-1 run the forward pass, then
+// every lane generates its own columns (lane + 32 t) and stores them; for a fixed row the 32
+// lanes write 32 consecutive doubles, so the stores are fully coalesced 256-byte segments.
+template <int MSMAX, int S>
+__global__ void __launch_bounds__(256) regressor_materialize_kernel(DevPlanPtrs pp, const double* __restrict__ q,
+                                                                    const double* __restrict__ qd,
+                                                                    const double* __restrict__ qdd, int64_t N,
+                                                                    double* __restrict__ W, int64_t ldw) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const Plan P0 = *pp.plan;
+  const int nwarps = blockDim.x / 32;
+  const SmemLayout L = make_layout(P0.nj, P0.ms, P0.p1, P0.nv, S, MSMAX * S, nwarps, false, true);
+  load_plan_to_smem(smem, L, pp);
+  const Plan& P = *reinterpret_cast<const Plan*>(smem + L.off_plan);
+  const DevJoint* J = reinterpret_cast<const DevJoint*>(smem + L.off_joints);
+  const RowDesc* rows = reinterpret_cast<const RowDesc*>(smem + L.off_rows);
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  unsigned char* wb = smem + L.off_warp0 + (size_t)warp * L.warp_stride;
+  double* fw = reinterpret_cast<double*>(wb + L.w_fw);
+  double* vs = reinterpret_cast<double*>(wb + L.w_vs);
+  double* as = reinterpret_cast<double*>(wb + L.w_as);
+  const int64_t ntiles = (N + S - 1) / S;
+  const int nslot = (P.ncols + 31) / 32;
+  for (int64_t tile = (int64_t)blockIdx.x * nwarps + warp; tile < ntiles; tile += (int64_t)gridDim.x * nwarps) {
+    const int64_t s0 = tile * S;
+    if (lane < S) {
+      const int64_t smp = s0 + lane;
+      const bool valid = smp < N;
+      const int64_t sc = valid ? smp : 0;
+      forward_sample(P, J, q + sc * P.nq, qd + sc * P.nv, qdd + sc * P.nv, fw + (size_t)lane * P.nj * FW_STRIDE,
+                     vs + lane * P.nv, as + lane * P.nv, valid);
+    }
+    __syncwarp();
+    for (int t = 0; t < nslot; ++t) {
+      const int col = lane + 32 * t;
+      ColDesc cd;
+      cd.kind = COL_ZERO; cd.body = 0; cd.k = 0; cd.vidx = 0; cd.grp = -2;
+      uint64_t anc = 0;
+      if (col < P.ncols) {
+        cd = pp.cols[col];
+        anc = col_ancmask(cd);
+      }
+      double out[MSMAX * S];
+      gen_column<MSMAX, S>(P, J, rows, cd, anc, fw, vs, as, nullptr, 0, s0, N, out);
+      if (col < P.ncols) {
+        const int fc = pp.fullcol[col];
+#pragma unroll
+        for (int g = 0; g < MSMAX; ++g) {
+          if (g < P.ms) {
+            const int64_t rb = rows[g].rowblock;
+#pragma unroll
+            for (int s = 0; s < S; ++s)
+              if (s0 + s < N) W[(rb * N + s0 + s) * ldw + fc] = out[g * S + s];
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------ partial factors in HBM
+// A "part" is one packed upper-triangular factor (p1 columns) plus p1 squared column norms.
+__host__ __device__ inline int64_t part_doubles(int p1) { return (int64_t)p1 * (p1 + 1) / 2 + p1; }
+
+// Fold the rows of packed factor `src` (p1 columns) into `dst` (packed).  One warp.
+template <int NSLOT, int TR>
+__device__ __forceinline__ void fold_factor(const double* src, double* dst, int p1, double* xs, int lane) {
+  for (int r0 = 0; r0 < p1; r0 += TR) {
+    double B[TR][NSLOT];
+#pragma unroll
+    for (int r = 0; r < TR; ++r) {
+      const int row = r0 + r;
+#pragma unroll
+      for (int t = 0; t < NSLOT; ++t) {
+        const int col = lane + 32 * t;
+        B[r][t] = (row < p1 && col >= row && col < p1) ? src[tri_off(row, p1) + col - row] : 0.0;
+      }
+    }
+    fold_tile<NSLOT, TR, TR>(B, dst, p1, xs, nullptr, r0, lane);
+    __syncwarp();
+  }
+}
+
+// End-of-kernel reduction of the per-warp factors of one CTA, then store to part[blockIdx.x].
+template <int NSLOT, int TR>
+__device__ __forceinline__ void cta_merge_and_store(double* myR, double* (*warpR)(int, void*), void* ctx,
+                                                    const double (&csq)[NSLOT], double* csq_smem /*[nwarps][32*NSLOT]*/,
+                                                    int p1, double* xs, double* parts, int lane, int warp, int nwarps) {
+  // squared column norms: fixed-order sum over warps
+#pragma unroll
+  for (int t = 0; t < NSLOT; ++t) csq_smem[(size_t)warp * 32 * NSLOT + 32 * t + lane] = csq[t];
+  __syncthreads();
+  for (int step = 1; step < nwarps; step *= 2) {
+    if ((warp % (2 * step)) == 0 && warp + step < nwarps) fold_factor<NSLOT, TR>(warpR(warp + step, ctx), myR, p1, xs, lane);
+    __syncthreads();
+  }
+  if (warp == 0) {
+    double* out = parts + (size_t)blockIdx.x * part_doubles(p1);
+    const int ntri = p1 * (p1 + 1) / 2;
+    for (int i = lane; i < ntri; i += 32) out[i] = myR[i];
+#pragma unroll
+    for (int t = 0; t < NSLOT; ++t) {
+      const int col = lane + 32 * t;
+      if (col < p1) {
+        double sacc = 0.0;
+        for (int w = 0; w < nwarps; ++w) sacc += csq_smem[(size_t)w * 32 * NSLOT + 32 * t + lane];
+        out[ntri + col] = sacc;
+      }
+    }
+  }
+}
+
+struct WarpRCtx {
+  unsigned char* base;  // smem or global base of warp 0's factor
+  size_t stride;        // bytes between consecutive warps' factors
+};
+__device__ inline double* warpR_fn(int w, void* ctx) {
+  WarpRCtx* c = reinterpret_cast<WarpRCtx*>(ctx);
+  return reinterpret_cast<double*>(c->base + (size_t)w * c->stride);
+}
+
+// ------------------------------------------------------------------ kernel (1)+(2) fused
+// Persistent grid, one warp = one TSQR stream.  Per tile of S samples:
+//   lanes 0..S-1: forward kinematics into shared memory;
+//   all lanes:    generate the entries of their own columns straight into registers
+//                 (B[row][slot]), accumulate exact column norms, Householder-fold into the
+//                 stream's packed R (shared memory when it fits, else an HBM scratch slot).
+// At the end the CTA's streams are merged and written to parts[blockIdx.x].
+template <int NSLOT, int MS, int S>
+__global__ void __launch_bounds__(256, 1)
+accumulate_samples_kernel(DevPlanPtrs pp, const double* __restrict__ q, const double* __restrict__ qd,
+                          const double* __restrict__ qdd, const double* __restrict__ tau, int64_t ld_tau, int64_t N,
+                          double* __restrict__ parts, double* __restrict__ gR /* global R slots or null */,
+                          int use_structure) {
+  constexpr int TR = MS * S;
+  constexpr int TRM = TR >= 8 ? TR : 8;  // tile height used by the factor merges
+  extern __shared__ __align__(16) unsigned char smem[];
+  const Plan P0 = *pp.plan;
+  const int nwarps = blockDim.x / 32;
+  const bool R_in_smem = gR == nullptr;
+  const SmemLayout L = make_layout(P0.nj, P0.ms, P0.p1, P0.nv, S, TRM, nwarps, R_in_smem, true);
+  load_plan_to_smem(smem, L, pp);
+  const Plan& P = *reinterpret_cast<const Plan*>(smem + L.off_plan);
+  const DevJoint* J = reinterpret_cast<const DevJoint*>(smem + L.off_joints);
+  const RowDesc* rows = reinterpret_cast<const RowDesc*>(smem + L.off_rows);
+  const int* nact = use_structure ? reinterpret_cast<const int*>(smem + L.off_nact) : nullptr;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  unsigned char* wb = smem + L.off_warp0 + (size_t)warp * L.warp_stride;
+  double* fw = reinterpret_cast<double*>(wb + L.w_fw);
+  double* vs = reinterpret_cast<double*>(wb + L.w_vs);
+  double* as = reinterpret_cast<double*>(wb + L.w_as);
+  double* xs = reinterpret_cast<double*>(wb + L.w_xs);
+  const int p1 = P.p1;
+  const int ntri = p1 * (p1 + 1) / 2;
+  const size_t gstride = (size_t)ntri * 8;
+  double* Rt = R_in_smem ? reinterpret_cast<double*>(wb + L.w_R)
+                         : gR + ((size_t)blockIdx.x * nwarps + warp) * ntri;
+  for (int i = lane; i < ntri; i += 32) Rt[i] = 0.0;
+
+  ColDesc cd[NSLOT];
+  uint64_t anc[NSLOT];
+  double csq[NSLOT];
+#pragma unroll
+  for (int t = 0; t < NSLOT; ++t) {
+    const int col = lane + 32 * t;
+    cd[t].kind = COL_ZERO; cd[t].body = 0; cd[t].k = 0; cd[t].vidx = 0; cd[t].grp = -2;
+    anc[t] = 0;
+    csq[t] = 0.0;
+    if (col < p1) {
+      cd[t] = pp.cols[col];
+      anc[t] = col_ancmask(cd[t]);
+    }
+  }
+  __syncwarp();
+
+  const int64_t ntiles = (N + S - 1) / S;
+  for (int64_t tile = (int64_t)blockIdx.x * nwarps + warp; tile < ntiles; tile += (int64_t)gridDim.x * nwarps) {
+    const int64_t s0 = tile * S;
+    if (lane < S) {
+      const int64_t smp = s0 + lane;
+      const bool valid = smp < N;
+      const int64_t sc = valid ? smp : 0;
+      forward_sample(P, J, q + sc * P.nq, qd + sc * P.nv, qdd + sc * P.nv, fw + (size_t)lane * P.nj * FW_STRIDE,
+                     vs + lane * P.nv, as + lane * P.nv, valid);
+    }
+    __syncwarp();
+    double B[TR][NSLOT];
+#pragma unroll
+    for (int t = 0; t < NSLOT; ++t) {
+      double out[TR];
+      gen_column<MS, S>(P, J, rows, cd[t], anc[t], fw, vs, as, tau, ld_tau, s0, N, out);
+#pragma unroll
+      for (int r = 0; r < TR; ++r) {
+        B[r][t] = out[r];
+        csq[t] = fma(out[r], out[r], csq[t]);
+      }
+    }
+    __syncwarp();
+    fold_tile<NSLOT, TR, S>(B, Rt, p1, xs, nact, 0, lane);
+    __syncwarp();
+  }
+
+  // ---- CTA-level merge of the warp streams
+  __shared__ double csq_buf[8 * 32 * NSLOT];
+  WarpRCtx ctx;
+  if (R_in_smem) { ctx.base = smem + L.off_warp0 + L.w_R; ctx.stride = (size_t)L.warp_stride; }
+  else { ctx.base = reinterpret_cast<unsigned char*>(gR + (size_t)blockIdx.x * nwarps * ntri); ctx.stride = gstride; }
+  __threadfence_block();
+  cta_merge_and_store<NSLOT, TRM>(Rt, warpR_fn, &ctx, csq, csq_buf, p1, xs, parts, lane, warp, nwarps);
+}
+
+// ------------------------------------------------------------------ dense TSQR fold
+// W is rows x p (ld = ldw) in HBM, tau optional.  Each warp streams tiles of TR rows:
+// B[r][t] = W[row0 + r][lane + 32 t] (coalesced), last column = tau.
+template <int NSLOT, int TR>
+__global__ void __launch_bounds__(256, 1)
+accumulate_dense_kernel(const double* __restrict__ W, int64_t ldw, const double* __restrict__ tau, int64_t nrows,
+                        int p1, double* __restrict__ parts, double* __restrict__ gR) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int nwarps = blockDim.x / 32;
+  const bool R_in_smem = gR == nullptr;
+  const int ntri = p1 * (p1 + 1) / 2;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int xs_bytes = align16(2 * (TR + 2) * 8);
+  const int r_bytes = R_in_smem ? align16(ntri * 8) : 0;
+  const int wstride = xs_bytes + r_bytes;
+  unsigned char* wb = smem + (size_t)warp * wstride;
+  double* xs = reinterpret_cast<double*>(wb);
+  double* Rt = R_in_smem ? reinterpret_cast<double*>(wb + xs_bytes) : gR + ((size_t)blockIdx.x * nwarps + warp) * ntri;
+  for (int i = lane; i < ntri; i += 32) Rt[i] = 0.0;
+  double csq[NSLOT];
+#pragma unroll
+  for (int t = 0; t < NSLOT; ++t) csq[t] = 0.0;
+  __syncwarp();
+  const int p = p1 - 1;
+  const int64_t ntiles = (nrows + TR - 1) / TR;
+  for (int64_t tile = (int64_t)blockIdx.x * nwarps + warp; tile < ntiles; tile += (int64_t)gridDim.x * nwarps) {
+    const int64_t r0 = tile * TR;
+    double B[TR][NSLOT];
+#pragma unroll
+    for (int r = 0; r < TR; ++r) {
+      const int64_t row = r0 + r;
+#pragma unroll
+      for (int t = 0; t < NSLOT; ++t) {
+        const int col = lane + 32 * t;
+        double val = 0.0;
+        if (row < nrows) {
+          if (col < p) val = W[row * ldw + col];
+          else if (col == p && tau != nullptr) val = tau[row];
+        }
+        B[r][t] = val;
+        csq[t] = fma(val, val, csq[t]);
+      }
+    }
+    fold_tile<NSLOT, TR, TR>(B, Rt, p1, xs, nullptr, 0, lane);
+    __syncwarp();
+  }
+  __shared__ double csq_buf[8 * 32 * NSLOT];
+  WarpRCtx ctx;
+  if (R_in_smem) { ctx.base = smem + xs_bytes; ctx.stride = (size_t)wstride; }
+  else { ctx.base = reinterpret_cast<unsigned char*>(gR + (size_t)blockIdx.x * nwarps * ntri); ctx.stride = (size_t)ntri * 8; }
+  __threadfence_block();
+  cta_merge_and_store<NSLOT, TR>(Rt, warpR_fn, &ctx, csq, csq_buf, p1, xs, parts, lane, warp, nwarps);
+}
+
+// ------------------------------------------------------------------ pairwise merge of parts
+// CTA b (one warp) merges part[(2b+1)*stride] into part[2b*stride] (if it exists).
+template <int NSLOT, int TR>
+__global__ void __launch_bounds__(32) merge_pairs_kernel(double* __restrict__ parts, int nparts, int stride, int p1,
+                                                         int use_smem) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int lane = threadIdx.x;
+  const int a = 2 * blockIdx.x * stride, b = a + stride;
+  if (b >= nparts) return;
+  const int ntri = p1 * (p1 + 1) / 2;
+  double* pa = parts + (size_t)a * part_doubles(p1);
+  double* pb = parts + (size_t)b * part_doubles(p1);
+  double* xs = reinterpret_cast<double*>(smem);
+  double* Rt = pa;
+  if (use_smem) {
+    Rt = reinterpret_cast<double*>(smem + align16(2 * (TR + 2) * 8));
+    for (int i = lane; i < ntri; i += 32) Rt[i] = pa[i];
+    __syncwarp();
+  }
+  fold_factor<NSLOT, TR>(pb, Rt, p1, xs, lane);
+  if (use_smem) {
+    __syncwarp();
+    for (int i = lane; i < ntri; i += 32) pa[i] = Rt[i];
+  }
+  for (int i = lane; i < p1; i += 32) pa[ntri + i] += pb[ntri + i];
+}
+
+// ------------------------------------------------------------------ packing helpers
+__global__ void tri_to_dense_kernel(const double* __restrict__ part, int p1, double* __restrict__ dense,
+                                    double nrows_as_double) {
+  const int ntri = p1 * (p1 + 1) / 2;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < p1 * p1; idx += gridDim.x * blockDim.x) {
+    const int r = idx / p1, c = idx % p1;
+    dense[idx] = c >= r ? part[tri_off(r, p1) + c - r] : 0.0;
+  }
+  if (blockIdx.x == 0) {
+    for (int i = threadIdx.x; i < p1; i += blockDim.x) dense[(size_t)p1 * p1 + i] = part[ntri + i];
+    if (threadIdx.x == 0) dense[(size_t)p1 * p1 + p1] = nrows_as_double;
+  }
+}
+
+// packed exchange buffers (dense square + norms + rows) -> parts (packed triangles)
+__global__ void dense_to_tri_kernel(const double* __restrict__ packed, int n, int p1, double* __restrict__ parts) {
+  const int ntri = p1 * (p1 + 1) / 2;
+  const int64_t pk = (int64_t)p1 * p1 + p1 + 1;
+  for (int k = blockIdx.y; k < n; k += gridDim.y) {
+    const double* src = packed + (size_t)k * pk;
+    double* dst = parts + (size_t)k * part_doubles(p1);
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < p1 * p1; idx += gridDim.x * blockDim.x) {
+      const int r = idx / p1, c = idx % p1;
+      if (c >= r) dst[tri_off(r, p1) + c - r] = src[idx];
+    }
+    if (blockIdx.x == 0)
+      for (int i = threadIdx.x; i < p1; i += blockDim.x) dst[ntri + i] = src[(size_t)p1 * p1 + i];
+  }
+}
+
+// ------------------------------------------------------------------ kernel (3): small stage
+// A (m rows x n cols, row-major, ld = n) = selected columns of an upper-triangular factor.
+// gather: A[r][j] = (r <= src_col[j]) ? Rsrc[r][src_col[j]] : 0, Rsrc either packed (tri) or dense.
+__global__ void gather_cols_kernel(const double* __restrict__ Rsrc, int src_p1, int src_is_tri,
+                                   const int* __restrict__ src_col, int m, int n, double* __restrict__ A) {
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < m * n; idx += gridDim.x * blockDim.x) {
+    const int r = idx / n, j = idx % n;
+    const int c = src_col[j];
+    double v = 0.0;
+    if (r <= c) v = src_is_tri ? Rsrc[tri_off(r, src_p1) + c - r] : Rsrc[(size_t)r * src_p1 + c];
+    A[idx] = v;
+  }
+}
+
+// In-place Householder QR of the m x n matrix A (row-major, ld = n), single CTA.
+// ext[j] = 1 + last possibly non-zero row of column j on entry.  Column c's reflector spans
+// rows c .. E_c-1 with E_c = max(ext[0..c]) (fill-in of earlier reflectors).  On exit the
+// upper triangle of A holds R (first min(m,n) rows); entries below the diagonal are zeroed.
+// The matrix is staged in shared memory when `use_smem` (m*n*8 bytes + n*8).
+__global__ void __launch_bounds__(1024) small_qr_kernel(double* __restrict__ Ag, int m, int n,
+                                                        const int* __restrict__ ext, int use_smem) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  double* A = Ag;
+  double* dg;
+  if (use_smem) {
+    A = reinterpret_cast<double*>(smem);
+    dg = A + (size_t)m * n;
+    for (int i = threadIdx.x; i < m * n; i += blockDim.x) A[i] = Ag[i];
+  } else {
+    dg = reinterpret_cast<double*>(smem);
+  }
+  __syncthreads();
+  const int kmax = m < n ? m : n;
+  int E = 0;
+  for (int c = 0; c < kmax; ++c) {
+    const int e = ext[c] < m ? ext[c] : m;
+    E = e > E ? e : E;
+    if (E < c + 1) E = c + 1;
+    const double alpha = A[(size_t)c * n + c];
+    double sigma = 0.0;
+    for (int r = c + 1; r < E; ++r) { const double x = A[(size_t)r * n + c]; sigma = fma(x, x, sigma); }
+    if (sigma == 0.0) {
+      if (threadIdx.x == 0) dg[c] = alpha;
+      continue;  // uniform: every thread computed the same sigma
+    }
+    const double nrm = sqrt(fma(alpha, alpha, sigma));
+    const double beta = alpha >= 0.0 ? -nrm : nrm;
+    const double inv = 1.0 / (alpha - beta);
+    const double tauh = (beta - alpha) / beta;
+    for (int j = c + 1 + threadIdx.x; j < n; j += blockDim.x) {
+      double d = 0.0;
+      for (int r = c + 1; r < E; ++r) d = fma(A[(size_t)r * n + c], A[(size_t)r * n + j], d);
+      const double rho = A[(size_t)c * n + j];
+      const double sdot = fma(d, inv, rho);
+      A[(size_t)c * n + j] = fma(-tauh, sdot, rho);
+      const double g = tauh * sdot * inv;
+      for (int r = c + 1; r < E; ++r) A[(size_t)r * n + j] = fma(-g, A[(size_t)r * n + c], A[(size_t)r * n + j]);
+    }
+    if (threadIdx.x == 0) dg[c] = beta;
+    __syncthreads();
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < m * n; i += blockDim.x) {
+    const int r = i / n, c = i % n;
+    double v = A[i];
+    if (r > c) v = 0.0;
+    else if (r == c && r < kmax) v = dg[r];
+    Ag[i] = v;
+  }
+}
+
+// Back substitution on the regrouped factor Rg ((nk+1) x (nk+1) dense, ld = ldr):
+//   X[:, j] = R1^-1 Rg[0:r, r + j]  for j in [0, nrhs)   (nrhs = n_regroup + 1, last = rhs)
+// X is r x nrhs row-major.  One thread per right-hand side.
+__global__ void upper_solve_kernel(const double* __restrict__ Rg, int ldr, int r, int nrhs, double* __restrict__ X) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nrhs) return;
+  for (int i = r - 1; i >= 0; --i) {
+    double acc = Rg[(size_t)i * ldr + r + j];
+    for (int k = i + 1; k < r; ++k) acc = fma(-Rg[(size_t)i * ldr + k], X[(size_t)k * nrhs + j], acc);
+    X[(size_t)i * nrhs + j] = acc / Rg[(size_t)i * ldr + i];
+  }
+}
+
+}  // namespace fg

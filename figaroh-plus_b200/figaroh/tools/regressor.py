@@ -1,0 +1,108 @@
+"""figaroh.tools.regressor drop-in (B200).
+
+Same functions, arguments and return values as
+/root/reference/src/figaroh/tools/regressor.py; the arithmetic runs in the CUDA library
+(kernel (1): batched joint-torque regressor; kernel (2): TSQR state for column norms).
+
+Inputs may be numpy arrays (results come back as fresh float64 C-contiguous numpy
+arrays, like the reference) or CUDA tensors / DeviceMatrix handles (results stay in
+HBM as DeviceMatrix, so a whole pipeline can run without the tall matrix crossing PCIe).
+Set ``figaroh.tools.regressor.RETURN_DEVICE = True`` to get DeviceMatrix results from
+numpy inputs as well.
+"""
+import numpy as np
+import torch
+
+from figaroh_b200 import engine as _eng
+from figaroh_b200._lib import FgError
+
+RETURN_DEVICE = False
+
+
+def _device_model(robot):
+    model = robot.model
+    dm = getattr(model, "_fg_device_model", None)
+    if dm is None:
+        dm = _eng.DeviceModel(model)
+        try:
+            model._fg_device_model = dm
+        except Exception:  # noqa: BLE001 - e.g. a pinocchio Model without __dict__
+            pass
+    return dm
+
+
+def _on_device(x):
+    return isinstance(x, _eng.DeviceMatrix) or (isinstance(x, torch.Tensor) and x.is_cuda)
+
+
+def _wrap(t, like_device):
+    if like_device or RETURN_DEVICE:
+        return _eng.DeviceMatrix(t)
+    return t.cpu().numpy()
+
+
+def build_regressor_basic(robot, q, v, a, param, tau=None):
+    """Tall regressor of the standard parameters (reference: regressor.py:20-194).
+
+    Rows are joint-major (row j*N+i), columns follow get_standard_parameters.  `tau` is
+    accepted and ignored, as in the reference."""
+    N = len(q)
+    # evaluated by the reference too (regressor.py:36-39); keeps duck-typed models honest
+    _ = [jj for jj in range(len(robot.model.inertias.tolist())) if robot.model.inertias.tolist()[jj].mass != 0]
+    cfg = _eng.RegressorConfig.from_param(param)
+    dm = _device_model(robot)
+    try:
+        W = dm.materialize(cfg, q, v, a)
+    except FgError as e:
+        if e.code == -2:  # what numpy raises in the reference for free-flyer models in joint-torque mode
+            raise ValueError(str(e)) from None
+        raise
+    assert W.shape[0] % max(N, 1) == 0
+    return _wrap(W, _on_device(q))
+
+
+def add_coupling_TX40(W, model, data, N, nq, nv, njoints, q, v, a):
+    """Append the Iam6 / fvm6 / fsm6 wrist-coupling columns (reference: regressor.py:198-227)."""
+    dev = _on_device(W)
+    Wd = _eng.as_device(W)
+    vd, ad = _eng.as_device(v), _eng.as_device(a)
+    out = torch.zeros((Wd.shape[0], Wd.shape[1] + 3), dtype=torch.float64, device=Wd.device)
+    out[:, :-3] = Wd
+    sg = torch.sign(vd[:N, 4] + vd[:N, 5])
+    out[4 * N:5 * N, -3], out[4 * N:5 * N, -2], out[4 * N:5 * N, -1] = ad[:N, 5], vd[:N, 5], sg
+    out[5 * N:6 * N, -3], out[5 * N:6 * N, -2], out[5 * N:6 * N, -1] = ad[:N, 4], vd[:N, 4], sg
+    return _wrap(out, dev)
+
+
+def _column_sq_norms(W):
+    """diag(W^T W) (regressor.py:243,271) from the TSQR state of W."""
+    Wd = _eng.as_device(W)
+    st = _eng.TsqrState(Wd.shape[1]).accumulate_dense(Wd, None)
+    return st.colsq()[:Wd.shape[1]]
+
+
+def eliminate_non_dynaffect(W, params_std, tol_e=1e-6):
+    """Drop columns whose squared norm is below tol_e (reference: regressor.py:230-255)."""
+    idx_e, params_r = get_index_eliminate(W, params_std, tol_e)
+    return build_regressor_reduced(W, tuple(idx_e)), params_r
+
+
+def get_index_eliminate(W, params_std, tol_e=1e-6):
+    """Indices of columns with squared norm < tol_e and names of the others (regressor.py:258-279)."""
+    col_norm = _column_sq_norms(W)
+    names = list(params_std.keys())
+    idx_e, params_r = [], []
+    for i in range(col_norm.shape[0]):
+        if col_norm[i] < tol_e:
+            idx_e.append(i)
+        else:
+            params_r.append(names[i])
+    return idx_e, params_r
+
+
+def build_regressor_reduced(W, idx_e):
+    """W without the columns idx_e (reference: regressor.py:282-293)."""
+    if _on_device(W):
+        Wm = W if isinstance(W, _eng.DeviceMatrix) else _eng.DeviceMatrix(W)
+        return Wm.drop_columns(list(idx_e))
+    return np.delete(W, idx_e, 1)

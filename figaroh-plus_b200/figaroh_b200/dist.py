@@ -1,0 +1,43 @@
+"""Multi-GPU sharding of the identification path.
+
+Samples are independent rows, so each rank folds its own shard into a local TsqrState
+with no data-path communication.  The only exchange is ONE all-gather of the packed
+per-GPU state ((p+1)^2 + p + 2 doubles: 58 KB for UR10) over NCCL / NVLink, after which
+every rank merges the G factors in rank order with the same kernel - deterministic and
+identical on all ranks (R^T R of the merged factor equals the global [W|tau]^T [W|tau]).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from .engine import TsqrState
+
+
+def shard_range(n_total: int, rank: int, world: int):
+    """Contiguous shard [lo, hi) of rank `rank` (the first n_total % world ranks get one extra)."""
+    base, rem = divmod(n_total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def allgather_packed(packed: torch.Tensor, group=None) -> torch.Tensor:
+    """All-gather equal-sized packed states; works on CUDA (nccl) and CPU (gloo) tensors."""
+    world = dist.get_world_size(group)
+    out = torch.empty(world * packed.numel(), dtype=packed.dtype, device=packed.device)
+    dist.all_gather_into_tensor(out, packed.contiguous(), group=group)
+    return out
+
+
+def allgather_merge(local: TsqrState, merged: TsqrState | None = None, group=None) -> TsqrState:
+    """Global state from the per-rank states (one all-gather + a local merge on every rank)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    gathered = allgather_packed(local.export(), group)
+    if merged is None:
+        merged = TsqrState(local.p)
+    else:
+        merged.reset()
+    merged.merge_packed(gathered, world)
+    return merged

@@ -21,7 +21,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-# joint type codes shared with csrc/fg_model.h and oracle/fg_oracle.c
+# joint type codes (FG_JT_* in include/figaroh_b200.h)
 JT_NONE = 0          # universe
 JT_REVOLUTE = 1      # nq=1, nv=1, rotation about `axis` (any unit axis)
 JT_REVOLUTE_UNB = 2  # nq=2 (cos,sin), nv=1  - URDF "continuous"

@@ -83,34 +83,41 @@ def build_regressor_basic(om, q, v, a, param, per_sample=True):
         raise ValueError(f"could not broadcast input array from shape ({10 * nb},) into shape ({10 * nv},)")
     nblk = nv if mode == 0 else 6
     W = np.zeros((nblk * N, 14 * nb))
+    W3 = W.reshape(nblk, N, 14 * nb)              # W3[j, i, :] is row j*N+i of the reference layout
     body_cols = (14 * np.arange(nb)[:, None] + _PIN_TO_FIG[None, :]).reshape(-1)
     has_mass = om.mass[1:] != 0.0
     ew_cols = (14 * np.nonzero(has_mass)[0][:, None] + _PIN_TO_FIG[None, :]).reshape(-1)
     ew_src = (10 * np.nonzero(has_mass)[0][:, None] + np.arange(10)[None, :]).reshape(-1)
-    rows = np.arange(nblk) * N
+    sel = np.array([j for j in range(6) if (mask >> j) & 1], dtype=np.int64)
+    jj = np.arange(nv if mode == 0 else nb)
+    c_fv, c_fs, c_ia, c_off = 14 * jj + 11, 14 * jj + 12, 14 * jj + 10, 14 * jj + 13
+    Wt = np.empty((nv, 10 * nb))
+    call = kernels.lib().orc_joint_torque_regressor
+    mp, wp = om.ptr, Wt.ctypes.data
+    qp, vp, ap = q.ctypes.data, v.ctypes.data, a.ctypes.data
+    sq, sv = 8 * om.nq, 8 * nv
     for i in range(N):
-        Wt = kernels.joint_torque_regressor(om, q[i], v[i], a[i])
+        # one native call per sample, like pin.computeJointTorqueRegressor at regressor.py:49
+        call(mp, qp + i * sq, vp + i * sv, ap + i * sv, wp)
         if mode == 0:
-            W[np.ix_(rows + i, body_cols)] = Wt
-            jj = np.arange(nv)
+            W3[:, i, body_cols] = Wt
             if flags & 1:
-                W[rows + i, 14 * jj + 11] = v[i]
-                W[rows + i, 14 * jj + 12] = np.sign(v[i])
+                W3[jj, i, c_fv] = v[i]
+                W3[jj, i, c_fs] = np.sign(v[i])
             if flags & 2:
-                W[rows + i, 14 * jj + 10] = a[i]
+                W3[jj, i, c_ia] = a[i]
             if flags & 4:
-                W[rows + i, 14 * jj + 13] = 1.0
+                W3[jj, i, c_off] = 1.0
         else:
-            sel = [j for j in range(6) if (mask >> j) & 1]
-            W[np.ix_(rows[sel] + i, ew_cols)] = Wt[np.ix_(sel, ew_src)]
-            bb = np.arange(nb)
+            if len(sel):
+                W3[sel[:, None], i, ew_cols[None, :]] = Wt[np.ix_(sel, ew_src)]
             if flags & 1:
-                W[np.ix_(rows + i, 14 * bb + 11)] = v[i, :nb]
-                W[np.ix_(rows + i, 14 * bb + 12)] = np.sign(v[i, :nb])
+                W3[:, i, c_fv] = v[i, :nb]
+                W3[:, i, c_fs] = np.sign(v[i, :nb])
             if flags & 2:
-                W[np.ix_(rows + i, 14 * bb + 10)] = a[i, :nb]
+                W3[:, i, c_ia] = a[i, :nb]
             if flags & 4:
-                W[np.ix_(rows + i, 14 * bb + 13)] = 1.0
+                W3[:, i, c_off] = 1.0
     return W
 
 

@@ -1,0 +1,138 @@
+"""GPU: the figaroh.tools drop-in modules behave like the reference's (same call sequences
+as examples/ur10/identification.py:71-91, examples/tiago/identification.py:296-348 and
+examples/staubli_TX40/identification.py:89-100,237-240), checked against the oracle."""
+import json
+
+import numpy as np
+import pytest
+
+from conftest import TX40_PARAM, golden_path, load_flat, load_oracle_model, make_param, rand_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+class _Robot:
+    """What the scripts hold: an object with .model / .data (figaroh.tools.robot.Robot without a URDF)."""
+
+    def __init__(self, name):
+        from figaroh.tools.robot import Robot
+        from figaroh_b200.model import model_from_flat
+        self._r = Robot.__new__(Robot)
+        self._r.model = model_from_flat(load_flat(name))
+        self._r.data = self._r.model.createData()
+        self.model, self.data = self._r.model, self._r.data
+
+    def get_standard_parameters(self, param):
+        return self._r.get_standard_parameters(param)
+
+
+def test_ur10_structural_script_sequence():
+    from figaroh.tools.qrdecomposition import get_baseIndex, get_baseParams, build_baseRegressor, cond_num
+    from figaroh.tools.regressor import build_regressor_basic, build_regressor_reduced, get_index_eliminate
+    from oracle import ref_path
+    robot, om = _Robot("ur10"), load_oracle_model("ur10")
+    param = make_param(False, False, False)
+    q, v, a = rand_inputs(load_flat("ur10"), 1000, 4)
+    std = robot.get_standard_parameters(param)
+    W = build_regressor_basic(robot, q, v, a, param)
+    assert isinstance(W, np.ndarray) and W.dtype == np.float64 and W.flags.c_contiguous and W.shape == (6000, 84)
+    Wref = ref_path.build_regressor_basic(om, q, v, a, param, per_sample=False)
+    assert np.abs(W - Wref).max() <= 1e-9 * np.abs(Wref).max()
+    idx_e, params_r = get_index_eliminate(W, std, 1e-6)
+    assert (idx_e, params_r) == ref_path.get_index_eliminate(Wref, std, 1e-6)
+    W_e = build_regressor_reduced(W, idx_e)
+    assert W_e.shape == (6000, 49)
+    W_b, params_base, idx_base = get_baseParams(W_e, params_r, std)
+    rb = ref_path.get_baseParams(ref_path.build_regressor_reduced(Wref, idx_e), params_r, std)
+    assert params_base == rb[1] and idx_base == rb[2] and len(idx_base) == 36
+    assert np.allclose(W_b, rb[0])
+    assert get_baseIndex(W_e, params_r) == tuple(idx_base)
+    assert np.array_equal(build_baseRegressor(W_e, idx_base), W_e[:, idx_base])
+    c_ref = np.linalg.cond(W_b)
+    assert abs(cond_num(W_b) / c_ref - 1) < 1e-8
+    assert abs(cond_num(W_b, "max_over_min_sigma") / ref_path.cond_num(W_b, "max_over_min_sigma") - 1) < 1e-7
+    with pytest.raises(np.linalg.LinAlgError):
+        cond_num(W_b, "fro")
+    with pytest.raises(AssertionError):
+        get_baseIndex(W_e, params_r[:-1])
+
+
+def test_tx40_coupling_and_eliminate():
+    from figaroh.tools.qrdecomposition import double_QR
+    from figaroh.tools.regressor import add_coupling_TX40, build_regressor_basic, eliminate_non_dynaffect
+    from oracle import ref_path
+    robot, om = _Robot("tx40"), load_oracle_model("tx40")
+    param = dict(TX40_PARAM)
+    N = 800
+    q, v, a = rand_inputs(load_flat("tx40"), N, 6, ((-6, 6), (-10, 10), (-30, 30)))
+    std = robot.get_standard_parameters(param)
+    std.update(Iam6=param["Iam6"], fvm6=param["fvm6"], fsm6=param["fsm6"])
+    W = build_regressor_basic(robot, q, v, a, param)
+    W = add_coupling_TX40(W, robot.model, robot.data, N, 6, 6, 7, q, v, a)
+    Wref = ref_path.add_coupling_TX40(ref_path.build_regressor_basic(om, q, v, a, param, per_sample=False), N, v, a)
+    assert W.shape == (6 * N, 87) and np.abs(W - Wref).max() <= 1e-9 * np.abs(Wref).max()
+    rng = np.random.default_rng(0)
+    tau = Wref @ np.array(list(std.values()), float) + rng.normal(0, 0.05, 6 * N)
+    W_e, params_r = eliminate_non_dynaffect(W, std, 1e-6)
+    W_e_ref, params_r_ref = ref_path.eliminate_non_dynaffect(Wref, std, 1e-6)
+    assert params_r == params_r_ref and W_e.shape == W_e_ref.shape
+    out = double_QR(tau, W_e, params_r, std)
+    ref = ref_path.double_QR(tau, W_e_ref, params_r_ref, std)
+    assert len(out) == 5 and out[2] == ref[2] and len(out[2]) == 61
+    assert list(out[1].keys()) == list(ref[1].keys())
+    np.testing.assert_allclose(out[3], ref[3], atol=2e-6)
+    np.testing.assert_allclose(out[4], ref[4], atol=1e-5)
+    out4 = double_QR(tau, W_e, params_r)
+    assert len(out4) == 4
+
+
+def test_device_resident_pipeline_and_errors():
+    import torch
+    from figaroh.tools.qrdecomposition import double_QR
+    from figaroh.tools.regressor import build_regressor_basic, build_regressor_reduced, get_index_eliminate
+    from figaroh_b200.engine import DeviceMatrix
+    robot = _Robot("ur10")
+    param = make_param(True, False, True)
+    q, v, a = (torch.from_numpy(x).cuda() for x in rand_inputs(load_flat("ur10"), 640, 8, ((-3, 3), (-3, 3), (-6, 6))))
+    std = robot.get_standard_parameters(param)
+    W = build_regressor_basic(robot, q, v, a, param)
+    assert isinstance(W, DeviceMatrix)                       # stays in HBM for CUDA inputs
+    idx_e, params_r = get_index_eliminate(W, std, 1e-6)
+    W_e = build_regressor_reduced(W, idx_e)
+    tau = torch.randn(W.shape[0], dtype=torch.float64, device="cuda")
+    W_b, bp, names, phi_b = double_QR(tau, W_e, params_r)
+    assert isinstance(W_b, DeviceMatrix) and W_b.shape == (W.shape[0], len(names))
+    phi_ls = np.linalg.lstsq(W_b.numpy(), tau.cpu().numpy(), rcond=None)[0]
+    np.testing.assert_allclose(phi_b, np.round(phi_ls, 6), atol=2e-6)
+    # reference error behaviour
+    ff = _Robot("talos_ff")
+    qq, vv, aa = rand_inputs(load_flat("talos_ff"), 3, 0)
+    with pytest.raises(ValueError):                           # regressor.py:53 cannot broadcast
+        build_regressor_basic(ff, qq, vv, aa, make_param(False, False, False))
+    with pytest.raises(ValueError, match="Please enter valid parameters"):
+        build_regressor_basic(ff, qq, vv, aa, make_param(False, False, False, is_joint_torques=False,
+                                                         is_external_wrench=True, force_torque=["F?"]))
+    with pytest.raises(UnboundLocalError):
+        build_regressor_basic(ff, qq, vv, aa, make_param(False, False, False, is_joint_torques=False))
+
+
+def test_tiago_golden_csv_on_gpu():
+    """The reference's TIAGo golden (44 expressions, phi_b to 6 decimals) with the regressor built
+    by kernel (1) and double_QR run by kernels (2)+(3); the per-column decimation between them is
+    scipy on the host exactly as in examples/tiago/identification.py:142-187."""
+    from figaroh.tools.qrdecomposition import double_QR
+    from figaroh.tools.regressor import build_regressor_basic, build_regressor_reduced, get_index_eliminate
+    from test_oracle_golden import tiago_decimate, tiago_inputs
+    meta = json.load(open(golden_path("tiago_kat.json")))
+    robot = _Robot("tiago")
+    param = make_param(False, False, False)
+    p, v, a, tau, idxv = tiago_inputs()
+    std = robot.get_standard_parameters(param)
+    W = build_regressor_basic(robot, p, v, a, param)
+    idx_e, params_r = get_index_eliminate(W, std, tol_e=0.001)
+    assert idx_e == meta["idx_e"]
+    W_rf, tau_rf = tiago_decimate(build_regressor_reduced(W, idx_e), tau, idxv, len(p))
+    W_b, bp, base, phi_b, phi_std = double_QR(tau_rf, W_rf, params_r, std)
+    assert base == [g[0] for g in meta["golden_csv"]]
+    np.testing.assert_allclose(phi_b, [g[1] for g in meta["golden_csv"]], atol=1.01e-6)
+    assert np.mean(phi_b == np.array([g[1] for g in meta["golden_csv"]])) > 0.9
