@@ -288,17 +288,19 @@ static int get_plan(fg_model* m, const fg_regressor_cfg* cfg, const int32_t* col
   const int ncols = (int)sel.size(), p1 = ncols + 1;
   pl->cols.resize(p1);
   pl->fullcol.resize(p1);
-  pl->nact.resize(p1);
+  pl->nact.assign(kMaxRowGroups + 1, 0);
   for (int c = 0; c < ncols; ++c) { pl->cols[c] = full[sel[c]]; pl->fullcol[c] = sel[c]; }
   memset(&pl->cols[ncols], 0, sizeof(ColDesc));
   pl->cols[ncols].kind = COL_RHS; pl->cols[ncols].grp = -1;
   pl->fullcol[ncols] = -1;
-  for (int c = 0; c < p1; ++c) {
-    int na = 0;
-    const int fc = c < ncols ? sel[c] : ncols_full;
-    for (auto& r : pl->rows) if (r.start_col <= fc) ++na;
-    pl->nact[c] = na;
+  // gstart[g]: first (compact) column at which row group g can be non-zero; the rhs column
+  // (index ncols) is non-zero in every row.  Row groups are ordered by joint, so this is ascending.
+  for (size_t g = 0; g < pl->rows.size(); ++g) {
+    int first = ncols;
+    for (int c = 0; c < ncols; ++c) if (sel[c] >= pl->rows[g].start_col) { first = c; break; }
+    pl->nact[g] = first;
   }
+  pl->nact[pl->rows.size()] = p1;
   Plan& P = pl->P;
   memset(&P, 0, sizeof P);
   P.nj = m->njoints; P.nq = m->nq; P.nv = m->nv; P.ms = (int)pl->rows.size();
@@ -307,13 +309,13 @@ static int get_plan(fg_model* m, const fg_regressor_cfg* cfg, const int32_t* col
   // ---- upload as one blob
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   const size_t o_plan = 0, o_rows = al(sizeof(Plan)), o_cols = o_rows + al(sizeof(RowDesc) * pl->rows.size());
-  const size_t o_nact = o_cols + al(sizeof(ColDesc) * p1), o_full = o_nact + al(sizeof(int) * p1);
+  const size_t o_nact = o_cols + al(sizeof(ColDesc) * p1), o_full = o_nact + al(sizeof(int) * (kMaxRowGroups + 1));
   const size_t total = o_full + al(sizeof(int) * p1);
   std::vector<unsigned char> blob(total, 0);
   memcpy(&blob[o_plan], &P, sizeof P);
   memcpy(&blob[o_rows], pl->rows.data(), sizeof(RowDesc) * pl->rows.size());
   memcpy(&blob[o_cols], pl->cols.data(), sizeof(ColDesc) * p1);
-  memcpy(&blob[o_nact], pl->nact.data(), sizeof(int) * p1);
+  memcpy(&blob[o_nact], pl->nact.data(), sizeof(int) * (kMaxRowGroups + 1));
   memcpy(&blob[o_full], pl->fullcol.data(), sizeof(int) * p1);
   FG_CUDA(cudaMalloc(&pl->d_blob, total));
   FG_CUDA(cudaMemcpy(pl->d_blob, blob.data(), total, cudaMemcpyHostToDevice));

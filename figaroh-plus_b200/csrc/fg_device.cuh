@@ -295,87 +295,98 @@ __device__ __forceinline__ int tri_off(int c, int p1) { return c * p1 - (c * (c 
 
 // ------------------------------------------------------------------------------------
 // Householder fold of a register tile into R.
-//   B[r][t]   : tile entry (row r, column lane + 32 t); rows come in groups of GS whose
-//               activation column is non-decreasing with the group index,
+//   B[r][t]   : tile entry (row r, column lane + 32 t); rows come in NG = TR/GS groups of GS
+//               rows whose activation column is non-decreasing with the group index,
 //   Rt        : packed upper-triangular (p1 columns) factor, shared or global memory,
 //   xs        : per-warp scratch, 2 * (TR + 2) doubles (double-buffered reflector broadcast),
-//   nact      : nact[c] = number of active row groups at column c, or nullptr (all active),
+//   gstart    : gstart[g] = first column at which row group g can be non-zero (g < NG) and
+//               gstart[NG] = p1; nullptr = every group active from column 0,
 //   c_begin   : first column that can be non-zero in this tile.
 // Reflector c annihilates column c of the tile against R[c][c] (LAPACK dlarfg convention:
 // beta = -sign(alpha) * norm, v = x / (alpha - beta), tau = (beta - alpha) / beta).
 // All p1 columns are eliminated, the rhs column last, so R[p1-1][p1-1] carries the residual.
+//
+// The column loop is split by (slot of the pivot column, number of active row groups) so that
+// every inner loop has compile-time bounds: rows that are still structurally zero cost nothing
+// (the block-triangular shape of a joint-torque regressor makes that ~60% of the dense work).
+
+// one reflector; NA = number of active rows (a multiple of GS), TO = slot of the pivot column
+template <int NSLOT, int TR, int NA, int TO>
+__device__ __forceinline__ void fold_column(double (&B)[TR][NSLOT], double* Rt, int p1, double* xs, int c, int lane) {
+  constexpr int XS = TR + 2;
+  const int o = c - 32 * TO;
+  double* xb = xs + (c & 1) * XS;
+  const int roff = tri_off(c, p1);
+  if (lane == o) {
+#pragma unroll
+    for (int r = 0; r < NA; ++r) xb[r] = B[r][TO];
+    xb[TR] = Rt[roff];  // alpha
+  }
+  __syncwarp();
+  double v[NA];
+  double sg[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int r = 0; r < NA; ++r) { v[r] = xb[r]; sg[r & 3] = fma(v[r], v[r], sg[r & 3]); }
+  const double sigma = (sg[0] + sg[1]) + (sg[2] + sg[3]);
+  if (sigma == 0.0) return;  // nothing to annihilate: H = I (dlarfg with xnorm == 0)
+  const double alpha = xb[TR];
+  const double mu = fma(alpha, alpha, sigma);
+  const double rs = rsqrt(mu);
+  const double nrm = mu * rs;
+  const double beta = alpha >= 0.0 ? -nrm : nrm;
+  const double den = alpha - beta;
+  const double inv = __drcp_rn(den);
+  const double tauh = fabs(den) * rs;  // (beta - alpha) / beta
+#pragma unroll
+  for (int t = TO; t < NSLOT; ++t) {
+    const int col = lane + 32 * t;
+    const bool act = (t > TO || lane > o) && col < p1;
+    double d[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int r = 0; r < NA; ++r) d[r & 3] = fma(v[r], B[r][t], d[r & 3]);
+    const double dd = (d[0] + d[1]) + (d[2] + d[3]);
+    double gco = 0.0;
+    if (act) {
+      const double rho = Rt[roff + col - c];
+      const double sdot = fma(dd, inv, rho);  // w^T [rho; b],  w = [1; x * inv]
+      Rt[roff + col - c] = fma(-tauh, sdot, rho);
+      gco = tauh * sdot * inv;
+    }
+#pragma unroll
+    for (int r = 0; r < NA; ++r) B[r][t] = fma(-gco, v[r], B[r][t]);
+  }
+  if (lane == o) Rt[roff] = beta;
+}
+
+template <int NSLOT, int TR, int GS, int TO, int NGA>
+__device__ __forceinline__ void fold_ranges(double (&B)[TR][NSLOT], double* Rt, int p1, double* xs,
+                                            const int* gstart, int c_begin, int lane) {
+  constexpr int NG = TR / GS;
+  if constexpr (NGA <= NG) {
+    int lo = gstart ? gstart[NGA - 1] : 0, hi = gstart ? gstart[NGA] : p1;
+    if (gstart == nullptr && NGA < NG) hi = 0;  // dense tiles: only the all-active range exists
+    if (lo < 32 * TO) lo = 32 * TO;
+    if (lo < c_begin) lo = c_begin;
+    if (hi > 32 * TO + 32) hi = 32 * TO + 32;
+    if (hi > p1) hi = p1;
+    for (int c = lo; c < hi; ++c) fold_column<NSLOT, TR, NGA * GS, TO>(B, Rt, p1, xs, c, lane);
+    fold_ranges<NSLOT, TR, GS, TO, NGA + 1>(B, Rt, p1, xs, gstart, c_begin, lane);
+  }
+}
+
+template <int NSLOT, int TR, int GS, int TO>
+__device__ __forceinline__ void fold_slots(double (&B)[TR][NSLOT], double* Rt, int p1, double* xs,
+                                           const int* gstart, int c_begin, int lane) {
+  if constexpr (TO < NSLOT) {
+    if (32 * TO < p1 && 32 * TO + 32 > c_begin) fold_ranges<NSLOT, TR, GS, TO, 1>(B, Rt, p1, xs, gstart, c_begin, lane);
+    fold_slots<NSLOT, TR, GS, TO + 1>(B, Rt, p1, xs, gstart, c_begin, lane);
+  }
+}
+
 template <int NSLOT, int TR, int GS>
 __device__ __forceinline__ void fold_tile(double (&B)[TR][NSLOT], double* Rt, int p1, double* xs,
-                                          const int* nact, int c_begin, int lane) {
-  constexpr int NG = TR / GS;
-  constexpr int XS = TR + 2;
-#pragma unroll
-  for (int to = 0; to < NSLOT; ++to) {
-    const int cbase = 32 * to;
-    if (cbase + 32 <= c_begin) continue;
-    const int o_lo = c_begin > cbase ? c_begin - cbase : 0;
-    const int o_hi = (p1 - cbase) < 32 ? (p1 - cbase) : 32;
-    for (int o = o_lo; o < o_hi; ++o) {
-      const int c = cbase + o;
-      const int ng = nact ? nact[c] : NG;   // active row groups (uniform)
-      double* xb = xs + (c & 1) * XS;
-      const int roff = tri_off(c, p1);
-      if (lane == o) {
-#pragma unroll
-        for (int g = 0; g < NG; ++g)
-          if (g < ng) {
-#pragma unroll
-            for (int s = 0; s < GS; ++s) xb[g * GS + s] = B[g * GS + s][to];
-          }
-        xb[TR] = Rt[roff];  // alpha
-      }
-      __syncwarp();
-      double v[TR];
-      double sigma = 0.0;
-#pragma unroll
-      for (int g = 0; g < NG; ++g) {
-        if (g < ng) {
-#pragma unroll
-          for (int s = 0; s < GS; ++s) { v[g * GS + s] = xb[g * GS + s]; sigma = fma(v[g * GS + s], v[g * GS + s], sigma); }
-        } else {
-#pragma unroll
-          for (int s = 0; s < GS; ++s) v[g * GS + s] = 0.0;
-        }
-      }
-      if (sigma == 0.0) continue;  // nothing to annihilate: H = I (dlarfg with xnorm == 0)
-      const double alpha = xb[TR];
-      const double nrm = sqrt(fma(alpha, alpha, sigma));
-      const double beta = alpha >= 0.0 ? -nrm : nrm;
-      const double inv = 1.0 / (alpha - beta);
-      const double tauh = (beta - alpha) / beta;
-#pragma unroll
-      for (int t = to; t < NSLOT; ++t) {
-        const int col = lane + 32 * t;
-        const bool act = (t > to || lane > o) && col < p1;
-        double d = 0.0;
-#pragma unroll
-        for (int g = 0; g < NG; ++g)
-          if (g < ng) {
-#pragma unroll
-            for (int s = 0; s < GS; ++s) d = fma(v[g * GS + s], B[g * GS + s][t], d);
-          }
-        double gco = 0.0;
-        if (act) {
-          const double rho = Rt[roff + col - c];
-          const double sdot = fma(d, inv, rho);   // w^T [rho; b],  w = [1; x * inv]
-          Rt[roff + col - c] = fma(-tauh, sdot, rho);
-          gco = tauh * sdot * inv;
-        }
-#pragma unroll
-        for (int g = 0; g < NG; ++g)
-          if (g < ng) {
-#pragma unroll
-            for (int s = 0; s < GS; ++s) B[g * GS + s][t] = fma(-gco, v[g * GS + s], B[g * GS + s][t]);
-          }
-      }
-      if (lane == o) Rt[roff] = beta;
-    }
-  }
+                                          const int* gstart, int c_begin, int lane) {
+  fold_slots<NSLOT, TR, GS, 0>(B, Rt, p1, xs, gstart, c_begin, lane);
 }
 
 }  // namespace fg

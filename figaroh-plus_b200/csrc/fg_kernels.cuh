@@ -27,7 +27,7 @@ __host__ __device__ inline SmemLayout make_layout(int nj, int ms, int p1, int nv
   L.off_plan = o;   o = align16(o + (int)sizeof(Plan));
   L.off_joints = o; o = align16(o + nj * (int)sizeof(DevJoint));
   L.off_rows = o;   o = align16(o + ms * (int)sizeof(RowDesc));
-  L.off_nact = o;   o = align16(o + p1 * (int)sizeof(int));
+  L.off_nact = o;   o = align16(o + (kMaxRowGroups + 1) * (int)sizeof(int));
   L.off_warp0 = o;
   int w = 0;
   L.w_R = w;  w = align16(w + (R_in_smem ? (p1 * (p1 + 1) / 2) * 8 : 0));
@@ -45,7 +45,7 @@ struct DevPlanPtrs {
   const DevJoint* joints;
   const RowDesc* rows;
   const ColDesc* cols;  // [p1] (last = rhs)
-  const int* nact;      // [p1]
+  const int* nact;      // [ms + 1] gstart: first column at which row group g is active; [ms] = p1
   const int* fullcol;   // [p1] full (reference) column index of each compact column, -1 for rhs
 };
 
@@ -59,7 +59,7 @@ __device__ inline void load_plan_to_smem(unsigned char* smem, const SmemLayout& 
   for (int i = threadIdx.x; i < P.ms * (int)(sizeof(RowDesc) / 8); i += blockDim.x)
     reinterpret_cast<double*>(Rw)[i] = reinterpret_cast<const double*>(pp.rows)[i];
   int* na = reinterpret_cast<int*>(smem + L.off_nact);
-  for (int i = threadIdx.x; i < P.p1; i += blockDim.x) na[i] = pp.nact[i];
+  for (int i = threadIdx.x; i <= P.ms; i += blockDim.x) na[i] = pp.nact[i];
   __syncthreads();
 }
 
