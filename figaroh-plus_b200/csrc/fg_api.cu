@@ -12,6 +12,7 @@
 
 #include "../../include/figaroh_b200.h"
 #include "fg_kernels.cuh"
+#include "fg_bq.h"
 
 using namespace fg;
 
@@ -612,6 +613,26 @@ static int launch_fused(fg_state* s, fg_model* m, DevPlan* pl, const double* q, 
   return FG_OK;
 }
 
+// second-generation fused kernel (fg_blockqr.cuh): register tile in DMMA fragment layout
+static int launch_bq(fg_state* s, fg_model* m, DevPlan* pl, const double* q, const double* v, const double* a,
+                     const double* tau, int64_t ld_tau, int64_t N, cudaStream_t st) {
+  const BqLaunch bl = bq_plan_launch(pl->P, N, m->sm_count, m->max_smem);
+  if (!bl.ok) return set_err(FG_ERR_UNSUPPORTED, "block-QR kernel needs %d bytes of shared memory", bl.smem);
+  int rc = ensure_parts(s, bl.nparts + 1);
+  if (rc) return rc;
+  rc = timing_begin(s, st);
+  if (rc) return rc;
+  cudaError_t e = bq_launch(bl, pl->ptrs, q, v, a, tau, ld_tau, N, s->d_parts, st);
+  rc = timing_end(s, st);
+  if (rc) return rc;
+  if (e != cudaSuccess) return set_err(FG_ERR_CUDA, "bq_launch failed: %s", cudaGetErrorString(e));
+  FG_LAUNCHED();
+  rc = merge_parts_into_state(s, bl.nparts, m->max_smem, st);
+  if (rc) return rc;
+  s->rows += N * pl->P.ms;
+  return FG_OK;
+}
+
 static int accumulate_samples_dev(fg_state* s, fg_model* m, const fg_regressor_cfg* cfg, const double* q,
                                   const double* v, const double* a, const double* tau, int64_t ld_tau, int64_t N,
                                   cudaStream_t st) {
@@ -623,6 +644,11 @@ static int accumulate_samples_dev(fg_state* s, fg_model* m, const fg_regressor_c
   if (N <= 0) return FG_OK;
   if (tau && ld_tau < N) return set_err(FG_ERR_INVALID, "ld_tau=%lld smaller than N=%lld", (long long)ld_tau, (long long)N);
   const int ms = pl->P.ms, nslot = (pl->P.p1 + 31) / 32;
+  {
+    const char* e = getenv("FG_USE_BQ");
+    const bool use_bq = !(e && e[0] == '0');
+    if (use_bq && bq_supported(pl->P)) return launch_bq(s, m, pl, q, v, a, tau, ld_tau, N, st);
+  }
   if (ms == 6 && nslot <= 3) return launch_fused<3, 6, 4>(s, m, pl, q, v, a, tau, ld_tau, N, st);
   if (ms == 6 && nslot <= 11) return launch_fused<11, 6, 1>(s, m, pl, q, v, a, tau, ld_tau, N, st);
   if (ms == 6 && nslot <= 15) return launch_fused<15, 6, 1>(s, m, pl, q, v, a, tau, ld_tau, N, st);

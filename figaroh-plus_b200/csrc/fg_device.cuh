@@ -58,6 +58,20 @@ struct Plan {
   double gravity[3];
 };
 
+__host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
+
+struct DevPlanPtrs {
+  const Plan* plan;
+  const DevJoint* joints;
+  const RowDesc* rows;
+  const ColDesc* cols;  // [p1] (last = rhs)
+  const int* nact;      // [ms + 1] gstart: first column at which row group g is active; [ms] = p1
+  const int* fullcol;   // [p1] full (reference) column index of each compact column, -1 for rhs
+};
+
+// A "part" is one packed upper-triangular factor (p1 columns) plus p1 squared column norms.
+__host__ __device__ inline int64_t part_doubles(int p1) { return (int64_t)p1 * (p1 + 1) / 2 + p1; }
+
 // per-joint forward state of one sample, kept in shared memory
 constexpr int FW_R = 0, FW_P = 9, FW_V = 12, FW_A = 18, FW_AP = 24, FW_STRIDE = 27;
 

@@ -18,7 +18,6 @@ struct SmemLayout {
   int total;
 };
 
-__host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
 
 __host__ __device__ inline SmemLayout make_layout(int nj, int ms, int p1, int nv, int S, int TR, int nwarps,
                                                   bool R_in_smem, bool need_fw) {
@@ -40,14 +39,6 @@ __host__ __device__ inline SmemLayout make_layout(int nj, int ms, int p1, int nv
   return L;
 }
 
-struct DevPlanPtrs {
-  const Plan* plan;
-  const DevJoint* joints;
-  const RowDesc* rows;
-  const ColDesc* cols;  // [p1] (last = rhs)
-  const int* nact;      // [ms + 1] gstart: first column at which row group g is active; [ms] = p1
-  const int* fullcol;   // [p1] full (reference) column index of each compact column, -1 for rhs
-};
 
 __device__ inline void load_plan_to_smem(unsigned char* smem, const SmemLayout& L, const DevPlanPtrs& pp) {
   const Plan P = *pp.plan;
@@ -127,7 +118,6 @@ __global__ void __launch_bounds__(256) regressor_materialize_kernel(DevPlanPtrs 
 
 // ------------------------------------------------------------------ partial factors in HBM
 // A "part" is one packed upper-triangular factor (p1 columns) plus p1 squared column norms.
-__host__ __device__ inline int64_t part_doubles(int p1) { return (int64_t)p1 * (p1 + 1) / 2 + p1; }
 
 // Fold the rows of packed factor `src` (p1 columns) into `dst` (packed).  One warp.
 template <int NSLOT, int TR>

@@ -332,23 +332,71 @@ class BaseSolution:
         self.rows = 0
 
 
-def solve_state(state: TsqrState, names, tol_e=None, idx_e=None, tol_qr=TOL_QR, params_std=None) -> BaseSolution:
+def structural_columns(dm: DeviceModel, cfg: RegressorConfig, nprobe=64, seed=20241017) -> np.ndarray:
+    """Columns of the regressor that are not identically zero for this model / configuration.
+
+    The N-independent "symbolic" pass: W is evaluated on `nprobe` random generic samples and the
+    columns whose every entry is exactly 0.0 are dropped before the QR.  Their squared norm is 0 for
+    any data, so get_index_eliminate (regressor.py:271-274) eliminates them for every tol_e > 0;
+    skipping them changes neither idx_e nor anything downstream.  Cached on the DeviceModel.
+    """
+    key = (cfg.mode, cfg.flags, cfg.ft_mask, None if cfg.row_sel is None else tuple(int(i) for i in cfg.row_sel))
+    cache = dm.__dict__.setdefault("_structural", {})
+    if key in cache:
+        return cache[key]
+    fm = dm.flat
+    rng = np.random.default_rng(seed)
+    q = rng.uniform(-np.pi, np.pi, size=(nprobe, fm.nq))
+    v = rng.uniform(-2.0, 2.0, size=(nprobe, fm.nv))
+    a = rng.uniform(-3.0, 3.0, size=(nprobe, fm.nv))
+    for i in range(1, fm.njoints):
+        iq = fm.idx_q[i]
+        if fm.jtype[i] == 2:
+            th = rng.uniform(-np.pi, np.pi, nprobe)
+            q[:, iq], q[:, iq + 1] = np.cos(th), np.sin(th)
+        elif fm.jtype[i] == 4:
+            quat = rng.normal(size=(nprobe, 4))
+            q[:, iq + 3:iq + 7] = quat / np.linalg.norm(quat, axis=1, keepdims=True)
+    W = dm.materialize(cfg, q, v, a)
+    rps = W.shape[0] // nprobe
+    amax = W.abs().view(rps, nprobe, -1).amax(dim=1)          # (row block, column)
+    if cfg.mode == _lib.FG_MODE_JOINT_TORQUES and cfg.row_sel is not None:
+        amax = amax[torch.as_tensor(np.asarray(cfg.row_sel, dtype=np.int64), device=amax.device)]
+    nz = (amax.amax(dim=0) != 0).cpu().numpy()
+    sel = np.flatnonzero(nz).astype(np.int32)
+    cache[key] = sel
+    return sel
+
+
+def solve_state(state: TsqrState, names, tol_e=None, idx_e=None, tol_qr=TOL_QR, params_std=None,
+                col_map=None, p_full=None) -> BaseSolution:
     """Reference post-processing (regressor.py:258-293 + qrdecomposition.py:89-187) on the R factor.
 
-    names: names of the state's p columns (list(params_std.keys())[:p] in the reference).
+    names: names of the regressor's columns (list(params_std.keys())[:p] in the reference).
     Either tol_e (squared-norm threshold, regressor.py:271-274) or an explicit idx_e.
+    col_map / p_full: when the state holds only a subset of the regressor's p_full columns
+    (structural_columns), col_map[i] is the regressor column of state column i; idx_e / keep /
+    names are then expressed in regressor columns, the dropped ones counting as eliminated.
     """
     sol = BaseSolution()
     p = state.p
     sol.rows = state.rows
+    if col_map is None:
+        col_map = np.arange(p)
+        p_full = p
+    col_map = np.asarray(col_map, dtype=np.int64)
     if idx_e is None:
         sq = state.colsq()[:p]
-        idx_e = [i for i in range(p) if sq[i] < tol_e] if tol_e is not None else []
-    sol.idx_e = [int(i) for i in idx_e]
-    eset = set(sol.idx_e)
-    sol.keep = [i for i in range(p) if i not in eset]
+        drop = set(i for i in range(p) if sq[i] < tol_e) if tol_e is not None else set()
+    else:
+        inv = {int(c): i for i, c in enumerate(col_map)}
+        drop = set(inv[int(c)] for c in idx_e if int(c) in inv)
+    keep_state = [i for i in range(p) if i not in drop]
+    sol.keep = [int(col_map[i]) for i in keep_state]
+    kept = set(sol.keep)
+    sol.idx_e = [i for i in range(int(p_full)) if i not in kept]
     sol.params_r = [names[i] for i in sol.keep]
-    diag = state.reduce(sol.keep)
+    diag = state.reduce(keep_state)
     sol.diag = diag
     nk = len(sol.keep)
     sol.idx_base = [i for i in range(nk) if diag[i] > tol_qr]
@@ -385,15 +433,22 @@ def relative_stdev_from_solution(sol: BaseSolution) -> np.ndarray:
 
 
 def identify(dm: DeviceModel, cfg: RegressorConfig, q, v, a, tau, names, tol_e=1e-6, tol_qr=TOL_QR,
-             params_std=None, host_inputs=False, state: TsqrState | None = None) -> BaseSolution:
+             params_std=None, host_inputs=False, state: TsqrState | None = None, prune=True) -> BaseSolution:
     """Samples -> base parameters in one fused pass: the whole hot path of the reference
     (build_regressor_basic -> get_index_eliminate -> build_regressor_reduced -> double_QR)
-    without ever forming W."""
+    without ever forming W.  Columns that are identically zero for the model (structural_columns)
+    are not generated at all unless prune=False."""
     _, cols = dm.shape(cfg)
-    p = cols if cfg.col_sel is None else len(cfg.col_sel)
+    col_map = None
+    if cfg.col_sel is None and prune:
+        col_map = structural_columns(dm, cfg)
+        cfg = cfg.with_columns(col_map)
+    elif cfg.col_sel is not None:
+        col_map = np.asarray(cfg.col_sel)
+    p = cols if col_map is None else len(col_map)
     st = state if state is not None else TsqrState(p)
     if host_inputs:
         st.accumulate_samples_host(dm, cfg, q, v, a, tau)
     else:
         st.accumulate_samples(dm, cfg, q, v, a, tau)
-    return solve_state(st, names, tol_e=tol_e, tol_qr=tol_qr, params_std=params_std)
+    return solve_state(st, names, tol_e=tol_e, tol_qr=tol_qr, params_std=params_std, col_map=col_map, p_full=cols)
