@@ -13,6 +13,7 @@
 #include "../../include/figaroh_b200.h"
 #include "fg_kernels.cuh"
 #include "fg_bq.h"
+#include "fg_tq.h"
 
 using namespace fg;
 
@@ -44,6 +45,10 @@ struct DevPlan {
   std::vector<int> nact, fullcol;
   void* d_blob = nullptr;  // one allocation holding everything
   DevPlanPtrs ptrs{};
+  // third-generation kernel (fg_tileqr.cuh): launch parameters, built on first use
+  bool tq_tried = false;
+  TqLaunch tql;
+  std::unique_ptr<TqParams> tq;
   ~DevPlan() { if (d_blob) cudaFree(d_blob); }
 };
 
@@ -73,6 +78,9 @@ struct fg_state {
   int* d_idx = nullptr;         // 2*p1 ints: column map + extents
   int nk = -1;                  // columns kept by the last fg_state_reduce
   std::vector<int> keep;
+  // column order of the factor: state column i holds caller column perm[i] (empty = identity).
+  // The tile-QR kernel eliminates the friction / inertia / offset columns first (fg_tq.cu).
+  std::vector<int> perm;
   // staging for the host-buffer path
   double* d_stage = nullptr;
   int64_t stage_cap = 0;
@@ -434,6 +442,35 @@ extern "C" int fg_state_reset(fg_state* s, void* stream) {
   if (!s) return set_err(FG_ERR_INVALID, "null state");
   FG_CUDA(cudaMemsetAsync(s->d_part, 0, sizeof(double) * part_doubles(s->p1), (cudaStream_t)stream));
   s->rows = 0; s->empty = true; s->nk = -1;
+  s->perm.clear();
+  return FG_OK;
+}
+
+// inverse of the state's column order: caller column -> state column
+static std::vector<int> inverse_perm(const fg_state* s) {
+  std::vector<int> inv(s->p);
+  for (int i = 0; i < s->p; ++i) inv[s->perm.empty() ? i : s->perm[i]] = i;
+  return inv;
+}
+
+extern "C" int fg_state_get_perm(const fg_state* s, int32_t* perm_out) {
+  if (!s || !perm_out) return set_err(FG_ERR_INVALID, "fg_state_get_perm: null argument");
+  for (int i = 0; i < s->p; ++i) perm_out[i] = s->perm.empty() ? i : s->perm[i];
+  return FG_OK;
+}
+
+extern "C" int fg_state_set_perm(fg_state* s, const int32_t* perm) {
+  if (!s || !perm) return set_err(FG_ERR_INVALID, "fg_state_set_perm: null argument");
+  if (!s->empty) return set_err(FG_ERR_INVALID, "fg_state_set_perm: the state already holds rows");
+  std::vector<char> seen(s->p, 0);
+  bool ident = true;
+  for (int i = 0; i < s->p; ++i) {
+    if (perm[i] < 0 || perm[i] >= s->p || seen[perm[i]]) return set_err(FG_ERR_INVALID, "fg_state_set_perm: not a permutation");
+    seen[perm[i]] = 1;
+    ident = ident && perm[i] == i;
+  }
+  s->perm.clear();
+  if (!ident) s->perm.assign(perm, perm + s->p);
   return FG_OK;
 }
 
@@ -553,6 +590,8 @@ extern "C" int fg_state_accumulate_dense(fg_state* s, const double* W, int64_t l
   if (!s || (!W && rows > 0)) return set_err(FG_ERR_INVALID, "fg_state_accumulate_dense: null argument");
   if (rows <= 0) return FG_OK;
   if (ldw < s->p) return set_err(FG_ERR_INVALID, "ldw=%lld smaller than p=%d", (long long)ldw, s->p);
+  if (!s->perm.empty())
+    return set_err(FG_ERR_UNSUPPORTED, "fg_state_accumulate_dense: the state holds a permuted factor (fused samples); use a fresh state");
   cudaStream_t st = (cudaStream_t)stream;
   const int nslot = (s->p1 + 31) / 32;
   if (nslot <= 1) return launch_dense<1, 24>(s, W, ldw, tau, rows, st);
@@ -633,6 +672,29 @@ static int launch_bq(fg_state* s, fg_model* m, DevPlan* pl, const double* q, con
   return FG_OK;
 }
 
+// third-generation fused kernel (fg_tileqr.cuh): shared-memory tiles of 32 samples, rows grouped by joint
+static int launch_tq(fg_state* s, fg_model* m, DevPlan* pl, const double* q, const double* v, const double* a,
+                     const double* tau, int64_t ld_tau, int64_t N, cudaStream_t st) {
+  const TqLaunch& tl = pl->tql;
+  const int64_t ntiles = (N + TQ_S - 1) / TQ_S;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, tl.grid));
+  int rc = ensure_parts(s, grid + 1);
+  if (rc) return rc;
+  rc = ensure_gR(s, (int64_t)grid * tl.r_doubles);
+  if (rc) return rc;
+  rc = timing_begin(s, st);
+  if (rc) return rc;
+  cudaError_t e = tq_launch(tl, *pl->tq, q, v, a, tau, ld_tau, N, s->d_gR, s->d_parts, grid, st);
+  rc = timing_end(s, st);
+  if (rc) return rc;
+  if (e != cudaSuccess) return set_err(FG_ERR_CUDA, "tq_launch failed: %s", cudaGetErrorString(e));
+  FG_LAUNCHED();
+  rc = merge_parts_into_state(s, grid, m->max_smem, st);
+  if (rc) return rc;
+  s->rows += N * pl->P.ms;
+  return FG_OK;
+}
+
 static int accumulate_samples_dev(fg_state* s, fg_model* m, const fg_regressor_cfg* cfg, const double* q,
                                   const double* v, const double* a, const double* tau, int64_t ld_tau, int64_t N,
                                   cudaStream_t st) {
@@ -644,6 +706,30 @@ static int accumulate_samples_dev(fg_state* s, fg_model* m, const fg_regressor_c
   if (N <= 0) return FG_OK;
   if (tau && ld_tau < N) return set_err(FG_ERR_INVALID, "ld_tau=%lld smaller than N=%lld", (long long)ld_tau, (long long)N);
   const int ms = pl->P.ms, nslot = (pl->P.p1 + 31) / 32;
+  {
+    const char* e = getenv("FG_USE_TQ");
+    const bool use_tq = !(e && e[0] == '0');
+    if (use_tq && !pl->tq_tried) {
+      pl->tq_tried = true;
+      pl->tq.reset(new TqParams);
+      const char* why = "";
+      pl->tql = tq_build(pl->P, m->joints.data(), pl->rows.data(), pl->cols.data(), m->sm_count, m->max_smem,
+                         pl->tq.get(), &why);
+      if (!pl->tql.ok) pl->tq.reset();
+      else {
+        bool ident = true;
+        for (size_t i = 0; i < pl->tql.perm.size(); ++i) ident = ident && pl->tql.perm[i] == (int)i;
+        if (ident) pl->tql.perm.clear();
+      }
+    }
+    if (use_tq && pl->tql.ok) {
+      if (s->empty) s->perm = pl->tql.perm;
+      if (s->perm == pl->tql.perm) return launch_tq(s, m, pl, q, v, a, tau, ld_tau, N, st);
+      // the state already holds a factor in another column order: stay on the path that produced it
+    }
+    if (!s->perm.empty())
+      return set_err(FG_ERR_INVALID, "the state holds a factor in a column order this configuration cannot extend");
+  }
   {
     const char* e = getenv("FG_USE_BQ");
     const bool use_bq = !(e && e[0] == '0');
@@ -751,8 +837,12 @@ extern "C" int fg_state_merge_packed(fg_state* s, const double* packed, int32_t 
 extern "C" int fg_state_colsq(fg_state* s, double* out, void* stream) {
   if (!s || !out) return set_err(FG_ERR_INVALID, "fg_state_colsq: null argument");
   const int ntri = s->p1 * (s->p1 + 1) / 2;
-  FG_CUDA(cudaMemcpyAsync(out, s->d_part + ntri, sizeof(double) * s->p1, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  std::vector<double> tmp(s->p1);
+  FG_CUDA(cudaMemcpyAsync(tmp.data(), s->d_part + ntri, sizeof(double) * s->p1, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   FG_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  const std::vector<int> inv = inverse_perm(s);
+  for (int i = 0; i < s->p; ++i) out[i] = tmp[inv[i]];
+  out[s->p] = tmp[s->p];
   return FG_OK;
 }
 
@@ -775,11 +865,12 @@ extern "C" int fg_state_reduce(fg_state* s, const int32_t* keep, int32_t nk, dou
   cudaStream_t st = (cudaStream_t)stream;
   const int p1 = s->p1, n = nk + 1;
   std::vector<int> idx(2 * n);
+  const std::vector<int> inv = inverse_perm(s);
   for (int j = 0; j < nk; ++j) {
     if (keep[j] < 0 || keep[j] >= s->p || (j > 0 && keep[j] <= keep[j - 1]))
       return set_err(FG_ERR_INVALID, "fg_state_reduce: keep must be ascending indices in [0,%d)", s->p);
-    idx[j] = keep[j];
-    idx[n + j] = keep[j] + 1;
+    idx[j] = inv[keep[j]];       // where the factor keeps caller column keep[j]
+    idx[n + j] = idx[j] + 1;     // rows 0..idx[j] of that column can be non-zero
   }
   idx[nk] = s->p;       // rhs column
   idx[n + nk] = p1;

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libfigaroh_b200.so")
+LIB_PATH = os.environ.get("FG_B200_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libfigaroh_b200.so")
 
 FG_MODE_JOINT_TORQUES = 0
 FG_MODE_EXTERNAL_WRENCH = 1
@@ -21,7 +21,7 @@ SYMBOLS = (
     "fg_regressor_materialize", "fg_state_create", "fg_state_destroy", "fg_state_reset", "fg_state_p",
     "fg_state_rows", "fg_state_accumulate_dense", "fg_state_accumulate_samples", "fg_state_packed_doubles",
     "fg_state_export", "fg_state_merge_packed", "fg_state_colsq", "fg_state_reduce", "fg_state_regroup_solve",
-    "fg_state_accumulate_samples_host", "fg_launch_count", "fg_state_set_timing", "fg_state_get_timing",
+    "fg_state_accumulate_samples_host", "fg_state_get_perm", "fg_state_set_perm", "fg_launch_count", "fg_state_set_timing", "fg_state_get_timing",
 )
 
 
@@ -77,6 +77,8 @@ def lib():
     L.fg_state_accumulate_samples_host.argtypes = [vp, vp, C.POINTER(RegressorCfg), dp, dp, dp, dp, i64, i64, vp]
     L.fg_state_packed_doubles.argtypes = [i32]
     L.fg_state_packed_doubles.restype = i64
+    L.fg_state_get_perm.argtypes = [vp, vp]
+    L.fg_state_set_perm.argtypes = [vp, vp]
     L.fg_state_export.argtypes = [vp, dp, vp]
     L.fg_state_merge_packed.argtypes = [vp, dp, i32, vp]
     L.fg_state_colsq.argtypes = [vp, dp, vp]

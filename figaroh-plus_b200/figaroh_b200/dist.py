@@ -39,5 +39,6 @@ def allgather_merge(local: TsqrState, merged: TsqrState | None = None, group=Non
         merged = TsqrState(local.p)
     else:
         merged.reset()
+    merged.set_perm(local.get_perm())  # packed factors are in the local kernel's column order
     merged.merge_packed(gathered, world)
     return merged

@@ -254,6 +254,18 @@ class TsqrState:
     def packed_doubles(self):
         return int(_lib.lib().fg_state_packed_doubles(self.p))
 
+    def get_perm(self) -> np.ndarray:
+        """State column i holds caller column perm[i] (the fused kernel picks the order)."""
+        perm = np.empty(self.p, dtype=np.int32)
+        check(_lib.lib().fg_state_get_perm(self._h, perm.ctypes.data))
+        return perm
+
+    def set_perm(self, perm):
+        perm = np.ascontiguousarray(perm, dtype=np.int32)
+        assert perm.shape == (self.p,)
+        check(_lib.lib().fg_state_set_perm(self._h, perm.ctypes.data))
+        return self
+
     def export(self, out: torch.Tensor | None = None) -> torch.Tensor:
         if out is None:
             out = torch.empty(self.packed_doubles(), dtype=torch.float64, device="cuda")
