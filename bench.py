@@ -309,7 +309,8 @@ def main():
                                                    + (len(sol.keep) + 1) ** 2))},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "fp64", "kernel": "bq_accumulate_samples_kernel (fused regressor + blocked Householder TSQR fold, DMMA trailing updates)",
+            "roofline": {"bound": "tensor", "pipe": "fp64 (DFMA panels + DMMA m8n8k4 trailing updates; tcgen05 has no fp64 mode)",
+                         "kernel": "tq_accumulate_kernel (sample-per-thread regressor + shared-memory tile QR, look-ahead panels, DMMA trailing updates)",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": None, "kernel_ms": kern_ms_avg, "kernel_share_of_step": kern_ms_avg / ms_step,
                          "flops_per_sample": FLOPS_PER_SAMPLE, "peak_source": peak_src},

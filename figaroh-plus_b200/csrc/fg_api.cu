@@ -382,7 +382,7 @@ extern "C" int fg_regressor_materialize(const fg_model* mc, const fg_regressor_c
 }
 
 // ------------------------------------------------------------------------------------ state
-extern "C" int64_t fg_state_packed_doubles(int32_t p) { return (int64_t)(p + 1) * (p + 1) + (p + 1) + 1; }
+extern "C" int64_t fg_state_packed_doubles(int32_t p) { return (int64_t)(p + 1) * (p + 1) + 2 * (p + 1); }
 extern "C" int fg_state_p(const fg_state* s) { return s ? s->p : -1; }
 extern "C" int64_t fg_state_rows(const fg_state* s) { return s ? s->rows : -1; }
 
@@ -672,32 +672,39 @@ static int launch_bq(fg_state* s, fg_model* m, DevPlan* pl, const double* q, con
   return FG_OK;
 }
 
-// third-generation fused kernel (fg_tileqr.cuh): shared-memory tiles of 32 samples, rows grouped by joint
+// third-generation fused kernel (fg_tileqr.cuh): shared-memory tiles of 32 samples, rows grouped by joint.
+// `phase`: TQ_PHASE_FIRST starts the per-CTA factors from zero, TQ_PHASE_LAST writes them out and merges
+// them into the state; a chunked caller (the host-buffer path) sets FIRST on its first chunk and LAST on its
+// last one, so the factors stay in the L2-resident scratch between launches and are merged once.
 static int launch_tq(fg_state* s, fg_model* m, DevPlan* pl, const double* q, const double* v, const double* a,
-                     const double* tau, int64_t ld_tau, int64_t N, cudaStream_t st) {
+                     const double* tau, int64_t ld_tau, int64_t N, int phase, cudaStream_t st) {
   const TqLaunch& tl = pl->tql;
   const int64_t ntiles = (N + TQ_S - 1) / TQ_S;
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, tl.grid));
+  const bool whole = phase == (TQ_PHASE_FIRST | TQ_PHASE_LAST);
+  const int grid = whole ? (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, tl.grid)) : tl.grid;
   int rc = ensure_parts(s, grid + 1);
   if (rc) return rc;
-  rc = ensure_gR(s, (int64_t)grid * tl.r_doubles);
-  if (rc) return rc;
+  if (phase & TQ_PHASE_FIRST) {
+    rc = ensure_gR(s, (int64_t)grid * tl.r_doubles);
+    if (rc) return rc;
+  } else if (s->gR_cap < (int64_t)grid * tl.r_doubles) {
+    return set_err(FG_ERR_INVALID, "internal: continued launch without a first one");
+  }
   rc = timing_begin(s, st);
   if (rc) return rc;
-  cudaError_t e = tq_launch(tl, *pl->tq, q, v, a, tau, ld_tau, N, s->d_gR, s->d_parts, grid, st);
+  cudaError_t e = tq_launch(tl, *pl->tq, q, v, a, tau, ld_tau, N, s->d_gR, s->d_parts, grid, phase, st);
   rc = timing_end(s, st);
   if (rc) return rc;
   if (e != cudaSuccess) return set_err(FG_ERR_CUDA, "tq_launch failed: %s", cudaGetErrorString(e));
   FG_LAUNCHED();
-  rc = merge_parts_into_state(s, grid, m->max_smem, st);
-  if (rc) return rc;
   s->rows += N * pl->P.ms;
-  return FG_OK;
+  if (!(phase & TQ_PHASE_LAST)) return FG_OK;
+  return merge_parts_into_state(s, grid, m->max_smem, st);
 }
 
 static int accumulate_samples_dev(fg_state* s, fg_model* m, const fg_regressor_cfg* cfg, const double* q,
                                   const double* v, const double* a, const double* tau, int64_t ld_tau, int64_t N,
-                                  cudaStream_t st) {
+                                  cudaStream_t st, int phase = TQ_PHASE_FIRST | TQ_PHASE_LAST, bool* chunkable = nullptr) {
   DevPlan* pl = nullptr;
   int rc = get_plan(m, cfg, cfg->col_sel, cfg->n_col_sel, &pl);
   if (rc) return rc;
@@ -724,7 +731,10 @@ static int accumulate_samples_dev(fg_state* s, fg_model* m, const fg_regressor_c
     }
     if (use_tq && pl->tql.ok) {
       if (s->empty) s->perm = pl->tql.perm;
-      if (s->perm == pl->tql.perm) return launch_tq(s, m, pl, q, v, a, tau, ld_tau, N, st);
+      if (s->perm == pl->tql.perm) {
+        if (chunkable) *chunkable = true;
+        return launch_tq(s, m, pl, q, v, a, tau, ld_tau, N, phase, st);
+      }
       // the state already holds a factor in another column order: stay on the path that produced it
     }
     if (!s->perm.empty())
@@ -778,8 +788,12 @@ extern "C" int fg_state_accumulate_samples_host(fg_state* s, const fg_model* mc,
   FG_CUDA(cudaEventRecord(s->ev[2], st));
   FG_CUDA(cudaEventRecord(s->ev[3], st));
   int b = 0;
+  bool chunkable = false;  // set by the first chunk when the tile-QR kernel took it: later chunks continue its factors
   for (int64_t i0 = 0; i0 < N; i0 += chunk, b ^= 1) {
     const int64_t n = std::min(chunk, N - i0);
+    int phase = TQ_PHASE_FIRST | TQ_PHASE_LAST;
+    if (i0 == 0) phase = N > chunk ? TQ_PHASE_FIRST : phase;
+    else if (chunkable) phase = i0 + chunk >= N ? TQ_PHASE_LAST : 0;
     double* base = s->d_stage + (int64_t)b * chunk * per_sample;
     double* dq = base;
     double* dv = dq + chunk * m->nq;
@@ -794,7 +808,7 @@ extern "C" int fg_state_accumulate_samples_host(fg_state* s, const fg_model* mc,
                                 cudaMemcpyHostToDevice, s->copy_stream));
     FG_CUDA(cudaEventRecord(s->ev[b], s->copy_stream));
     FG_CUDA(cudaStreamWaitEvent(st, s->ev[b], 0));
-    rc = accumulate_samples_dev(s, m, cfg, dq, dv, da, tau ? dt : nullptr, chunk, n, st);
+    rc = accumulate_samples_dev(s, m, cfg, dq, dv, da, tau ? dt : nullptr, chunk, n, st, phase, i0 == 0 ? &chunkable : nullptr);
     if (rc) return rc;
     FG_CUDA(cudaEventRecord(s->ev[2 + b], st));
   }
@@ -804,9 +818,15 @@ extern "C" int fg_state_accumulate_samples_host(fg_state* s, const fg_model* mc,
 // ---- export / merge (multi-GPU exchange)
 extern "C" int fg_state_export(const fg_state* s, double* packed, void* stream) {
   if (!s || !packed) return set_err(FG_ERR_INVALID, "fg_state_export: null argument");
-  tri_to_dense_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(s->d_part, s->p1, packed, (double)s->rows);
+  cudaStream_t st = (cudaStream_t)stream;
+  tri_to_dense_kernel<<<64, 256, 0, st>>>(s->d_part, s->p1, packed, (double)s->rows);
   FG_CUDA(cudaGetLastError());
   FG_LAUNCHED();
+  // the column order travels with the factor: p doubles after [R | norms | rows]
+  std::vector<double> pd(s->p);
+  for (int i = 0; i < s->p; ++i) pd[i] = s->perm.empty() ? (double)i : (double)s->perm[i];
+  FG_CUDA(cudaMemcpyAsync(packed + (int64_t)s->p1 * s->p1 + s->p1 + 1, pd.data(), sizeof(double) * s->p,
+                          cudaMemcpyHostToDevice, st));  // pageable source: staged before the call returns
   return FG_OK;
 }
 
@@ -818,18 +838,34 @@ extern "C" int fg_state_merge_packed(fg_state* s, const double* packed, int32_t 
   if (rc) return rc;
   rc = ensure_parts(s, n + 1);
   if (rc) return rc;
+  // row counts and column orders travel behind the factor
+  const int64_t pk = fg_state_packed_doubles(s->p);
+  const int64_t tail0 = (int64_t)s->p1 * s->p1 + s->p1, ntail = 1 + s->p;
+  std::vector<double> tail((size_t)n * ntail);
+  FG_CUDA(cudaMemcpy2DAsync(tail.data(), sizeof(double) * ntail, packed + tail0, sizeof(double) * pk,
+                            sizeof(double) * ntail, n, cudaMemcpyDeviceToHost, st));
+  FG_CUDA(cudaStreamSynchronize(st));
+  std::vector<int> perm(s->p);
+  bool ident = true;
+  for (int i = 0; i < s->p; ++i) {
+    const double v = tail[1 + i];
+    if (!(v >= 0 && v < s->p) || v != (double)(int)v) return set_err(FG_ERR_INVALID, "fg_state_merge_packed: corrupt column order");
+    perm[i] = (int)v;
+    ident = ident && perm[i] == i;
+    for (int k = 1; k < n; ++k)
+      if (tail[(size_t)k * ntail + 1 + i] != v)
+        return set_err(FG_ERR_INVALID, "fg_state_merge_packed: the packed factors use different column orders");
+  }
+  if (ident) perm.clear();
+  if (s->empty) s->perm = perm;
+  else if (s->perm != perm)
+    return set_err(FG_ERR_INVALID, "fg_state_merge_packed: the state and the packed factors use different column orders");
   dense_to_tri_kernel<<<dim3(16, n), 256, 0, st>>>(packed, n, s->p1, s->d_parts);
   FG_CUDA(cudaGetLastError());
   FG_LAUNCHED();
-  // row counts travel in the last packed double
-  const int64_t pk = fg_state_packed_doubles(s->p);
-  std::vector<double> cnt(n);
-  FG_CUDA(cudaMemcpy2DAsync(cnt.data(), sizeof(double), packed + pk - 1, sizeof(double) * pk, sizeof(double), n,
-                            cudaMemcpyDeviceToHost, st));
-  FG_CUDA(cudaStreamSynchronize(st));
   rc = merge_parts_into_state(s, n, max_smem, st);
   if (rc) return rc;
-  for (double c : cnt) s->rows += (int64_t)c;
+  for (int k = 0; k < n; ++k) s->rows += (int64_t)tail[(size_t)k * ntail];
   return FG_OK;
 }
 

@@ -364,7 +364,7 @@ __global__ void tri_to_dense_kernel(const double* __restrict__ part, int p1, dou
 // packed exchange buffers (dense square + norms + rows) -> parts (packed triangles)
 __global__ void dense_to_tri_kernel(const double* __restrict__ packed, int n, int p1, double* __restrict__ parts) {
   const int ntri = p1 * (p1 + 1) / 2;
-  const int64_t pk = (int64_t)p1 * p1 + p1 + 1;
+  const int64_t pk = (int64_t)p1 * p1 + 2 * (int64_t)p1;  // fg_state_packed_doubles(p1 - 1)
   for (int k = blockIdx.y; k < n; k += gridDim.y) {
     const double* src = packed + (size_t)k * pk;
     double* dst = parts + (size_t)k * part_doubles(p1);

@@ -52,6 +52,15 @@ __host__ __device__ __forceinline__ int tq_idx(int c, int s) { return c * TQ_S +
 // index of R block (k, j), j >= k, in the per-CTA block-upper-triangular scratch (64 doubles each, [refl][col])
 __host__ __device__ __forceinline__ int tq_rblk(int ncb, int k, int j) { return k * ncb - (k * (k - 1)) / 2 + (j - k); }
 
+// named barriers (ids 1..4; id 0 is __syncthreads): producer arrives, consumers sync
+__device__ __forceinline__ void tq_bar_arrive(int id, int count) {
+  __threadfence_block();
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tq_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
 __device__ __forceinline__ double tq_allreduce(double x) {
   x += __shfl_xor_sync(0xffffffffu, x, 16);
   x += __shfl_xor_sync(0xffffffffu, x, 8);
@@ -94,13 +103,13 @@ __device__ __forceinline__ void tq_emit(const TqParams& P, double* tile, int g, 
 #pragma unroll
     for (int k = 0; k < 10; ++k) {
       const int slot = P.islot[body][k];
-      if (slot >= 0) tile[P.blkoff[g][slot >> 3] + tq_idx(slot & 7, lane)] = val[k];
+      if (slot >= 0) tile[P.blkoff[g][slot >> 3] + (slot & 7) * TQ_S + (lane ^ P.swz[slot & 7])] = val[k];
     }
   }
 }
 
 // Forward pass of one sample per lane; warp w emits the row groups w and w + 4.
-__device__ __noinline__ void tq_generate(const TqParams& P, double* tile, const double* scr,
+__device__ __noinline__ void tq_generate(const TqParams& P, double* tile, const double* scr, const DevJoint* Js,
                                          const double* __restrict__ q, const double* __restrict__ qd,
                                          const double* __restrict__ qdd, const double* __restrict__ tau,
                                          int64_t ld_tau, int64_t s0, int64_t N, int warp, int lane) {
@@ -116,9 +125,18 @@ __device__ __noinline__ void tq_generate(const TqParams& P, double* tile, const 
   double oR[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, op[3] = {0, 0, 0};
   double v[6] = {0, 0, 0, 0, 0, 0}, a[6] = {0, 0, 0, 0, 0, 0};
   const unsigned mine = (1u << g0) | (g1 < P.ms ? (1u << g1) : 0u);
+  // the (q, dq, ddq) entries of the NEXT joint are requested one joint ahead: their HBM/L2 round trip
+  // overlaps the arithmetic of the current joint
+  double nq0 = __ldg(qs + Js[P.proc[0]].idx_q), nv0 = __ldg(vs + Js[P.proc[0]].idx_v),
+         na0 = __ldg(as + Js[P.proc[0]].idx_v);
   for (int t = 0; t < P.nproc; ++t) {
     const int i = P.proc[t];
-    const DevJoint& jt = P.joints[i];
+    const DevJoint& jt = Js[i];
+    const double cq0 = nq0, cv0 = nv0, ca0 = na0;
+    if (t + 1 < P.nproc) {
+      const DevJoint& jn = Js[P.proc[t + 1]];
+      nq0 = __ldg(qs + jn.idx_q); nv0 = __ldg(vs + jn.idx_v); na0 = __ldg(as + jn.idx_v);
+    }
     if (jt.parent == 0) {  // restart from the universe (the host only admits chains hanging off it)
       oR[0] = 1; oR[1] = 0; oR[2] = 0; oR[3] = 0; oR[4] = 1; oR[5] = 0; oR[6] = 0; oR[7] = 0; oR[8] = 1;
       op[0] = op[1] = op[2] = 0.0;
@@ -132,14 +150,14 @@ __device__ __noinline__ void tq_generate(const TqParams& P, double* tile, const 
     if (jt.jtype == 1) {
       const double c = scr[(2 * t) * TQ_S + lane], s = scr[(2 * t + 1) * TQ_S + lane];
       axis_rot(jt.axis, c, s, Rj);
-      const double qd1 = __ldg(vs + iv), qdd1 = __ldg(as + iv);
+      const double qd1 = cv0, qdd1 = ca0;
       for (int k = 0; k < 3; ++k) { vj[3 + k] = jt.axis[k] * qd1; aj[3 + k] = jt.axis[k] * qdd1; }
     } else if (jt.jtype == 2) {
-      axis_rot(jt.axis, __ldg(qs + iq), __ldg(qs + iq + 1), Rj);
-      const double qd1 = __ldg(vs + iv), qdd1 = __ldg(as + iv);
+      axis_rot(jt.axis, cq0, __ldg(qs + iq + 1), Rj);
+      const double qd1 = cv0, qdd1 = ca0;
       for (int k = 0; k < 3; ++k) { vj[3 + k] = jt.axis[k] * qd1; aj[3 + k] = jt.axis[k] * qdd1; }
     } else if (jt.jtype == 3) {
-      const double qq = __ldg(qs + iq), qd1 = __ldg(vs + iv), qdd1 = __ldg(as + iv);
+      const double qq = cq0, qd1 = cv0, qdd1 = ca0;
       for (int k = 0; k < 3; ++k) { pj[k] = jt.axis[k] * qq; vj[k] = jt.axis[k] * qd1; aj[k] = jt.axis[k] * qdd1; }
     } else {  // free-flyer
       quat_rot(__ldg(qs + iq + 3), __ldg(qs + iq + 4), __ldg(qs + iq + 5), __ldg(qs + iq + 6), Rj);
@@ -208,7 +226,8 @@ __device__ __noinline__ void tq_generate(const TqParams& P, double* tile, const 
       if (g1 < P.ms && ((am >> g1) & 1u)) tq_emit(P, tile, g1, i, A1, oR, op, v + 3, a + 3, ap, valid, lane);
     }
   }
-  // columns read straight off the inputs
+  // columns read straight off the inputs (unrolled so that the loads of several columns are in flight together)
+#pragma unroll 4
   for (int t = warp; t < P.nsimple; t += TQ_WARPS) {
     const TqSimple sc1 = P.simple[t];
     const int j = sc1.slot >> 3, ix = tq_idx(sc1.slot & 7, lane);
@@ -252,54 +271,55 @@ __device__ __noinline__ void tq_generate(const TqParams& P, double* tile, const 
 //   shared memory); sc: 16 doubles of shared scratch (tau_j, 1 / (alpha_j - beta_j)).
 // On exit x holds the NORMALISED reflectors v = x / (alpha - beta) (LAPACK dlarfg convention), Rkk the
 // updated block, sc[0..7] the taus (0 for a skipped / padding column).
-template <int NG, bool FULL>
-__device__ __forceinline__ void tq_panel_factor(double (&x)[NG][8], int ncols, double* Rkk, int ldr, double* sc,
+template <int NG, int W>
+__device__ __forceinline__ void tq_panel_factor(double (&x)[NG][8], const double* Rin, double* Rout, int ldr, double* sc,
                                                 int lane) {
-  // row blocks that do not take part hold zeros in x, so every loop runs over all NG of them
+  // Row blocks that do not take part and padding columns hold zeros in x, so every loop has compile-time
+  // bounds (a zero column gives sigma == 0 and is skipped).  The diagonal block is read from Rin and the
+  // updated rows are written to Rout by lane 0: no read-after-write hazard between lanes.
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < W; ++j) {
     double tauh = 0.0, inv = 0.0;
-    if (FULL || j < ncols) {
-      // Row j of the diagonal block is read by every lane BEFORE the reductions and rewritten by lane 0
-      // AFTER them: the full-mask shuffles in between order the two across the warp.
-      double d[8], rr[8];
+    double d[8];
 #pragma unroll
-      for (int c = j; c < 8; ++c) rr[c] = Rkk[j * ldr + c];
+    for (int c = j; c < W; ++c) {
+      double acc = 0.0;
 #pragma unroll
-      for (int c = j; c < 8; ++c) {
-        double acc = 0.0;
-#pragma unroll
-        for (int gi = 0; gi < NG; ++gi) acc = fma(x[gi][j], x[gi][c], acc);
-        d[c] = acc;
-      }
-#pragma unroll
-      for (int c = j; c < 8; ++c)
-        if (FULL || c < ncols) d[c] = tq_allreduce(d[c]);
-      const double sigma = d[j];
-      if (sigma != 0.0) {  // uniform: every lane holds the same sum
-        const double alpha = rr[j];
-        const double mu = fma(alpha, alpha, sigma);
-        const double rs = rsqrt(mu);
-        const double nrm = mu * rs;
-        const double beta = alpha >= 0.0 ? -nrm : nrm;
-        const double den = alpha - beta;
-        inv = __drcp_rn(den);
-        tauh = fabs(den) * rs;  // (beta - alpha) / beta
-#pragma unroll
-        for (int c = j + 1; c < 8; ++c) {
-          if (FULL || c < ncols) {
-            const double rho = rr[c];
-            const double w = tauh * fma(d[c], inv, rho);  // tau * v^T [rho; b]
-            const double coef = w * inv;
-#pragma unroll
-            for (int gi = 0; gi < NG; ++gi) x[gi][c] = fma(-coef, x[gi][j], x[gi][c]);
-            if (lane == 0) Rkk[j * ldr + c] = rho - w;
-          }
-        }
-        if (lane == 0) Rkk[j * ldr + j] = beta;
-      }
+      for (int gi = 0; gi < NG; ++gi) acc = fma(x[gi][j], x[gi][c], acc);
+      d[c] = acc;
     }
-    if (lane == 0) sc[j] = tauh;
+    // butterfly all-reduce of d[j..W-1], level by level for all values at once: the shuffles of one level
+    // are independent, so their latencies overlap (one value after the other costs 5 round trips EACH)
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      double t[8];
+#pragma unroll
+      for (int c = j; c < W; ++c) t[c] = __shfl_xor_sync(0xffffffffu, d[c], off);
+#pragma unroll
+      for (int c = j; c < W; ++c) d[c] += t[c];
+    }
+    const double sigma = d[j];
+    const double alpha = Rin[j * ldr + j];
+    double beta = alpha;
+    if (sigma != 0.0) {  // uniform: the butterfly leaves the same bits in every lane
+      const double mu = fma(alpha, alpha, sigma);
+      const double rs = rsqrt(mu);
+      const double nrm = mu * rs;
+      beta = alpha >= 0.0 ? -nrm : nrm;
+      const double den = alpha - beta;
+      inv = __drcp_rn(den);
+      tauh = fabs(den) * rs;  // (beta - alpha) / beta
+    }
+    if (lane == 0) { Rout[j * ldr + j] = beta; sc[j] = tauh; }
+#pragma unroll
+    for (int c = j + 1; c < W; ++c) {
+      const double rho = Rin[j * ldr + c];
+      const double w = tauh * fma(d[c], inv, rho);  // tau * v^T [rho; b]  (0 when the reflector is skipped)
+      const double coef = w * inv;
+#pragma unroll
+      for (int gi = 0; gi < NG; ++gi) x[gi][c] = fma(-coef, x[gi][j], x[gi][c]);
+      if (lane == 0) Rout[j * ldr + c] = rho - w;
+    }
 #pragma unroll
     for (int gi = 0; gi < NG; ++gi) x[gi][j] *= inv;  // H = I (dlarfg with xnorm == 0) leaves v = 0
   }
@@ -312,16 +332,15 @@ __device__ __forceinline__ void tq_panel_factor(double (&x)[NG][8], int ncols, d
 // receives T row-major.  KW = stored width of the panel block.
 template <int KW>
 __device__ __forceinline__ void tq_panel_T(const TqParams& P, const double* tile, int k, unsigned gmask,
-                                           const double* sc, double* TS, int lane) {
+                                           const double* sc, double* TS, const int (&oy)[TQ_S / 4], int lane) {
   const int cq = lane >> 2, rq = lane & 3;
-  const int ca = cq * TQ_S, swa = tq_sw(cq);
   double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
   for (unsigned gm = gmask; gm; gm &= gm - 1) {
     const double* Xk = tile + P.blkoff[__ffs(gm) - 1][k];
 #pragma unroll
     for (int kk = 0; kk < TQ_S / 4; kk += 2) {
-      const double v0 = (KW == 8 || cq < KW) ? Xk[ca + ((4 * kk + rq) ^ swa)] : 0.0;
-      const double v1 = (KW == 8 || cq < KW) ? Xk[ca + ((4 * kk + 4 + rq) ^ swa)] : 0.0;
+      const double v0 = (KW == 8 || cq < KW) ? Xk[oy[kk]] : 0.0;
+      const double v1 = (KW == 8 || cq < KW) ? Xk[oy[kk + 1]] : 0.0;
       tq_dmma(a0, a1, v0, v0);
       tq_dmma(b0, b1, v1, v1);
     }
@@ -358,53 +377,69 @@ __device__ __forceinline__ void tq_panel_T(const TqParams& P, const double* tile
   __syncwarp();
 }
 
+// Per-lane offsets inside a tile block of the three access patterns of the trailing update; they
+// depend on the lane only, so a warp computes them once.
+struct TqOffs {
+  int oy[TQ_S / 4];       // (row 4kk + rq, column cq): A / B fragments of the row contraction
+  int oc0[TQ_S / 8], oc1[TQ_S / 8];  // (rows 8nn + 2rq, +1; column cq): accumulator fragments of the update
+  int ob0[TQ_S / 8], ob1[TQ_S / 8];  // (row 8nn + cq; columns 2rq, 2rq + 1): V^T as B fragment of the update
+};
+__device__ __forceinline__ void tq_make_offs(TqOffs& o, int lane) {
+  const int cq = lane >> 2, rq = lane & 3;
+#pragma unroll
+  for (int kk = 0; kk < TQ_S / 4; ++kk) o.oy[kk] = tq_idx(cq, 4 * kk + rq);
+#pragma unroll
+  for (int nn = 0; nn < TQ_S / 8; ++nn) {
+    o.oc0[nn] = tq_idx(cq, 8 * nn + 2 * rq);
+    o.oc1[nn] = tq_idx(cq, 8 * nn + 2 * rq + 1);
+    o.ob0[nn] = tq_idx(2 * rq, 8 * nn + cq);
+    o.ob1[nn] = tq_idx(2 * rq + 1, 8 * nn + cq);
+  }
+}
+
 // Trailing update of column block j by panel k for the row groups in gmask (one warp):
 //   Y^T = R_kj^T + sum_g B_gj^T V_g ;  W^T = Y^T T ;  R_kj^T -= W^T ;  B_gj^T -= W^T V_g^T
 // KW = stored width of the panel block (8, or 4 for a private block whose columns 4..7 are padding).
 template <int KW>
 __device__ __forceinline__ void tq_trailing(const TqParams& P, double* tile, double* Rb, const double* TS, int k, int j,
-                                            unsigned gmask, int lane) {
+                                            unsigned gmask, const TqOffs& o, int lane) {
   const int cq = lane >> 2, rq = lane & 3;
   const double t0 = TS[(2 * rq) * 8 + cq], t1 = TS[(2 * rq + 1) * 8 + cq];
-  const int ca = cq * TQ_S, swa = tq_sw(cq);
   const double r0 = Rb[(2 * rq) * 8 + cq], r1 = Rb[(2 * rq + 1) * 8 + cq];  // L2 round trip hidden by the DMMA chain
-  double y0 = 0.0, y1 = 0.0;
+  double y0 = 0.0, y1 = 0.0, z0 = 0.0, z1 = 0.0;  // two accumulator pairs: two independent DMMA chains
   for (unsigned gm = gmask; gm; gm &= gm - 1) {
     const int g = __ffs(gm) - 1;
     const double* Bj = tile + P.blkoff[g][j];
     const double* Xk = tile + P.blkoff[g][k];
 #pragma unroll
-    for (int kk = 0; kk < TQ_S / 4; ++kk) {
-      const int o = ca + ((4 * kk + rq) ^ swa);
-      const double b = (KW == 8 || cq < KW) ? Xk[o] : 0.0;
-      tq_dmma(y0, y1, Bj[o], b);
+    for (int kk = 0; kk < TQ_S / 4; kk += 2) {
+      const double b0 = (KW == 8 || cq < KW) ? Xk[o.oy[kk]] : 0.0;
+      const double b1 = (KW == 8 || cq < KW) ? Xk[o.oy[kk + 1]] : 0.0;
+      tq_dmma(y0, y1, Bj[o.oy[kk]], b0);
+      tq_dmma(z0, z1, Bj[o.oy[kk + 1]], b1);
     }
   }
-  y0 += r0;
-  y1 += r1;
+  y0 += z0 + r0;
+  y1 += z1 + r1;
   double w0 = 0.0, w1 = 0.0;
   tq_dmma(w0, w1, y0, t0);
   tq_dmma(w0, w1, y1, t1);
   Rb[(2 * rq) * 8 + cq] = r0 - w0;
   Rb[(2 * rq + 1) * 8 + cq] = r1 - w1;
   const double nw0 = -w0, nw1 = -w1;
-  const int cb0 = (2 * rq) * TQ_S, cb1 = (2 * rq + 1) * TQ_S, swb0 = tq_sw(2 * rq), swb1 = tq_sw(2 * rq + 1);
   for (unsigned gm = gmask; gm; gm &= gm - 1) {
     const int g = __ffs(gm) - 1;
     double* Bj = tile + P.blkoff[g][j];
     const double* Xk = tile + P.blkoff[g][k];
 #pragma unroll
     for (int nn = 0; nn < TQ_S / 8; ++nn) {
-      const int rc = 8 * nn + 2 * rq;
-      const int o0 = ca + (rc ^ swa), o1 = ca + ((rc + 1) ^ swa);
-      double c0 = Bj[o0], c1 = Bj[o1];
-      const int rb = 8 * nn + cq;
-      const double b0 = (KW == 8 || 2 * rq < KW) ? Xk[cb0 + (rb ^ swb0)] : 0.0;
-      const double b1 = (KW == 8 || 2 * rq + 1 < KW) ? Xk[cb1 + (rb ^ swb1)] : 0.0;
+      double c0 = Bj[o.oc0[nn]], c1 = Bj[o.oc1[nn]];
+      const double b0 = (KW == 8 || 2 * rq < KW) ? Xk[o.ob0[nn]] : 0.0;
+      const double b1 = (KW == 8 || 2 * rq + 1 < KW) ? Xk[o.ob1[nn]] : 0.0;
       tq_dmma(c0, c1, nw0, b0);
       tq_dmma(c0, c1, nw1, b1);
-      Bj[o0] = c0;
-      Bj[o1] = c1;
+      Bj[o.oc0[nn]] = c0;
+      Bj[o.oc1[nn]] = c1;
     }
   }
 }
@@ -414,29 +449,36 @@ template <int MAXG>
 __global__ void __launch_bounds__(TQ_WARPS * 32, 3)
 tq_accumulate_kernel(const __grid_constant__ TqParams P, const double* __restrict__ q, const double* __restrict__ qd,
                      const double* __restrict__ qdd, const double* __restrict__ tau, int64_t ld_tau, int64_t N,
-                     double* __restrict__ r_all, int64_t r_doubles, double* __restrict__ parts) {
+                     double* __restrict__ r_all, int64_t r_doubles, double* __restrict__ parts, int phase) {
   extern __shared__ __align__(16) double tq_smem[];
   double* tile = tq_smem;
   double* scr = tq_smem + P.tile_doubles;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* Rg = r_all + (size_t)blockIdx.x * r_doubles;
-  for (int i = threadIdx.x; i < r_doubles; i += blockDim.x) Rg[i] = 0.0;
+  // phase bit 0: start from R = 0 (else continue the factor a previous launch left in the scratch);
+  // phase bit 1: write the packed factor to parts[] at the end
+  if (phase & 1)
+    for (int i = threadIdx.x; i < r_doubles; i += blockDim.x) Rg[i] = 0.0;
   const int ncb = P.ncb;
-  // CTAs that share an SM (blockIdx.x = sm + i * sm_count) use different warps - SM sub-partitions - for a panel
-#ifdef TQ_DBG_NOROT
-  const int prot = -P.npriv;
-#else
-  const int prot = (int)blockIdx.x / P.sm_count;
-#endif
+  // Roles in the general phase: ONE panel warp per CTA (CTAs that share an SM - blockIdx.x = sm + i * sm_count -
+  // pick different warps, i.e. different SM sub-partitions) and three workers that own the column blocks
+  // round-robin and apply the trailing updates in the shadow of the next panel (look-ahead).
+  const int pw = ((int)blockIdx.x / P.sm_count) & (TQ_WARPS - 1);
+  const int wi = (warp - pw - 1) & (TQ_WARPS - 1);  // 0..2 for the workers, 3 for the panel warp
+  DevJoint* Js = reinterpret_cast<DevJoint*>(scr + 2 * TQ_S * P.nproc);
+  TqOffs offs;
+  tq_make_offs(offs, lane);
   const int64_t ntiles = (N + TQ_S - 1) / TQ_S;
   for (int64_t tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
     const int64_t s0 = tl * TQ_S;
     __syncthreads();
-    // ---- clear the tile; sines / cosines of the revolute joints (one joint per warp at a time)
+    // ---- clear the tile; joint constants and the sines / cosines of the revolute joints into the scratch
     {
       double2* t2 = reinterpret_cast<double2*>(tile);
       const int n2 = P.tile_doubles / 2;
       for (int i = threadIdx.x; i < n2; i += blockDim.x) t2[i] = make_double2(0.0, 0.0);
+      for (int i = threadIdx.x; i < P.nj * (int)(sizeof(DevJoint) / 8); i += blockDim.x)
+        reinterpret_cast<double*>(Js)[i] = reinterpret_cast<const double*>(P.joints)[i];
       const int64_t smp = s0 + lane;
       const int64_t sc = smp < N ? smp : N - 1;
       for (int t = warp; t < P.nproc; t += TQ_WARPS) {
@@ -450,16 +492,15 @@ tq_accumulate_kernel(const __grid_constant__ TqParams P, const double* __restric
       }
     }
     __syncthreads();
-    tq_generate(P, tile, scr, q, qd, qdd, tau, ld_tau, s0, N, warp, lane);
+    tq_generate(P, tile, scr, Js, q, qd, qdd, tau, ld_tau, s0, N, warp, lane);
     __syncthreads();
     // ---- phase A: private panels, one warp each, no CTA-wide synchronisation
     {
-      double* TS = scr + warp * 96;
+      double* TS = scr + warp * 112;
       double* Ree = TS + 64;
       for (int e = warp; e < P.npriv; e += TQ_WARPS) {
         const unsigned gm = P.gmask[e];
         const int g = __ffs(gm) - 1;
-        const int ncols = P.ncols[e];
         double* Xe = tile + P.blkoff[g][e];
         double* Rd = Rg + (size_t)tq_rblk(ncb, e, e) * 64;
         if (lane < 16) Ree[lane] = Rd[(lane >> 2) * 8 + (lane & 3)];
@@ -467,78 +508,86 @@ tq_accumulate_kernel(const __grid_constant__ TqParams P, const double* __restric
 #pragma unroll
         for (int c = 0; c < 8; ++c) x[0][c] = c < 4 ? Xe[tq_idx(c, lane)] : 0.0;
         __syncwarp();
-        tq_panel_factor<1, false>(x, ncols, Ree, 4, Ree + 16, lane);
+        tq_panel_factor<1, 4>(x, Ree, Ree + 16, 4, Ree + 32, lane);
 #pragma unroll
         for (int c = 0; c < 4; ++c) Xe[tq_idx(c, lane)] = x[0][c];
         __syncwarp();
-        tq_panel_T<4>(P, tile, e, gm, Ree + 16, TS, lane);
-        if (lane < 16) Rd[(lane >> 2) * 8 + (lane & 3)] = Ree[lane];
+        tq_panel_T<4>(P, tile, e, gm, Ree + 32, TS, offs.oy, lane);
+        if (lane < 16 && (lane >> 2) <= (lane & 3)) Rd[(lane >> 2) * 8 + (lane & 3)] = Ree[16 + lane];
         __syncwarp();
         for (unsigned tm = P.trmask[e]; tm; tm &= tm - 1) {
           const int j = __ffs(tm) - 1;
-          tq_trailing<4>(P, tile, Rg + (size_t)tq_rblk(ncb, e, j) * 64, TS, e, j, gm, lane);
+          tq_trailing<4>(P, tile, Rg + (size_t)tq_rblk(ncb, e, j) * 64, TS, e, j, gm, offs, lane);
         }
         __syncwarp();
       }
     }
     __syncthreads();
-    // ---- phase B: general panels
+    // ---- phase B: general panels with look-ahead.  Barrier 1 + (k & 1): "panel k is factored" (panel warp
+    // arrives, workers wait); barrier 3 + (k & 1): "block k + 1 carries the updates of every panel <= k" (its
+    // owner arrives, the panel warp waits).  Scratch: one T per worker, the diagonal block (in / out) and the
+    // taus of panel k (double-buffered by the parity of k).
     {
-      double* TS = scr;
-      double* Rkk = scr + 384;
-      for (int k = P.npriv; k < ncb; ++k) {
-        const unsigned gm = P.gmask[k];
-        if (gm == 0) continue;  // uniform
-        if (warp == ((k + prot) & (TQ_WARPS - 1))) {
-          double* Rd = Rg + (size_t)tq_rblk(ncb, k, k) * 64;
-          Rkk[lane] = Rd[lane];
-          Rkk[lane + 32] = Rd[lane + 32];
-          int gl[MAXG];
-          int ng = 0;
+      double* TSw = scr + 64 * wi;       // workers: wi = 0..2
+      double* Rkk = scr + 192;           // [192, 256) in, [256, 320) out
+      double* scb = scr + 320;           // [320, 336): taus of panel k at scb + 8 * (k & 1)
+      if (wi == 3) {
+        for (int k = P.npriv; k < ncb; ++k) {
+          if (k > P.npriv) tq_bar_sync(3 + ((k - 1) & 1), 64);
+          const unsigned gm = P.gmask[k];
+          if (gm) {
+            double* Rd = Rg + (size_t)tq_rblk(ncb, k, k) * 64;
+            Rkk[lane] = Rd[lane];
+            Rkk[lane + 32] = Rd[lane + 32];
+            int gl[MAXG];
+            int ng = 0;
 #pragma unroll
-          for (int gi = 0; gi < MAXG; ++gi) gl[gi] = 0;
-          {
-            unsigned m2 = gm;
+            for (int gi = 0; gi < MAXG; ++gi) gl[gi] = 0;
+            {
+              unsigned m2 = gm;
+#pragma unroll
+              for (int gi = 0; gi < MAXG; ++gi)
+                if (m2) { gl[gi] = P.blkoff[__ffs(m2) - 1][k]; m2 &= m2 - 1; ++ng; }
+            }
+            double x[MAXG][8];
 #pragma unroll
             for (int gi = 0; gi < MAXG; ++gi)
-              if (m2) { gl[gi] = P.blkoff[__ffs(m2) - 1][k]; m2 &= m2 - 1; ++ng; }
+#pragma unroll
+              for (int c = 0; c < 8; ++c) x[gi][c] = gi < ng ? tile[gl[gi] + tq_idx(c, lane)] : 0.0;
+            __syncwarp();
+            tq_panel_factor<MAXG, 8>(x, Rkk, Rkk + 64, 8, scb + 8 * (k & 1), lane);
+#pragma unroll
+            for (int gi = 0; gi < MAXG; ++gi)
+              if (gi < ng) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) tile[gl[gi] + tq_idx(c, lane)] = x[gi][c];
+              }
+            if ((lane >> 3) <= (lane & 7)) Rd[lane] = Rkk[64 + lane];            // rows 0..3 of the upper triangle
+            if ((lane >> 3) + 4 <= (lane & 7)) Rd[lane + 32] = Rkk[96 + lane];   // rows 4..7
           }
-          double x[MAXG][8];
-#pragma unroll
-          for (int gi = 0; gi < MAXG; ++gi)
-#pragma unroll
-            for (int c = 0; c < 8; ++c) x[gi][c] = gi < ng ? tile[gl[gi] + tq_idx(c, lane)] : 0.0;
-          __syncwarp();
-#ifndef TQ_DBG_NOFULL
-          if (P.ncols[k] == 8) tq_panel_factor<MAXG, true>(x, 8, Rkk, 8, Rkk + 64, lane);
-          else
-#endif
-            tq_panel_factor<MAXG, false>(x, P.ncols[k], Rkk, 8, Rkk + 64, lane);
-#pragma unroll
-          for (int gi = 0; gi < MAXG; ++gi)
-            if (gi < ng) {
-#pragma unroll
-              for (int c = 0; c < 8; ++c) tile[gl[gi] + tq_idx(c, lane)] = x[gi][c];
+          tq_bar_arrive(1 + (k & 1), 128);
+        }
+      } else {
+        for (int k = P.npriv; k < ncb; ++k) {
+          tq_bar_sync(1 + (k & 1), 128);
+          const unsigned gm = P.gmask[k];
+          const unsigned tm = P.trmask[k];
+          if (gm && tm) {
+            tq_panel_T<8>(P, tile, k, gm, scb + 8 * (k & 1), TSw, offs.oy, lane);
+            for (int j = k + 1; j < ncb; ++j) {  // block k + 1 first: the next panel waits for it
+              if ((j - P.npriv) % 3 != wi || !((tm >> j) & 1u)) continue;
+              tq_trailing<8>(P, tile, Rg + (size_t)tq_rblk(ncb, k, j) * 64, TSw, k, j, gm, offs, lane);
+              if (j == k + 1) tq_bar_arrive(3 + (k & 1), 64);
             }
-          __syncwarp();
-          tq_panel_T<8>(P, tile, k, gm, Rkk + 64, TS, lane);
-          Rd[lane] = Rkk[lane];
-          Rd[lane + 32] = Rkk[lane + 32];
-        }
-        __syncthreads();
-        {
-          int n = 0;
-          for (unsigned tm = P.trmask[k]; tm; tm &= tm - 1, ++n) {
-            if ((n & (TQ_WARPS - 1)) != warp) continue;
-            const int j = __ffs(tm) - 1;
-            tq_trailing<8>(P, tile, Rg + (size_t)tq_rblk(ncb, k, j) * 64, TS, k, j, gm, lane);
           }
+          if (k + 1 < ncb && (k + 1 - P.npriv) % 3 == wi && !(gm && tm && ((tm >> (k + 1)) & 1u)))
+            tq_bar_arrive(3 + (k & 1), 64);  // nothing to apply to block k + 1, but the hand-shake is unconditional
         }
-        __syncthreads();
       }
     }
   }
   __syncthreads();
+  if (!(phase & 2)) return;
   // ---- write the CTA's factor: packed upper triangle (p1 state columns) + squared column norms
   const int p1 = P.p1;
   const int ntri = p1 * (p1 + 1) / 2;

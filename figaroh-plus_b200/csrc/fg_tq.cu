@@ -131,6 +131,7 @@ TqLaunch tq_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, co
     }
   }
   T.nsimple = nsimple;
+  for (int c = 0; c < 8; ++c) T.swz[c] = (unsigned char)tq_sw(c);
   // ---- forward pass: the joints that support a generated body, which must form chains hanging
   //      off the universe when walked in index order (parent = previously walked joint, or 0)
   std::vector<char> need(nj, 0);
@@ -158,7 +159,7 @@ TqLaunch tq_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, co
     for (int k = 0; k < 10; ++k) has = has || T.islot[b][k] >= 0;
     T.anc[b] = has ? (unsigned char)m : 0;
   }
-  T.scratch_doubles = std::max(nproc * 2 * TQ_S, 4 * 96 + 64 + 16);
+  T.scratch_doubles = std::max(nproc * 2 * TQ_S + nj * (int)(sizeof(DevJoint) / 8), 4 * 112);
   tl.smem = (T.tile_doubles + T.scratch_doubles) * 8;
   if (tl.smem > max_smem) { fail(why, "tile does not fit shared memory"); return tl; }
   tl.maxg = 0;
@@ -172,11 +173,11 @@ TqLaunch tq_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, co
 
 cudaError_t tq_launch(const TqLaunch& tl, const TqParams& prm, const double* q, const double* v, const double* a,
                       const double* tau, int64_t ld_tau, int64_t N, double* r_scratch, double* parts, int grid,
-                      cudaStream_t st) {
+                      int phase, cudaStream_t st) {
   auto kern = tl.maxg <= 6 ? tq_accumulate_kernel<6> : tq_accumulate_kernel<8>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tl.smem);
   if (e != cudaSuccess) return e;
-  kern<<<grid, TQ_WARPS * 32, tl.smem, st>>>(prm, q, v, a, tau, ld_tau, N, r_scratch, tl.r_doubles, parts);
+  kern<<<grid, TQ_WARPS * 32, tl.smem, st>>>(prm, q, v, a, tau, ld_tau, N, r_scratch, tl.r_doubles, parts, phase);
   return cudaGetLastError();
 }
 

@@ -52,6 +52,7 @@ struct TqParams {
   unsigned trmask[TQ_MAXCB];        // column blocks updated by panel j
   short islot[TQ_MAXJ][10];         // (body, pinocchio parameter) -> slot, -1 = column not generated
   unsigned char anc[TQ_MAXJ];       // row groups whose joint supports body b
+  unsigned char swz[8];             // tq_sw(c)
   unsigned char ncols[TQ_MAXCB];    // real columns of block j
   unsigned char sc_blk[TQ_MAXP];    // state column -> column block
   unsigned char sc_c[TQ_MAXP];      // state column -> column inside the block
@@ -72,6 +73,8 @@ TqLaunch tq_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, co
 
 cudaError_t tq_launch(const TqLaunch& tl, const TqParams& prm, const double* q, const double* v, const double* a,
                       const double* tau, int64_t ld_tau, int64_t N, double* r_scratch, double* parts, int grid,
-                      cudaStream_t st);
+                      int phase, cudaStream_t st);
+
+enum { TQ_PHASE_FIRST = 1, TQ_PHASE_LAST = 2 };
 
 }  // namespace fg

@@ -2,7 +2,7 @@
 
 Samples are independent rows, so each rank folds its own shard into a local TsqrState
 with no data-path communication.  The only exchange is ONE all-gather of the packed
-per-GPU state ((p+1)^2 + p + 2 doubles: 58 KB for UR10) over NCCL / NVLink, after which
+per-GPU state ((p+1)^2 + 2(p+1) doubles: 45 KB for UR10's 73 folded columns) over NCCL / NVLink, after which
 every rank merges the G factors in rank order with the same kernel - deterministic and
 identical on all ranks (R^T R of the merged factor equals the global [W|tau]^T [W|tau]).
 """
@@ -39,6 +39,5 @@ def allgather_merge(local: TsqrState, merged: TsqrState | None = None, group=Non
         merged = TsqrState(local.p)
     else:
         merged.reset()
-    merged.set_perm(local.get_perm())  # packed factors are in the local kernel's column order
     merged.merge_packed(gathered, world)
     return merged

@@ -129,13 +129,15 @@ int fg_state_accumulate_samples(fg_state* s, const fg_model* m, const fg_regress
  * permutation P of its choosing (it eliminates the Ia/fv/fs/off columns, which are non-zero in one
  * row block only, before the inertial columns): state column i holds caller column perm[i].
  * fg_state_colsq / fg_state_reduce / fg_state_regroup_solve always speak caller columns; only the
- * packed exchange format below is in state order, so a state that receives packed factors must
- * carry the same perm (fg_state_set_perm on an empty state; identity after create / reset). */
+ * packed exchange format below is in state order (and carries perm with it); identity after
+ * create / reset. */
 int fg_state_get_perm(const fg_state* s, int32_t* perm_out /* host [p] */);
 int fg_state_set_perm(fg_state* s, const int32_t* perm /* host [p] */);
 
-/* Packed form for the multi-GPU exchange: (p+1)^2 doubles of R (row-major, zeros below
- * the diagonal, columns in state order), (p+1) squared column norms, then the row count as a double. */
+/* Packed form for the multi-GPU exchange: (p+1)^2 doubles of R (row-major, zeros below the
+ * diagonal, columns in state order), (p+1) squared column norms, the row count as a double, then the
+ * p entries of perm as doubles: (p+1)^2 + 2(p+1) doubles.  fg_state_merge_packed adopts the order of
+ * the packed factors when the state is empty and refuses factors in a different order otherwise. */
 int64_t fg_state_packed_doubles(int32_t p);
 int fg_state_export(const fg_state* s, double* packed_dev, void* stream);
 /* Merge `n` packed states (contiguous, n*fg_state_packed_doubles(p) doubles) into s,

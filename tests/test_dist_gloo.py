@@ -1,6 +1,7 @@
 """CPU, world_size 2 over gloo: the sharding + all-gather plumbing of the multi-GPU path.
 
-The exchange only moves packed per-rank states ((p+1)^2 + (p+1) + 1 doubles).  Here each
+The exchange only moves packed per-rank states ((p+1)^2 + 2(p+1) doubles: R, column norms,
+row count, column order).  Here each
 rank builds its packed state with the CPU oracle (numpy QR of its shard), the product's
 all-gather helper moves them, and the merged factor must reproduce the global index sets
 and OLS solution.  The CUDA merge kernel itself is covered by the -m gpu tests
@@ -23,7 +24,7 @@ def _pack(W, tau):
     R = np.linalg.qr(A, mode="r")
     Rfull = np.zeros((p + 1, p + 1))
     Rfull[:R.shape[0]] = R
-    return np.concatenate([Rfull.reshape(-1), (A * A).sum(0), [float(W.shape[0])]])
+    return np.concatenate([Rfull.reshape(-1), (A * A).sum(0), [float(W.shape[0])], np.arange(p, dtype=float)])
 
 
 def _worker(rank, world, port, q):
@@ -45,10 +46,11 @@ def _worker(rank, world, port, q):
         p1 = p + 1
         Rs = [allp[r, :p1 * p1].reshape(p1, p1) for r in range(world)]
         colsq = sum(allp[r, p1 * p1:p1 * p1 + p1] for r in range(world))
-        rows = sum(allp[r, -1] for r in range(world))
+        rows = sum(allp[r, p1 * p1 + p1] for r in range(world))
+        ok0 = all(np.array_equal(allp[r, p1 * p1 + p1 + 1:], np.arange(p)) for r in range(world))
         Rm = np.linalg.qr(np.vstack(Rs), mode="r")
         A = np.c_[W, tau]
-        ok = rows == M
+        ok = (rows == M) and ok0
         ok &= np.allclose(colsq, (A * A).sum(0), rtol=1e-12)
         ok &= np.allclose(Rm.T @ Rm, A.T @ A, rtol=1e-10, atol=1e-9)
         keep = [i for i in range(p) if colsq[i] >= 1e-6]

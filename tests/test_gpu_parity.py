@@ -150,7 +150,9 @@ def test_fused_structural_index_sets(name, structural_cases):
     # Margins: once a dependent column has been passed, the direction of its reflector is rounding
     # noise, so later |R_ii| are only reproducible to O(#dependent / rows) (see DESIGN.md "R is not
     # unique"); the classification is what must match, with the same order of magnitude of margin.
-    assert abs(d[d > 1e-8].min() / c["min_base_diag"] - 1) < 0.05
+    # (the fused kernel eliminates the friction / inertia / offset columns first, so its noise directions
+    # differ from LAPACK's: 10 % covers the O(#dependent / rows) spread at these small N)
+    assert abs(d[d > 1e-8].min() / c["min_base_diag"] - 1) < 0.10
     assert d[d <= 1e-8].max() < 1e-8
 
 

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for sym in sorted(declared):
         assert hasattr(L, sym), sym
     assert _lib.lib().fg_abi_version() == 1
-    assert _lib.lib().fg_state_packed_doubles(84) == 85 * 85 + 85 + 1
+    assert _lib.lib().fg_state_packed_doubles(84) == 85 * 85 + 2 * 85
 
 
 def test_no_cpu_fallback_without_gpu():
