@@ -14,6 +14,7 @@
 #include "fg_kernels.cuh"
 #include "fg_bq.h"
 #include "fg_tq.h"
+#include "fg_gq.h"
 
 using namespace fg;
 
@@ -49,6 +50,10 @@ struct DevPlan {
   bool tq_tried = false;
   TqLaunch tql;
   std::unique_ptr<TqParams> tq;
+  // fourth-generation kernel (fg_groupqr.cuh)
+  bool gq_tried = false;
+  GqLaunch gql;
+  std::unique_ptr<GqParams> gq;
   ~DevPlan() { if (d_blob) cudaFree(d_blob); }
 };
 
@@ -702,6 +707,44 @@ static int launch_tq(fg_state* s, fg_model* m, DevPlan* pl, const double* q, con
   return merge_parts_into_state(s, grid, m->max_smem, st);
 }
 
+// fourth-generation fused kernel (fg_groupqr.cuh): one independent TSQR stream per (warp, row group); the
+// per-leaf factors stay in the L2-resident scratch between the launches of a chunked caller and are merged
+// (tree per row group, then the roots into the full factor) by gq_merge on the last chunk.
+static int launch_gq(fg_state* s, fg_model* m, DevPlan* pl, const double* q, const double* v, const double* a,
+                     const double* tau, int64_t ld_tau, int64_t N, int phase, cudaStream_t st) {
+  const GqLaunch& gl = pl->gql;
+  const int64_t ntiles = (N + GQ_S - 1) / GQ_S;
+  const bool whole = phase == (TQ_PHASE_FIRST | TQ_PHASE_LAST);
+  const int leaves = whole ? (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, gl.leaves)) : gl.leaves;
+  const int64_t r_doubles = (int64_t)leaves * gl.r_leaf_doubles;
+  const int64_t cnt_doubles = ((int64_t)GQ_MAXG * leaves + 2) / 2 + 1;
+  const int64_t need = r_doubles + gl.rfull_doubles + cnt_doubles;
+  int rc;
+  if (phase & TQ_PHASE_FIRST) {
+    rc = ensure_gR(s, need);
+    if (rc) return rc;
+  } else if (s->gR_cap < need) {
+    return set_err(FG_ERR_INVALID, "internal: continued launch without a first one");
+  }
+  rc = ensure_parts(s, 2);
+  if (rc) return rc;
+  rc = timing_begin(s, st);
+  if (rc) return rc;
+  cudaError_t e = gq_launch(gl, *pl->gq, q, v, a, tau, ld_tau, N, s->d_gR, leaves, (phase & TQ_PHASE_FIRST) ? 1 : 0, st);
+  rc = timing_end(s, st);
+  if (rc) return rc;
+  if (e != cudaSuccess) return set_err(FG_ERR_CUDA, "gq_launch failed: %s", cudaGetErrorString(e));
+  FG_LAUNCHED();
+  s->rows += N * pl->P.ms;
+  if (!(phase & TQ_PHASE_LAST)) return FG_OK;
+  double* rfull = s->d_gR + r_doubles;
+  unsigned* counters = reinterpret_cast<unsigned*>(rfull + gl.rfull_doubles);
+  e = gq_merge(gl, *pl->gq, s->d_gR, leaves, counters, rfull, s->d_parts, st);
+  if (e != cudaSuccess) return set_err(FG_ERR_CUDA, "gq_merge failed: %s", cudaGetErrorString(e));
+  FG_LAUNCHED();
+  return merge_parts_into_state(s, 1, m->max_smem, st);
+}
+
 static int accumulate_samples_dev(fg_state* s, fg_model* m, const fg_regressor_cfg* cfg, const double* q,
                                   const double* v, const double* a, const double* tau, int64_t ld_tau, int64_t N,
                                   cudaStream_t st, int phase = TQ_PHASE_FIRST | TQ_PHASE_LAST, bool* chunkable = nullptr) {
@@ -713,6 +756,22 @@ static int accumulate_samples_dev(fg_state* s, fg_model* m, const fg_regressor_c
   if (N <= 0) return FG_OK;
   if (tau && ld_tau < N) return set_err(FG_ERR_INVALID, "ld_tau=%lld smaller than N=%lld", (long long)ld_tau, (long long)N);
   const int ms = pl->P.ms, nslot = (pl->P.p1 + 31) / 32;
+  {
+    const char* e = getenv("FG_USE_GQ");
+    const bool use_gq = !(e && e[0] == '0');
+    if (use_gq && !pl->gq_tried) {
+      pl->gq_tried = true;
+      pl->gq.reset(new GqParams);
+      const char* why = "";
+      pl->gql = gq_build(pl->P, m->joints.data(), pl->rows.data(), pl->cols.data(), m->sm_count, m->max_smem,
+                         pl->gq.get(), &why);
+      if (!pl->gql.ok) pl->gq.reset();
+    }
+    if (use_gq && pl->gql.ok && s->perm.empty()) {
+      if (chunkable) *chunkable = true;
+      return launch_gq(s, m, pl, q, v, a, tau, ld_tau, N, phase, st);
+    }
+  }
   {
     const char* e = getenv("FG_USE_TQ");
     const bool use_tq = !(e && e[0] == '0');

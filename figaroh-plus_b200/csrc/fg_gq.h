@@ -1,0 +1,89 @@
+// fg_gq.h - host interface and launch parameters of the fourth-generation fused kernel
+// (fg_groupqr.cuh): one independent Householder TSQR stream per (warp, row group).
+//
+// The regressor of row group g (the rows S_g^T B of joint g, regressor.py:49-70 of the reference) is
+// non-zero only in the columns of the bodies that joint supports plus the joint's own Ia/fv/fs/off
+// columns.  Rows of different row groups are different rows of W, so
+//     W^T W = sum_g W_g^T W_g      and      R = qr([R_0; R_1; ...; R_{ms-1}])
+// where R_g is the factor of the w_g non-zero columns of row group g alone.  Every R_g is an
+// ordinary dense TSQR with no fill-in from the other row groups: 2 sum_g w_g^2 flop per sample
+// (UR10: 19.6 k) instead of 2 m_s p^2 (65.7 k), and m_s independent streams instead of one.
+#pragma once
+#include <cstdint>
+#include <vector>
+#include <cuda_runtime.h>
+
+#include "fg_device.cuh"
+
+namespace fg {
+
+constexpr int GQ_S = 32;         // samples (= rows) of one tile: one row per lane
+constexpr int GQ_ROLES = 4;      // warps with different row-group lists that share a leaf index
+constexpr int GQ_MAXJ = 32;      // joints incl. universe
+constexpr int GQ_MAXG = 8;       // row groups per sample
+constexpr int GQ_MAXB = 12;      // 8-column blocks of one row group's local problem (and of the full factor)
+constexpr int GQ_MAXW = 8 * GQ_MAXB;
+constexpr int GQ_MAXSIMPLE = 16; // input-fed columns (friction / inertia / offset / coupling / rhs) per row group
+constexpr int GQ_BLK = 8 * GQ_S; // doubles of one tile block (8 columns x 32 rows)
+constexpr int GQ_SCRATCH = 64 + 64 + 64 + 16;  // T, diagonal block in / out, taus
+
+struct GqSimple {
+  short kind;   // COL_EXTRA / COL_COUPLING / COL_RHS
+  short src;    // ExtraSrc, or the coupling column 0..2
+  short vidx;   // velocity index of the source
+  short slot;   // (local block << 3) | column inside the block
+};
+
+struct GqGroup {
+  int nb;        // local 8-column blocks (the rhs is the last real column)
+  int w;         // real local columns incl. the rhs
+  int r_off;     // offset (doubles) of this group's block-triangular factor inside a leaf's scratch
+  int joint;     // joint whose motion axis the rows project on
+  int rowblock;  // reference row-block index (add_coupling_TX40 addresses rows by it)
+  int nsimple;
+  double S[6];   // motion axis in the joint frame [lin; ang]
+};
+
+// Passed by value as a __grid_constant__ kernel parameter: read through the constant cache with
+// warp-uniform addresses.
+struct GqParams {
+  int nj, nq, nv, ms;
+  int nproc;            // joints walked by the forward pass
+  int p1;               // state columns incl. the rhs
+  int nbf;              // 8-column blocks of the full factor
+  int maxnb;            // largest local block count
+  int r_leaf_doubles;   // scratch doubles of one leaf (all row groups)
+  int role_n[GQ_ROLES];
+  int role_g[GQ_ROLES][GQ_MAXG];
+  double gravity[3];
+  DevJoint joints[GQ_MAXJ];
+  int proc[GQ_MAXJ];
+  unsigned char anc[GQ_MAXJ];          // row groups whose joint supports body b (bodies with generated columns only)
+  GqGroup grp[GQ_MAXG];
+  short islot[GQ_MAXG][GQ_MAXJ][10];   // (row group, body, pinocchio parameter) -> local slot, -1 = not generated
+  GqSimple simple[GQ_MAXG][GQ_MAXSIMPLE];
+  unsigned char gcol[GQ_MAXG][GQ_MAXW]; // local column -> state column
+};
+
+struct GqLaunch {
+  bool ok = false;
+  int smem = 0;        // accumulate kernel, per warp
+  int smem_merge = 0;  // merge kernel, per warp
+  int leaves = 0;      // leaves of a full launch (grid = GQ_ROLES * leaves, one warp per CTA)
+  int64_t r_leaf_doubles = 0;
+  int64_t rfull_doubles = 0;
+};
+
+GqLaunch gq_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, const ColDesc* cols, int sm_count,
+                  int max_smem, GqParams* out, const char** why);
+
+// accumulate N samples into the per-leaf factors (scratch r_all, `leaves` leaves)
+cudaError_t gq_launch(const GqLaunch& gl, const GqParams& prm, const double* q, const double* v, const double* a,
+                      const double* tau, int64_t ld_tau, int64_t N, double* r_all, int leaves, int first,
+                      cudaStream_t st);
+// tree-merge the per-leaf factors of every row group, fold the roots into one full factor and write it as a
+// packed part (upper triangle + squared column norms) to part_out.  counters: GQ_MAXG * leaves + 1 unsigneds.
+cudaError_t gq_merge(const GqLaunch& gl, const GqParams& prm, double* r_all, int leaves, unsigned* counters,
+                     double* rfull, double* part_out, cudaStream_t st);
+
+}  // namespace fg

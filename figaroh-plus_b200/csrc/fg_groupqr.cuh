@@ -1,0 +1,500 @@
+// fg_groupqr.cuh - kernel (1)+(2), fourth generation: row-group streams.
+//
+// What the generation-3 profile showed (profiles/ncu_tq_r01_v3.md): 2 165 warp instructions per
+// sample at an issue rate of 24 %, the largest stall reason by far being the CTA barriers between
+// the one panel warp and its three workers - the panel chain of a tile that mixes all row groups is
+// serial, and every trailing update pays for the fill-in between row groups.
+//
+// This kernel removes both.  Rows of different row groups are different rows of W, hence
+// R = qr([R_0; ...; R_{ms-1}]) with R_g the factor of row group g's own non-zero columns (fg_gq.h).
+// A warp owns a static list of row groups (its "role") and, per tile of 32 samples and per row
+// group of its role:
+//   1. runs the forward pass with one sample per lane and writes that row group's entries
+//      s_g^T B_b (pinocchio::computeJointTorqueRegressor, reference call sites regressor.py:49,93)
+//      into its private 32 x w_g shared-memory tile,
+//   2. folds the tile into its private block-triangular R_g (L2-resident scratch) by a blocked
+//      Householder QR: 8-column panels with one row per lane, compact-WY T, DMMA trailing updates
+//      whose reflector fragments stay in registers for the whole panel.
+// No warp ever waits for another one: a CTA is a single warp, there is no barrier in the kernel.
+// The per-leaf factors are merged by gq_merge_kernel (pairwise tree per row group driven by arrival
+// counters, then the ms roots are folded into the full factor in state column order).
+#pragma once
+#include "fg_tileqr.cuh"
+#include "fg_gq.h"
+
+namespace fg {
+
+struct GqOffs {
+  int oc0[4], oc1[4];  // (rows 8nn + 2rq, +1; column cq): C fragments of a tile block, also A/B of the row contraction
+  int ob0[4], ob1[4];  // (row 8nn + cq; columns 2rq, 2rq + 1): V^T as B fragment of the update
+};
+__device__ __forceinline__ void gq_make_offs(GqOffs& o, int lane) {
+  const int cq = lane >> 2, rq = lane & 3;
+#pragma unroll
+  for (int nn = 0; nn < 4; ++nn) {
+    o.oc0[nn] = tq_idx(cq, 8 * nn + 2 * rq);
+    o.oc1[nn] = tq_idx(cq, 8 * nn + 2 * rq + 1);
+    o.ob0[nn] = tq_idx(2 * rq, 8 * nn + cq);
+    o.ob1[nn] = tq_idx(2 * rq + 1, 8 * nn + cq);
+  }
+}
+
+template <bool CG>
+__device__ __forceinline__ double gq_ld(const double* p) {
+  if (CG) return __ldcg(p);
+  return *p;
+}
+
+// Compact-WY factor from the register fragments of the normalised reflectors:
+// T^-1 = diag(1/tau) + striu(V^T V); V^T V is a DMMA whose A and B fragments are the same register
+// (the row contraction runs over the rows in fragment order).  sc[0..7]: taus; TS: T row-major.
+__device__ __forceinline__ void gq_panel_T(const double (&vc0)[4], const double (&vc1)[4], const double* sc, double* TS,
+                                           int lane) {
+  const int cq = lane >> 2, rq = lane & 3;
+  double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+#pragma unroll
+  for (int nn = 0; nn < 4; ++nn) {
+    tq_dmma(a0, a1, vc0[nn], vc0[nn]);
+    tq_dmma(b0, b1, vc1[nn], vc1[nn]);
+  }
+  a0 += b0;
+  a1 += b1;
+  if (2 * rq < cq) TS[cq * 8 + 2 * rq] = a0;
+  if (2 * rq + 1 < cq) TS[cq * 8 + 2 * rq + 1] = a1;
+  if (lane < 8) TS[lane * 8 + lane] = sc[lane];
+  __syncwarp();
+  double t[8];
+  if (lane < 8) {
+    double acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.0;
+#pragma unroll
+    for (int m = 7; m >= 0; --m) {
+      const double taum = TS[m * 8 + m];
+      const double tm = (m == lane) ? taum : (m < lane ? -taum * acc[m] : 0.0);
+      t[m] = tm;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < m) acc[i] = fma(TS[m * 8 + i], tm, acc[i]);
+    }
+  }
+  __syncwarp();
+  if (lane < 8) {
+#pragma unroll
+    for (int m = 0; m < 8; ++m) TS[m * 8 + lane] = t[m];
+  }
+  __syncwarp();
+}
+
+// Fold a 32-row tile (nb blocks of 8 columns, shared memory, blocks < k0 all zero) into the
+// block-upper-triangular factor Rg (nb (nb + 1) / 2 blocks of 8 x 8, row-major, global memory).
+template <bool CG>
+__device__ __forceinline__ void gq_fold(double* tile, int nb, double* Rg, int k0, double* scr, const GqOffs& o,
+                                        int lane) {
+  const int cq = lane >> 2, rq = lane & 3;
+  double* TS = scr;
+  double* Rin = scr + 64;
+  double* Rout = scr + 128;
+  double* sc = scr + 192;
+  double d0, d1;
+  {
+    const double* Rd = Rg + (size_t)tq_rblk(nb, k0, k0) * 64;
+    d0 = gq_ld<CG>(Rd + lane);
+    d1 = gq_ld<CG>(Rd + lane + 32);
+  }
+  for (int k = k0; k < nb; ++k) {
+    double* Rd = Rg + (size_t)tq_rblk(nb, k, k) * 64;
+    double* Xk = tile + k * GQ_BLK;
+    Rin[lane] = d0;
+    Rin[lane + 32] = d1;
+    double x[1][8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) x[0][c] = Xk[tq_idx(c, lane)];
+    __syncwarp();
+    tq_panel_factor<1, 8>(x, Rin, Rout, 8, sc, lane);
+    if ((lane >> 3) <= (lane & 7)) Rd[lane] = Rout[lane];            // rows 0..3 of the upper triangle
+    if ((lane >> 3) + 4 <= (lane & 7)) Rd[lane + 32] = Rout[lane + 32];  // rows 4..7
+    if (k + 1 == nb) break;
+    {  // the next diagonal block is only touched by the next panel: request it now
+      const double* Rn = Rg + (size_t)tq_rblk(nb, k + 1, k + 1) * 64;
+      d0 = gq_ld<CG>(Rn + lane);
+      d1 = gq_ld<CG>(Rn + lane + 32);
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) Xk[tq_idx(c, lane)] = x[0][c];
+    __syncwarp();
+    // reflector fragments of this panel, kept in registers for every trailing block
+    double vc0[4], vc1[4], vb0[4], vb1[4];
+#pragma unroll
+    for (int nn = 0; nn < 4; ++nn) {
+      vc0[nn] = Xk[o.oc0[nn]];
+      vc1[nn] = Xk[o.oc1[nn]];
+      vb0[nn] = Xk[o.ob0[nn]];
+      vb1[nn] = Xk[o.ob1[nn]];
+    }
+    gq_panel_T(vc0, vc1, sc, TS, lane);
+    const double t0 = TS[(2 * rq) * 8 + cq], t1 = TS[(2 * rq + 1) * 8 + cq];
+    double* Rb = Rg + (size_t)tq_rblk(nb, k, k + 1) * 64;
+    double r0 = gq_ld<CG>(Rb + (2 * rq) * 8 + cq), r1 = gq_ld<CG>(Rb + (2 * rq + 1) * 8 + cq);
+    for (int j = k + 1; j < nb; ++j, Rb += 64) {
+      double nr0 = 0.0, nr1 = 0.0;
+      if (j + 1 < nb) {  // R blocks of one block row are consecutive: request the next one a block ahead
+        nr0 = gq_ld<CG>(Rb + 64 + (2 * rq) * 8 + cq);
+        nr1 = gq_ld<CG>(Rb + 64 + (2 * rq + 1) * 8 + cq);
+      }
+      double* Bj = tile + j * GQ_BLK;
+      double c0[4], c1[4];
+#pragma unroll
+      for (int nn = 0; nn < 4; ++nn) { c0[nn] = Bj[o.oc0[nn]]; c1[nn] = Bj[o.oc1[nn]]; }
+      // Y^T = R_kj^T + B_j^T V   (rows contracted in fragment order: the C fragments are the A operands)
+      double y0 = 0.0, y1 = 0.0, z0 = 0.0, z1 = 0.0;
+#pragma unroll
+      for (int nn = 0; nn < 4; ++nn) {
+        tq_dmma(y0, y1, c0[nn], vc0[nn]);
+        tq_dmma(z0, z1, c1[nn], vc1[nn]);
+      }
+      y0 += z0 + r0;
+      y1 += z1 + r1;
+      // W^T = Y^T T
+      double w0 = 0.0, w1 = 0.0;
+      tq_dmma(w0, w1, y0, t0);
+      tq_dmma(w0, w1, y1, t1);
+      Rb[(2 * rq) * 8 + cq] = r0 - w0;
+      Rb[(2 * rq + 1) * 8 + cq] = r1 - w1;
+      const double nw0 = -w0, nw1 = -w1;
+      // B_j^T -= W^T V^T
+#pragma unroll
+      for (int nn = 0; nn < 4; ++nn) {
+        tq_dmma(c0[nn], c1[nn], nw0, vb0[nn]);
+        tq_dmma(c0[nn], c1[nn], nw1, vb1[nn]);
+        Bj[o.oc0[nn]] = c0[nn];
+        Bj[o.oc1[nn]] = c1[nn];
+      }
+      r0 = nr0;
+      r1 = nr1;
+    }
+    __syncwarp();
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+// regressor entries of (row group g, body): s = oM_body^-1 o A,  value[k] = s^T B[:, k]  (see tq_emit)
+__device__ __forceinline__ void gq_emit(const GqParams& P, double* tile, int g, int body, const double* A,
+                                        const double* oR, const double* op, const double* om, const double* al,
+                                        const double* ap, bool valid, int lane) {
+  double t[3], sl[3], sa[3];
+  cross3(op, A + 3, t);
+  for (int k = 0; k < 3; ++k) t[k] = A[k] - t[k];
+  for (int k = 0; k < 3; ++k) {
+    sl[k] = oR[k] * t[0] + oR[3 + k] * t[1] + oR[6 + k] * t[2];
+    sa[k] = oR[k] * A[3] + oR[3 + k] * A[4] + oR[6 + k] * A[5];
+  }
+  double val[10];
+  val[0] = sl[0] * ap[0] + sl[1] * ap[1] + sl[2] * ap[2];
+  const double ww = om[0] * om[0] + om[1] * om[1] + om[2] * om[2];
+  const double so = sl[0] * om[0] + sl[1] * om[1] + sl[2] * om[2];
+  double x1[3], x2[3], h[3];
+  cross3(sl, al, x1);
+  cross3(ap, sa, x2);
+  for (int j = 0; j < 3; ++j) val[1 + j] = x1[j] + so * om[j] - ww * sl[j] + x2[j];
+  cross3(sa, om, h);
+  val[4] = sa[0] * al[0] + h[0] * om[0];                                   // Ixx
+  val[5] = sa[0] * al[1] + sa[1] * al[0] + h[0] * om[1] + h[1] * om[0];   // Ixy
+  val[6] = sa[1] * al[1] + h[1] * om[1];                                   // Iyy
+  val[7] = sa[0] * al[2] + sa[2] * al[0] + h[0] * om[2] + h[2] * om[0];   // Ixz
+  val[8] = sa[1] * al[2] + sa[2] * al[1] + h[1] * om[2] + h[2] * om[1];   // Iyz
+  val[9] = sa[2] * al[2] + h[2] * om[2];                                   // Izz
+  if (valid) {
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+      const int slot = P.islot[g][body][k];
+      if (slot >= 0) tile[(slot >> 3) * GQ_BLK + tq_idx(slot & 7, lane)] = val[k];
+    }
+  }
+}
+
+// Forward pass of one sample per lane, emitting the entries of row group g.
+static __device__ __noinline__ void gq_generate(const GqParams& P, int g, double* tile, const double* __restrict__ q,
+                                         const double* __restrict__ qd, const double* __restrict__ qdd,
+                                         const double* __restrict__ tau, int64_t ld_tau, int64_t s0, int64_t N,
+                                         int lane) {
+  const int64_t smp = s0 + lane;
+  const bool valid = smp < N;
+  const int64_t sc = valid ? smp : N - 1;
+  const double* qs = q + sc * P.nq;
+  const double* vs = qd + sc * P.nv;
+  const double* as = qdd + sc * P.nv;
+  const GqGroup& G = P.grp[g];
+  double A[6] = {0, 0, 0, 0, 0, 0};
+  double oR[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, op[3] = {0, 0, 0};
+  double v[6] = {0, 0, 0, 0, 0, 0}, a[6] = {0, 0, 0, 0, 0, 0};
+  double nq0 = __ldg(qs + P.joints[P.proc[0]].idx_q), nv0 = __ldg(vs + P.joints[P.proc[0]].idx_v),
+         na0 = __ldg(as + P.joints[P.proc[0]].idx_v);
+  for (int t = 0; t < P.nproc; ++t) {
+    const int i = P.proc[t];
+    const DevJoint& jt = P.joints[i];
+    const double cq0 = nq0, cv0 = nv0, ca0 = na0;
+    if (t + 1 < P.nproc) {
+      const DevJoint& jn = P.joints[P.proc[t + 1]];
+      nq0 = __ldg(qs + jn.idx_q); nv0 = __ldg(vs + jn.idx_v); na0 = __ldg(as + jn.idx_v);
+    }
+    if (jt.parent == 0) {  // restart from the universe (the host only admits chains hanging off it)
+      oR[0] = 1; oR[1] = 0; oR[2] = 0; oR[3] = 0; oR[4] = 1; oR[5] = 0; oR[6] = 0; oR[7] = 0; oR[8] = 1;
+      op[0] = op[1] = op[2] = 0.0;
+      for (int k = 0; k < 6; ++k) v[k] = 0.0;
+      a[0] = -P.gravity[0]; a[1] = -P.gravity[1]; a[2] = -P.gravity[2];
+      a[3] = a[4] = a[5] = 0.0;
+    }
+    double Rj[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, pj[3] = {0, 0, 0};
+    double vj[6] = {0, 0, 0, 0, 0, 0}, aj[6] = {0, 0, 0, 0, 0, 0};
+    const int iq = jt.idx_q, iv = jt.idx_v;
+    if (jt.jtype == 1) {
+      double s, c;
+      sincos(cq0, &s, &c);
+      axis_rot(jt.axis, c, s, Rj);
+      for (int k = 0; k < 3; ++k) { vj[3 + k] = jt.axis[k] * cv0; aj[3 + k] = jt.axis[k] * ca0; }
+    } else if (jt.jtype == 2) {
+      axis_rot(jt.axis, cq0, __ldg(qs + iq + 1), Rj);
+      for (int k = 0; k < 3; ++k) { vj[3 + k] = jt.axis[k] * cv0; aj[3 + k] = jt.axis[k] * ca0; }
+    } else if (jt.jtype == 3) {
+      for (int k = 0; k < 3; ++k) { pj[k] = jt.axis[k] * cq0; vj[k] = jt.axis[k] * cv0; aj[k] = jt.axis[k] * ca0; }
+    } else {  // free-flyer
+      quat_rot(__ldg(qs + iq + 3), __ldg(qs + iq + 4), __ldg(qs + iq + 5), __ldg(qs + iq + 6), Rj);
+      for (int k = 0; k < 3; ++k) pj[k] = __ldg(qs + iq + k);
+      for (int k = 0; k < 6; ++k) { vj[k] = __ldg(vs + iv + k); aj[k] = __ldg(as + iv + k); }
+    }
+    // liMi = placement * Mj
+    double R[9], p[3];
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 3; ++c)
+        R[3 * r + c] = jt.plcR[3 * r] * Rj[c] + jt.plcR[3 * r + 1] * Rj[3 + c] + jt.plcR[3 * r + 2] * Rj[6 + c];
+      p[r] = jt.plcR[3 * r] * pj[0] + jt.plcR[3 * r + 1] * pj[1] + jt.plcR[3 * r + 2] * pj[2] + jt.plcp[r];
+    }
+    // v = vJ + liMi.actInv(v_parent);  a = v x vJ + S qdd + liMi.actInv(a_parent)
+    double vn[6], an[6], tt[3];
+    cross3(p, v + 3, tt);
+    for (int k = 0; k < 3; ++k) tt[k] = v[k] - tt[k];
+    for (int k = 0; k < 3; ++k) {
+      vn[k] = vj[k] + R[k] * tt[0] + R[3 + k] * tt[1] + R[6 + k] * tt[2];
+      vn[3 + k] = vj[3 + k] + R[k] * v[3] + R[3 + k] * v[4] + R[6 + k] * v[5];
+    }
+    double l1[3], l2[3], l3[3];
+    cross3(vn + 3, vj, l1);
+    cross3(vn, vj + 3, l2);
+    cross3(vn + 3, vj + 3, l3);
+    cross3(p, a + 3, tt);
+    for (int k = 0; k < 3; ++k) tt[k] = a[k] - tt[k];
+    for (int k = 0; k < 3; ++k) {
+      an[k] = l1[k] + l2[k] + aj[k] + R[k] * tt[0] + R[3 + k] * tt[1] + R[6 + k] * tt[2];
+      an[3 + k] = l3[k] + aj[3 + k] + R[k] * a[3] + R[3 + k] * a[4] + R[6 + k] * a[5];
+    }
+    // world pose oMi = oM_parent * liMi
+    double nR[9], np[3];
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 3; ++c) nR[3 * r + c] = oR[3 * r] * R[c] + oR[3 * r + 1] * R[3 + c] + oR[3 * r + 2] * R[6 + c];
+      np[r] = oR[3 * r] * p[0] + oR[3 * r + 1] * p[1] + oR[3 * r + 2] * p[2] + op[r];
+    }
+    for (int k = 0; k < 9; ++k) oR[k] = nR[k];
+    for (int k = 0; k < 3; ++k) op[k] = np[k];
+    for (int k = 0; k < 6; ++k) { v[k] = vn[k]; a[k] = an[k]; }
+    if (G.joint == i) {  // world-frame motion axis of the row group
+      for (int k = 0; k < 3; ++k) {
+        A[3 + k] = oR[3 * k] * G.S[3] + oR[3 * k + 1] * G.S[4] + oR[3 * k + 2] * G.S[5];
+        A[k] = oR[3 * k] * G.S[0] + oR[3 * k + 1] * G.S[1] + oR[3 * k + 2] * G.S[2];
+      }
+      cross3(op, A + 3, tt);
+      for (int k = 0; k < 3; ++k) A[k] += tt[k];
+    }
+    if ((P.anc[i] >> g) & 1u) {
+      double ap[3];
+      cross3(v + 3, v, ap);  // classical acceleration a' = a_lin + w x v_lin
+      for (int k = 0; k < 3; ++k) ap[k] += a[k];
+      gq_emit(P, tile, g, i, A, oR, op, v + 3, a + 3, ap, valid, lane);
+    }
+  }
+  // columns read straight off the inputs
+  for (int t = 0; t < G.nsimple; ++t) {
+    const GqSimple s1 = P.simple[g][t];
+    const int ix = (s1.slot >> 3) * GQ_BLK + tq_idx(s1.slot & 7, lane);
+    double val = 0.0;
+    if (s1.kind == COL_RHS) {
+      if (valid && tau != nullptr) val = __ldg(tau + (int64_t)g * ld_tau + smp);
+    } else if (s1.kind == COL_EXTRA) {
+      const double vv = __ldg(vs + s1.vidx), aa = __ldg(as + s1.vidx);
+      val = s1.src == SRC_QDD ? aa : (s1.src == SRC_QD ? vv : (s1.src == SRC_SIGN_QD ? sgn(vv) : 1.0));
+    } else {
+      // add_coupling_TX40 (regressor.py:216-225): row block 4 <- [a5, v5, sign(v4+v5)], 5 <- [a4, v4, sign(v4+v5)]
+      const double v4 = __ldg(vs + 4), v5 = __ldg(vs + 5), a4 = __ldg(as + 4), a5 = __ldg(as + 5);
+      const double sg = sgn(v4 + v5);
+      val = G.rowblock == 4 ? (s1.src == 0 ? a5 : (s1.src == 1 ? v5 : sg)) : (s1.src == 0 ? a4 : (s1.src == 1 ? v4 : sg));
+    }
+    tile[ix] = valid ? val : 0.0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32, 14)
+gq_accumulate_kernel(const __grid_constant__ GqParams P, const double* __restrict__ q, const double* __restrict__ qd,
+                     const double* __restrict__ qdd, const double* __restrict__ tau, int64_t ld_tau, int64_t N,
+                     double* __restrict__ r_all, int leaves, int first) {
+  extern __shared__ __align__(16) double gq_smem[];
+  const int lane = threadIdx.x;
+  const int role = blockIdx.x % GQ_ROLES, leaf = blockIdx.x / GQ_ROLES;
+  double* tile = gq_smem;
+  double* scr = gq_smem + P.maxnb * GQ_BLK;
+  double* Rleaf = r_all + (size_t)leaf * P.r_leaf_doubles;
+  const int ng = P.role_n[role];
+  if (first) {
+    for (int gi = 0; gi < ng; ++gi) {
+      const GqGroup& G = P.grp[P.role_g[role][gi]];
+      const int n = G.nb * (G.nb + 1) / 2 * 64;
+      for (int i = lane; i < n; i += 32) Rleaf[G.r_off + i] = 0.0;
+    }
+    __syncwarp();
+  }
+  GqOffs offs;
+  gq_make_offs(offs, lane);
+  const int64_t ntiles = (N + GQ_S - 1) / GQ_S;
+  for (int64_t tl = leaf; tl < ntiles; tl += leaves) {
+    for (int gi = 0; gi < ng; ++gi) {
+      const int g = P.role_g[role][gi];
+      const int nb = P.grp[g].nb;
+      {
+        double2* t2 = reinterpret_cast<double2*>(tile);
+        for (int i = lane; i < nb * (GQ_BLK / 2); i += 32) t2[i] = make_double2(0.0, 0.0);
+      }
+      __syncwarp();
+      gq_generate(P, g, tile, q, qd, qdd, tau, ld_tau, tl * GQ_S, N, lane);
+      __syncwarp();
+      gq_fold<false>(tile, nb, Rleaf + P.grp[g].r_off, 0, scr, offs, lane);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Merge of the per-leaf factors.  One warp per (row group g, pair of leaves).  A warp folds leaf i + stride
+// into leaf i, then climbs: at every internal node the first of the two children to arrive leaves, the second
+// one does the node's merge (always "right child into left child", so the result does not depend on who came
+// last).  The warp that completes the last row-group root folds the ms roots into the full factor.
+__device__ __forceinline__ void gq_merge_into(const GqParams& P, double* tile, int nb, double* Rdst, const double* Rsrc,
+                                              double* scr, const GqOffs& o, int lane) {
+  for (int t0 = 0; t0 < nb; t0 += 4) {
+    {
+      double2* t2 = reinterpret_cast<double2*>(tile);
+      for (int i = lane; i < nb * (GQ_BLK / 2); i += 32) t2[i] = make_double2(0.0, 0.0);
+    }
+    __syncwarp();
+    for (int m = 0; m < 4 && t0 + m < nb; ++m) {
+      const int rb = t0 + m;
+      for (int j = rb; j < nb; ++j) {
+        const double* B = Rsrc + (size_t)tq_rblk(nb, rb, j) * 64;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int e = lane + 32 * h, i = e >> 3, c = e & 7;
+          tile[j * GQ_BLK + tq_idx(c, 8 * m + i)] = __ldcg(B + e);
+        }
+      }
+    }
+    __syncwarp();
+    gq_fold<true>(tile, nb, Rdst, t0, scr, o, lane);
+  }
+}
+
+__global__ void __launch_bounds__(32)
+gq_merge_kernel(const __grid_constant__ GqParams P, double* __restrict__ r_all, int leaves, int npairs,
+                unsigned* __restrict__ counters, double* __restrict__ rfull, double* __restrict__ part_out) {
+  extern __shared__ __align__(16) double gq_smem[];
+  const int lane = threadIdx.x;
+  const int g = blockIdx.x / npairs;
+  int i = 2 * (blockIdx.x % npairs);
+  const int mb = P.maxnb > P.nbf ? P.maxnb : P.nbf;
+  double* tile = gq_smem;
+  double* scr = gq_smem + mb * GQ_BLK;
+  GqOffs offs;
+  gq_make_offs(offs, lane);
+  const GqGroup& G = P.grp[g];
+  const int nb = G.nb;
+  for (int stride = 1;; stride *= 2) {
+    if (i + stride < leaves)
+      gq_merge_into(P, tile, nb, r_all + (size_t)i * P.r_leaf_doubles + G.r_off,
+                    r_all + (size_t)(i + stride) * P.r_leaf_doubles + G.r_off, scr, offs, lane);
+    const int s2 = 2 * stride;
+    if (s2 >= leaves) break;  // i == 0: the root of this row group is complete
+    const int ip = i & ~(2 * s2 - 1);
+    const int sib = (i == ip) ? ip + s2 : ip;
+    if (sib < leaves) {
+      __threadfence();
+      __syncwarp();
+      unsigned old = 0;
+      if (lane == 0) old = atomicAdd(&counters[(size_t)g * leaves + ip + s2], 1u);
+      old = __shfl_sync(0xffffffffu, old, 0);
+      if (old == 0) return;
+      __threadfence();
+    }
+    i = ip;
+  }
+  // ---- root of row group g done
+  {
+    __threadfence();
+    __syncwarp();
+    unsigned old = 0;
+    if (lane == 0) old = atomicAdd(&counters[(size_t)GQ_MAXG * leaves], 1u);
+    old = __shfl_sync(0xffffffffu, old, 0);
+    if ((int)old != P.ms - 1) return;
+    __threadfence();
+  }
+  // ---- fold the roots (leaf 0 of every row group) into the full factor, state column order
+  const int nbf = P.nbf;
+  for (int idx = lane; idx < nbf * (nbf + 1) / 2 * 64; idx += 32) rfull[idx] = 0.0;
+  __syncwarp();
+  for (int gg = 0; gg < P.ms; ++gg) {
+    const GqGroup& H = P.grp[gg];
+    const double* Rsrc = r_all + H.r_off;
+    for (int t0 = 0; t0 < H.nb; t0 += 4) {
+      {
+        double2* t2 = reinterpret_cast<double2*>(tile);
+        for (int idx = lane; idx < nbf * (GQ_BLK / 2); idx += 32) t2[idx] = make_double2(0.0, 0.0);
+      }
+      __syncwarp();
+      int kmin = nbf - 1;
+      for (int m = 0; m < 4 && t0 + m < H.nb; ++m) {
+        const int rb = t0 + m;
+        for (int j = rb; j < H.nb; ++j) {
+          const double* B = Rsrc + (size_t)tq_rblk(H.nb, rb, j) * 64;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int e = lane + 32 * h, ii = e >> 3, c = e & 7;
+            const int l = 8 * j + c;
+            if (l < H.w) {
+              const int scol = P.gcol[gg][l];
+              tile[(scol >> 3) * GQ_BLK + tq_idx(scol & 7, 8 * m + ii)] = __ldcg(B + e);
+              kmin = min(kmin, scol >> 3);
+            }
+          }
+        }
+      }
+      kmin = __reduce_min_sync(0xffffffffu, kmin);
+      __syncwarp();
+      gq_fold<true>(tile, nbf, rfull, kmin, scr, offs, lane);
+    }
+  }
+  __syncwarp();
+  // ---- packed upper triangle + squared column norms
+  const int p1 = P.p1;
+  const int ntri = p1 * (p1 + 1) / 2;
+  for (int idx = lane; idx < p1 * p1; idx += 32) {
+    const int r = idx / p1, c = idx % p1;
+    if (c >= r) part_out[tri_off(r, p1) + c - r] = __ldcg(rfull + (size_t)tq_rblk(nbf, r >> 3, c >> 3) * 64 + (r & 7) * 8 + (c & 7));
+  }
+  for (int c = lane; c < p1; c += 32) {
+    double sacc = 0.0;
+    for (int r = 0; r <= c; ++r) {
+      const double x = __ldcg(rfull + (size_t)tq_rblk(nbf, r >> 3, c >> 3) * 64 + (r & 7) * 8 + (c & 7));
+      sacc = fma(x, x, sacc);
+    }
+    part_out[ntri + c] = sacc;
+  }
+}
+
+}  // namespace fg

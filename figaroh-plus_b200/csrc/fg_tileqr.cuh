@@ -109,7 +109,7 @@ __device__ __forceinline__ void tq_emit(const TqParams& P, double* tile, int g, 
 }
 
 // Forward pass of one sample per lane; warp w emits the row groups w and w + 4.
-__device__ __noinline__ void tq_generate(const TqParams& P, double* tile, const double* scr, const DevJoint* Js,
+static __device__ __noinline__ void tq_generate(const TqParams& P, double* tile, const double* scr, const DevJoint* Js,
                                          const double* __restrict__ q, const double* __restrict__ qd,
                                          const double* __restrict__ qdd, const double* __restrict__ tau,
                                          int64_t ld_tau, int64_t s0, int64_t N, int warp, int lane) {

@@ -9,6 +9,6 @@ timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpu
 cat gpurun_out/bench.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/launches_bench.log 2>&1; echo "ncu list rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:tq_accumulate -s 3 -c 1 -f -o gpurun_out/prof_tq \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --samples ${PROF_SAMPLES:-300000} > gpurun_out/prof_tq_bench.log 2>&1; echo "ncu full rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:gq_accumulate -s 3 -c 1 -f -o gpurun_out/prof_gq \
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --samples ${PROF_SAMPLES:-300000} > gpurun_out/prof_gq_bench.log 2>&1; echo "ncu full rc=$?"
 ls -la gpurun_out
