@@ -86,6 +86,94 @@ __device__ __forceinline__ void gq_panel_T(const double (&vc0)[4], const double 
   __syncwarp();
 }
 
+// ---------------------------------------------------------------------------------------------
+// sqrt(x) and 1/sqrt(x) of a normal positive double: MUFU seed (2^-22) + two coupled Newton steps
+__device__ __forceinline__ void gq_sqrt_rsqrt(double x, double& sq, double& rs) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double g = x * y, h = 0.5 * y;
+  double r = fma(-g, h, 0.5);
+  g = fma(g, r, g);
+  h = fma(h, r, h);
+  r = fma(-g, h, 0.5);
+  sq = fma(g, r, g);
+  rs = 2.0 * fma(h, r, h);
+}
+__device__ __forceinline__ double gq_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+
+// Householder panel, one warp, one row per lane (x[c] = entry (row = lane, column c)) under the 8 x 8
+// diagonal block Rin (row-major, shared memory).  The 32-lane dot products of column j with the columns to
+// its right are reduced through shared memory instead of a 5-level shuffle butterfly per value: every lane
+// stores its partial products into Pb (8 values x 32 lanes, the panel's own tile block, free while the
+// panel sits in registers), lane (value = lane >> 2, part = lane & 3) adds 8 of them and a 2-level
+// butterfly over `part` finishes the sum; the 8 results go back through 8 doubles of scratch (sc[8..15]).
+// Rotating value c's row by 4c doubles and the read order by part >> 1 keeps both sides bank-conflict free.
+// On exit x holds the normalised reflectors v = x / (alpha - beta) (LAPACK dlarfg convention), Rout the
+// updated block (upper triangle), sc[0..7] the taus (0 for a skipped / padding column).
+__device__ __forceinline__ void gq_panel_factor(double (&x)[8], const double* Rin, double* Rout, double* sc, double* Pb,
+                                                int lane) {
+  const int ci = lane >> 2, part = lane & 3;
+  int rd[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) rd[k] = ci * 32 + ((8 * part + 2 * ((k + (part >> 1)) & 3) + 4 * ci) & 31);
+  double* dbuf = sc + 8;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+#pragma unroll
+    for (int c = j; c < 8; ++c) Pb[c * 32 + ((lane + 4 * c) & 31)] = x[j] * x[c];
+    __syncwarp();
+    double s;
+    {
+      const double2 p0 = *reinterpret_cast<const double2*>(Pb + rd[0]);
+      const double2 p1 = *reinterpret_cast<const double2*>(Pb + rd[1]);
+      const double2 p2 = *reinterpret_cast<const double2*>(Pb + rd[2]);
+      const double2 p3 = *reinterpret_cast<const double2*>(Pb + rd[3]);
+      s = ((p0.x + p0.y) + (p1.x + p1.y)) + ((p2.x + p2.y) + (p3.x + p3.y));
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (part == 0) dbuf[ci] = s;
+    __syncwarp();
+    double d[8];
+#pragma unroll
+    for (int c = (j & ~1); c < 8; c += 2) {
+      const double2 t = *reinterpret_cast<const double2*>(dbuf + c);
+      d[c] = t.x;
+      d[c + 1] = t.y;
+    }
+    const double sigma = d[j];
+    const double alpha = Rin[j * 8 + j];
+    double beta = alpha, tauh = 0.0, inv = 0.0;
+    const double mu = fma(alpha, alpha, sigma);
+    if (sigma != 0.0 && mu > 1e-280) {  // uniform: every lane read the same d[j]
+      double nrm, rs;
+      gq_sqrt_rsqrt(mu, nrm, rs);
+      beta = alpha >= 0.0 ? -nrm : nrm;
+      const double den = alpha - beta;
+      inv = gq_rcp(den);
+      tauh = fabs(den) * rs;  // (beta - alpha) / beta
+    }
+    if (lane == 0) { Rout[j * 8 + j] = beta; sc[j] = tauh; }
+#pragma unroll
+    for (int c = j + 1; c < 8; ++c) {
+      const double rho = Rin[j * 8 + c];
+      const double w = tauh * fma(d[c], inv, rho);  // tau * v^T [rho; b]  (0 when the reflector is skipped)
+      const double coef = w * inv;
+      x[c] = fma(-coef, x[j], x[c]);
+      if (lane == 0) Rout[j * 8 + c] = rho - w;
+    }
+    x[j] *= inv;  // H = I (dlarfg with xnorm == 0) leaves v = 0
+  }
+  __syncwarp();
+}
+
 // Fold a 32-row tile (nb blocks of 8 columns, shared memory, blocks < k0 all zero) into the
 // block-upper-triangular factor Rg (nb (nb + 1) / 2 blocks of 8 x 8, row-major, global memory).
 template <bool CG>
@@ -107,11 +195,11 @@ __device__ __forceinline__ void gq_fold(double* tile, int nb, double* Rg, int k0
     double* Xk = tile + k * GQ_BLK;
     Rin[lane] = d0;
     Rin[lane + 32] = d1;
-    double x[1][8];
+    double x[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) x[0][c] = Xk[tq_idx(c, lane)];
+    for (int c = 0; c < 8; ++c) x[c] = Xk[tq_idx(c, lane)];
     __syncwarp();
-    tq_panel_factor<1, 8>(x, Rin, Rout, 8, sc, lane);
+    gq_panel_factor(x, Rin, Rout, sc, Xk, lane);
     if ((lane >> 3) <= (lane & 7)) Rd[lane] = Rout[lane];            // rows 0..3 of the upper triangle
     if ((lane >> 3) + 4 <= (lane & 7)) Rd[lane + 32] = Rout[lane + 32];  // rows 4..7
     if (k + 1 == nb) break;
@@ -121,7 +209,7 @@ __device__ __forceinline__ void gq_fold(double* tile, int nb, double* Rg, int k0
       d1 = gq_ld<CG>(Rn + lane + 32);
     }
 #pragma unroll
-    for (int c = 0; c < 8; ++c) Xk[tq_idx(c, lane)] = x[0][c];
+    for (int c = 0; c < 8; ++c) Xk[tq_idx(c, lane)] = x[c];
     __syncwarp();
     // reflector fragments of this panel, kept in registers for every trailing block
     double vc0[4], vc1[4], vb0[4], vb1[4];
