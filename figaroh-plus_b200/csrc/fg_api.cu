@@ -713,9 +713,8 @@ static int launch_tq(fg_state* s, fg_model* m, DevPlan* pl, const double* q, con
 static int launch_gq(fg_state* s, fg_model* m, DevPlan* pl, const double* q, const double* v, const double* a,
                      const double* tau, int64_t ld_tau, int64_t N, int phase, cudaStream_t st) {
   const GqLaunch& gl = pl->gql;
-  const int64_t ntiles = (N + GQ_S - 1) / GQ_S;
   const bool whole = phase == (TQ_PHASE_FIRST | TQ_PHASE_LAST);
-  const int leaves = whole ? (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, gl.leaves)) : gl.leaves;
+  const int leaves = gq_leaves_for(gl, N, whole);
   const int64_t r_doubles = (int64_t)leaves * gl.r_leaf_doubles;
   const int64_t cnt_doubles = ((int64_t)GQ_MAXG * leaves + 2) / 2 + 1;
   const int64_t need = r_doubles + gl.rfull_doubles + cnt_doubles;
@@ -1011,7 +1010,8 @@ extern "C" int fg_state_regroup_solve(fg_state* s, const int32_t* base, int32_t 
   int rc = run_small_qr(s->d_A, n, n, s->d_idx + n, st);
   if (rc) return rc;
   const int nrhs = ng + 1;
-  upper_solve_kernel<<<(nrhs + 63) / 64, 64, 0, st>>>(s->d_A, n, nb, nrhs, s->d_X);
+  if (nb <= 32 * US_M) upper_solve_kernel<<<(nrhs + 3) / 4, 128, 0, st>>>(s->d_A, n, nb, nrhs, s->d_X);
+  else upper_solve_serial_kernel<<<(nrhs + 63) / 64, 64, 0, st>>>(s->d_A, n, nb, nrhs, s->d_X);
   FG_CUDA(cudaGetLastError());
   FG_LAUNCHED();
   std::vector<double> X((size_t)nb * nrhs), Rg((size_t)n * n);

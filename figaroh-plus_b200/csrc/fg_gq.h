@@ -26,6 +26,8 @@ constexpr int GQ_MAXW = 8 * GQ_MAXB;
 constexpr int GQ_MAXSIMPLE = 16; // input-fed columns (friction / inertia / offset / coupling / rhs) per row group
 constexpr int GQ_BLK = 8 * GQ_S; // doubles of one tile block (8 columns x 32 rows)
 constexpr int GQ_SCRATCH = 64 + 64 + 64 + 16;  // T, diagonal block in / out, taus
+constexpr int GQ_MAXPROC = 12;   // joints walked by the forward pass
+constexpr int GQ_MAXNW = 14;     // warps (independent streams) of one CTA; one CTA per SM
 
 struct GqSimple {
   short kind;   // COL_EXTRA / COL_COUPLING / COL_RHS
@@ -39,9 +41,19 @@ struct GqGroup {
   int w;         // real local columns incl. the rhs
   int r_off;     // offset (doubles) of this group's block-triangular factor inside a leaf's scratch
   int joint;     // joint whose motion axis the rows project on
+  int tjoint;    // its position in the forward walk
   int rowblock;  // reference row-block index (add_coupling_TX40 addresses rows by it)
   int nsimple;
   double S[6];   // motion axis in the joint frame [lin; ang]
+};
+
+// What the regressor generator reads per joint / per column: copied to shared memory once per CTA (indexed
+// constant-bank loads miss the small constant L1 when 14 warps walk different parts of it).
+struct GqGen {
+  DevJoint pj[GQ_MAXPROC];             // joints in walk order
+  int emit[GQ_MAXG][GQ_MAXPROC];       // (first local slot << 10) | mask of generated pinocchio parameters; 0 = none
+  GqGroup grp[GQ_MAXG];
+  GqSimple simple[GQ_MAXG][GQ_MAXSIMPLE];
 };
 
 // Passed by value as a __grid_constant__ kernel parameter: read through the constant cache with
@@ -56,20 +68,17 @@ struct GqParams {
   int role_n[GQ_ROLES];
   int role_g[GQ_ROLES][GQ_MAXG];
   double gravity[3];
-  DevJoint joints[GQ_MAXJ];
-  int proc[GQ_MAXJ];
-  unsigned char anc[GQ_MAXJ];          // row groups whose joint supports body b (bodies with generated columns only)
-  GqGroup grp[GQ_MAXG];
-  short islot[GQ_MAXG][GQ_MAXJ][10];   // (row group, body, pinocchio parameter) -> local slot, -1 = not generated
-  GqSimple simple[GQ_MAXG][GQ_MAXSIMPLE];
+  GqGen gen;
   unsigned char gcol[GQ_MAXG][GQ_MAXW]; // local column -> state column
 };
 
 struct GqLaunch {
   bool ok = false;
-  int smem = 0;        // accumulate kernel, per warp
+  int smem_warp = 0;   // accumulate kernel, bytes per warp (tile + scratch)
+  int nw = 0;          // warps per CTA
   int smem_merge = 0;  // merge kernel, per warp
-  int leaves = 0;      // leaves of a full launch (grid = GQ_ROLES * leaves, one warp per CTA)
+  int sm_count = 0;
+  int leaves = 0;      // leaves of a full launch (4 warps - one per role - share a leaf index)
   int64_t r_leaf_doubles = 0;
   int64_t rfull_doubles = 0;
 };
@@ -81,8 +90,10 @@ GqLaunch gq_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, co
 cudaError_t gq_launch(const GqLaunch& gl, const GqParams& prm, const double* q, const double* v, const double* a,
                       const double* tau, int64_t ld_tau, int64_t N, double* r_all, int leaves, int first,
                       cudaStream_t st);
+// leaves a launch over N samples uses (a whole number of CTAs)
+int gq_leaves_for(const GqLaunch& gl, int64_t N, bool whole);
 // tree-merge the per-leaf factors of every row group, fold the roots into one full factor and write it as a
-// packed part (upper triangle + squared column norms) to part_out.  counters: GQ_MAXG * leaves + 1 unsigneds.
+// packed part (upper triangle + squared column norms) to part_out.  counters: GQ_MAXG * leaves + 2 unsigneds.
 cudaError_t gq_merge(const GqLaunch& gl, const GqParams& prm, double* r_all, int leaves, unsigned* counters,
                      double* rfull, double* part_out, cudaStream_t st);
 

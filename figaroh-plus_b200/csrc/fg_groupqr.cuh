@@ -198,6 +198,10 @@ __device__ __forceinline__ void gq_fold(double* tile, int nb, double* Rg, int k0
     double x[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) x[c] = Xk[tq_idx(c, lane)];
+    // first off-diagonal block of this block row: requested before the panel so that its L2 round trip is hidden
+    double* Rb = Rd + 64;
+    double r0 = 0.0, r1 = 0.0;
+    if (k + 1 < nb) { r0 = gq_ld<CG>(Rb + (2 * rq) * 8 + cq); r1 = gq_ld<CG>(Rb + (2 * rq + 1) * 8 + cq); }
     __syncwarp();
     gq_panel_factor(x, Rin, Rout, sc, Xk, lane);
     if ((lane >> 3) <= (lane & 7)) Rd[lane] = Rout[lane];            // rows 0..3 of the upper triangle
@@ -222,8 +226,6 @@ __device__ __forceinline__ void gq_fold(double* tile, int nb, double* Rg, int k0
     }
     gq_panel_T(vc0, vc1, sc, TS, lane);
     const double t0 = TS[(2 * rq) * 8 + cq], t1 = TS[(2 * rq + 1) * 8 + cq];
-    double* Rb = Rg + (size_t)tq_rblk(nb, k, k + 1) * 64;
-    double r0 = gq_ld<CG>(Rb + (2 * rq) * 8 + cq), r1 = gq_ld<CG>(Rb + (2 * rq + 1) * 8 + cq);
     for (int j = k + 1; j < nb; ++j, Rb += 64) {
       double nr0 = 0.0, nr1 = 0.0;
       if (j + 1 < nb) {  // R blocks of one block row are consecutive: request the next one a block ahead
@@ -267,10 +269,11 @@ __device__ __forceinline__ void gq_fold(double* tile, int nb, double* Rg, int k0
 }
 
 // ---------------------------------------------------------------------------------------------
-// regressor entries of (row group g, body): s = oM_body^-1 o A,  value[k] = s^T B[:, k]  (see tq_emit)
-__device__ __forceinline__ void gq_emit(const GqParams& P, double* tile, int g, int body, const double* A,
-                                        const double* oR, const double* op, const double* om, const double* al,
-                                        const double* ap, bool valid, int lane) {
+// regressor entries of (row group g, body): s = oM_body^-1 o A,  value[k] = s^T B[:, k]  (see tq_emit).
+// ed = (first local slot << 10) | mask of the generated pinocchio parameters: the generated entries of one
+// body occupy consecutive local columns in parameter order.
+__device__ __forceinline__ void gq_emit(double* tile, int ed, const double* A, const double* oR, const double* op,
+                                        const double* om, const double* al, const double* ap, bool valid, int lane) {
   double t[3], sl[3], sa[3];
   cross3(op, A + 3, t);
   for (int k = 0; k < 3; ++k) t[k] = A[k] - t[k];
@@ -293,39 +296,43 @@ __device__ __forceinline__ void gq_emit(const GqParams& P, double* tile, int g, 
   val[7] = sa[0] * al[2] + sa[2] * al[0] + h[0] * om[2] + h[2] * om[0];   // Ixz
   val[8] = sa[1] * al[2] + sa[2] * al[1] + h[1] * om[2] + h[2] * om[1];   // Iyz
   val[9] = sa[2] * al[2] + h[2] * om[2];                                   // Izz
-  if (valid) {
+  int slot = ed >> 10;
 #pragma unroll
-    for (int k = 0; k < 10; ++k) {
-      const int slot = P.islot[g][body][k];
-      if (slot >= 0) tile[(slot >> 3) * GQ_BLK + tq_idx(slot & 7, lane)] = val[k];
+  for (int k = 0; k < 10; ++k) {
+    if ((ed >> k) & 1) {  // uniform
+      if (valid) tile[(slot >> 3) * GQ_BLK + tq_idx(slot & 7, lane)] = val[k];
+      ++slot;
     }
   }
 }
 
-// Forward pass of one sample per lane, emitting the entries of row group g.
-static __device__ __noinline__ void gq_generate(const GqParams& P, int g, double* tile, const double* __restrict__ q,
-                                         const double* __restrict__ qd, const double* __restrict__ qdd,
-                                         const double* __restrict__ tau, int64_t ld_tau, int64_t s0, int64_t N,
-                                         int lane) {
+// Forward pass of one sample per lane, emitting the entries of row group g.  S: the generator tables in
+// shared memory.  The (q, dq, ddq) entries of a joint are requested two joints ahead.
+static __device__ __forceinline__ void gq_generate(const GqParams& P, const GqGen& S, int g, double* tile,
+                                                   const double* __restrict__ q, const double* __restrict__ qd,
+                                                   const double* __restrict__ qdd, const double* __restrict__ tau,
+                                                   int64_t ld_tau, int64_t s0, int64_t N, int lane) {
   const int64_t smp = s0 + lane;
   const bool valid = smp < N;
   const int64_t sc = valid ? smp : N - 1;
   const double* qs = q + sc * P.nq;
   const double* vs = qd + sc * P.nv;
   const double* as = qdd + sc * P.nv;
-  const GqGroup& G = P.grp[g];
+  const GqGroup& G = S.grp[g];
+  const int nproc = P.nproc;
   double A[6] = {0, 0, 0, 0, 0, 0};
   double oR[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, op[3] = {0, 0, 0};
   double v[6] = {0, 0, 0, 0, 0, 0}, a[6] = {0, 0, 0, 0, 0, 0};
-  double nq0 = __ldg(qs + P.joints[P.proc[0]].idx_q), nv0 = __ldg(vs + P.joints[P.proc[0]].idx_v),
-         na0 = __ldg(as + P.joints[P.proc[0]].idx_v);
-  for (int t = 0; t < P.nproc; ++t) {
-    const int i = P.proc[t];
-    const DevJoint& jt = P.joints[i];
+  double nq0 = __ldg(qs + S.pj[0].idx_q), nv0 = __ldg(vs + S.pj[0].idx_v), na0 = __ldg(as + S.pj[0].idx_v);
+  double nq1 = 0.0, nv1 = 0.0, na1 = 0.0;
+  if (nproc > 1) { nq1 = __ldg(qs + S.pj[1].idx_q); nv1 = __ldg(vs + S.pj[1].idx_v); na1 = __ldg(as + S.pj[1].idx_v); }
+  for (int t = 0; t < nproc; ++t) {
+    const DevJoint& jt = S.pj[t];
     const double cq0 = nq0, cv0 = nv0, ca0 = na0;
-    if (t + 1 < P.nproc) {
-      const DevJoint& jn = P.joints[P.proc[t + 1]];
-      nq0 = __ldg(qs + jn.idx_q); nv0 = __ldg(vs + jn.idx_v); na0 = __ldg(as + jn.idx_v);
+    nq0 = nq1; nv0 = nv1; na0 = na1;
+    if (t + 2 < nproc) {
+      const DevJoint& jn = S.pj[t + 2];
+      nq1 = __ldg(qs + jn.idx_q); nv1 = __ldg(vs + jn.idx_v); na1 = __ldg(as + jn.idx_v);
     }
     if (jt.parent == 0) {  // restart from the universe (the host only admits chains hanging off it)
       oR[0] = 1; oR[1] = 0; oR[2] = 0; oR[3] = 0; oR[4] = 1; oR[5] = 0; oR[6] = 0; oR[7] = 0; oR[8] = 1;
@@ -337,16 +344,17 @@ static __device__ __noinline__ void gq_generate(const GqParams& P, int g, double
     double Rj[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, pj[3] = {0, 0, 0};
     double vj[6] = {0, 0, 0, 0, 0, 0}, aj[6] = {0, 0, 0, 0, 0, 0};
     const int iq = jt.idx_q, iv = jt.idx_v;
+    const double ax[3] = {jt.axis[0], jt.axis[1], jt.axis[2]};
     if (jt.jtype == 1) {
       double s, c;
       sincos(cq0, &s, &c);
-      axis_rot(jt.axis, c, s, Rj);
-      for (int k = 0; k < 3; ++k) { vj[3 + k] = jt.axis[k] * cv0; aj[3 + k] = jt.axis[k] * ca0; }
+      axis_rot(ax, c, s, Rj);
+      for (int k = 0; k < 3; ++k) { vj[3 + k] = ax[k] * cv0; aj[3 + k] = ax[k] * ca0; }
     } else if (jt.jtype == 2) {
-      axis_rot(jt.axis, cq0, __ldg(qs + iq + 1), Rj);
-      for (int k = 0; k < 3; ++k) { vj[3 + k] = jt.axis[k] * cv0; aj[3 + k] = jt.axis[k] * ca0; }
+      axis_rot(ax, cq0, __ldg(qs + iq + 1), Rj);
+      for (int k = 0; k < 3; ++k) { vj[3 + k] = ax[k] * cv0; aj[3 + k] = ax[k] * ca0; }
     } else if (jt.jtype == 3) {
-      for (int k = 0; k < 3; ++k) { pj[k] = jt.axis[k] * cq0; vj[k] = jt.axis[k] * cv0; aj[k] = jt.axis[k] * ca0; }
+      for (int k = 0; k < 3; ++k) { pj[k] = ax[k] * cq0; vj[k] = ax[k] * cv0; aj[k] = ax[k] * ca0; }
     } else {  // free-flyer
       quat_rot(__ldg(qs + iq + 3), __ldg(qs + iq + 4), __ldg(qs + iq + 5), __ldg(qs + iq + 6), Rj);
       for (int k = 0; k < 3; ++k) pj[k] = __ldg(qs + iq + k);
@@ -355,9 +363,9 @@ static __device__ __noinline__ void gq_generate(const GqParams& P, int g, double
     // liMi = placement * Mj
     double R[9], p[3];
     for (int r = 0; r < 3; ++r) {
-      for (int c = 0; c < 3; ++c)
-        R[3 * r + c] = jt.plcR[3 * r] * Rj[c] + jt.plcR[3 * r + 1] * Rj[3 + c] + jt.plcR[3 * r + 2] * Rj[6 + c];
-      p[r] = jt.plcR[3 * r] * pj[0] + jt.plcR[3 * r + 1] * pj[1] + jt.plcR[3 * r + 2] * pj[2] + jt.plcp[r];
+      const double m0 = jt.plcR[3 * r], m1 = jt.plcR[3 * r + 1], m2 = jt.plcR[3 * r + 2];
+      for (int c = 0; c < 3; ++c) R[3 * r + c] = m0 * Rj[c] + m1 * Rj[3 + c] + m2 * Rj[6 + c];
+      p[r] = m0 * pj[0] + m1 * pj[1] + m2 * pj[2] + jt.plcp[r];
     }
     // v = vJ + liMi.actInv(v_parent);  a = v x vJ + S qdd + liMi.actInv(a_parent)
     double vn[6], an[6], tt[3];
@@ -386,7 +394,7 @@ static __device__ __noinline__ void gq_generate(const GqParams& P, int g, double
     for (int k = 0; k < 9; ++k) oR[k] = nR[k];
     for (int k = 0; k < 3; ++k) op[k] = np[k];
     for (int k = 0; k < 6; ++k) { v[k] = vn[k]; a[k] = an[k]; }
-    if (G.joint == i) {  // world-frame motion axis of the row group
+    if (G.tjoint == t) {  // world-frame motion axis of the row group
       for (int k = 0; k < 3; ++k) {
         A[3 + k] = oR[3 * k] * G.S[3] + oR[3 * k + 1] * G.S[4] + oR[3 * k + 2] * G.S[5];
         A[k] = oR[3 * k] * G.S[0] + oR[3 * k + 1] * G.S[1] + oR[3 * k + 2] * G.S[2];
@@ -394,16 +402,17 @@ static __device__ __noinline__ void gq_generate(const GqParams& P, int g, double
       cross3(op, A + 3, tt);
       for (int k = 0; k < 3; ++k) A[k] += tt[k];
     }
-    if ((P.anc[i] >> g) & 1u) {
+    const int ed = S.emit[g][t];
+    if (ed) {
       double ap[3];
       cross3(v + 3, v, ap);  // classical acceleration a' = a_lin + w x v_lin
       for (int k = 0; k < 3; ++k) ap[k] += a[k];
-      gq_emit(P, tile, g, i, A, oR, op, v + 3, a + 3, ap, valid, lane);
+      gq_emit(tile, ed, A, oR, op, v + 3, a + 3, ap, valid, lane);
     }
   }
   // columns read straight off the inputs
   for (int t = 0; t < G.nsimple; ++t) {
-    const GqSimple s1 = P.simple[g][t];
+    const GqSimple s1 = S.simple[g][t];
     const int ix = (s1.slot >> 3) * GQ_BLK + tq_idx(s1.slot & 7, lane);
     double val = 0.0;
     if (s1.kind == COL_RHS) {
@@ -422,20 +431,34 @@ static __device__ __noinline__ void gq_generate(const GqParams& P, int g, double
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32, 14)
+// One CTA per SM, blockDim.x / 32 independent warps; the only CTA-wide synchronisation is the one after the
+// generator tables have been copied to shared memory.  Warp gw = blockIdx.x * nw + warp plays role gw % 4 for
+// leaf gw / 4.
+__global__ void __launch_bounds__(GQ_MAXNW * 32, 1)
 gq_accumulate_kernel(const __grid_constant__ GqParams P, const double* __restrict__ q, const double* __restrict__ qd,
                      const double* __restrict__ qdd, const double* __restrict__ tau, int64_t ld_tau, int64_t N,
                      double* __restrict__ r_all, int leaves, int first) {
   extern __shared__ __align__(16) double gq_smem[];
-  const int lane = threadIdx.x;
-  const int role = blockIdx.x % GQ_ROLES, leaf = blockIdx.x / GQ_ROLES;
-  double* tile = gq_smem;
-  double* scr = gq_smem + P.maxnb * GQ_BLK;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int wdoubles = P.maxnb * GQ_BLK + GQ_SCRATCH;
+  GqGen* Sg = reinterpret_cast<GqGen*>(gq_smem + (size_t)nw * wdoubles);
+  {
+    const int* src = reinterpret_cast<const int*>(&P.gen);
+    int* dst = reinterpret_cast<int*>(Sg);
+    for (int i = threadIdx.x; i < (int)(sizeof(GqGen) / 4); i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const GqGen& S = *Sg;
+  const int gw = blockIdx.x * nw + warp;
+  const int role = gw % GQ_ROLES, leaf = gw / GQ_ROLES;
+  if (leaf >= leaves) return;
+  double* tile = gq_smem + (size_t)warp * wdoubles;
+  double* scr = tile + P.maxnb * GQ_BLK;
   double* Rleaf = r_all + (size_t)leaf * P.r_leaf_doubles;
   const int ng = P.role_n[role];
   if (first) {
     for (int gi = 0; gi < ng; ++gi) {
-      const GqGroup& G = P.grp[P.role_g[role][gi]];
+      const GqGroup& G = S.grp[P.role_g[role][gi]];
       const int n = G.nb * (G.nb + 1) / 2 * 64;
       for (int i = lane; i < n; i += 32) Rleaf[G.r_off + i] = 0.0;
     }
@@ -445,17 +468,25 @@ gq_accumulate_kernel(const __grid_constant__ GqParams P, const double* __restric
   gq_make_offs(offs, lane);
   const int64_t ntiles = (N + GQ_S - 1) / GQ_S;
   for (int64_t tl = leaf; tl < ntiles; tl += leaves) {
+    if (tl + leaves < ntiles) {  // pull the next tile's inputs into L2 while this one is folded
+      const int64_t sn = (tl + leaves) * GQ_S + lane;
+      if (sn < N) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(q + sn * P.nq));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(qd + sn * P.nv));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(qdd + sn * P.nv));
+      }
+    }
     for (int gi = 0; gi < ng; ++gi) {
       const int g = P.role_g[role][gi];
-      const int nb = P.grp[g].nb;
+      const int nb = S.grp[g].nb;
       {
         double2* t2 = reinterpret_cast<double2*>(tile);
         for (int i = lane; i < nb * (GQ_BLK / 2); i += 32) t2[i] = make_double2(0.0, 0.0);
       }
       __syncwarp();
-      gq_generate(P, g, tile, q, qd, qdd, tau, ld_tau, tl * GQ_S, N, lane);
+      gq_generate(P, S, g, tile, q, qd, qdd, tau, ld_tau, tl * GQ_S, N, lane);
       __syncwarp();
-      gq_fold<false>(tile, nb, Rleaf + P.grp[g].r_off, 0, scr, offs, lane);
+      gq_fold<false>(tile, nb, Rleaf + S.grp[g].r_off, 0, scr, offs, lane);
     }
   }
 }
@@ -501,7 +532,7 @@ gq_merge_kernel(const __grid_constant__ GqParams P, double* __restrict__ r_all, 
   double* scr = gq_smem + mb * GQ_BLK;
   GqOffs offs;
   gq_make_offs(offs, lane);
-  const GqGroup& G = P.grp[g];
+  const GqGroup& G = P.gen.grp[g];
   const int nb = G.nb;
   for (int stride = 1;; stride *= 2) {
     if (i + stride < leaves)
@@ -522,22 +553,44 @@ gq_merge_kernel(const __grid_constant__ GqParams P, double* __restrict__ r_all, 
     }
     i = ip;
   }
-  // ---- root of row group g done
+  // ---- root of row group g done.  The roots are folded into the full factor in the fixed order ms-1, ..., 0
+  // (deterministic result) by whichever warp holds the BUSY bit of `fin`: a finishing root publishes its bit and,
+  // if nobody is busy, becomes the worker; the worker folds the next root in order as soon as its bit is there
+  // and otherwise releases BUSY (compare-and-swap against the value it examined, so a bit that arrives in
+  // between makes the release fail and is picked up).  No warp ever spins on another one.  The small row
+  // groups finish their trees first, so their folds overlap the trees of the large ones.
+  unsigned* fin = counters + (size_t)GQ_MAXG * leaves;
+  unsigned* nfolded = fin + 1;
+  const unsigned BUSY = 0x80000000u;
   {
     __threadfence();
     __syncwarp();
     unsigned old = 0;
-    if (lane == 0) old = atomicAdd(&counters[(size_t)GQ_MAXG * leaves], 1u);
+    if (lane == 0) old = atomicOr(fin, (1u << g) | BUSY);
     old = __shfl_sync(0xffffffffu, old, 0);
-    if ((int)old != P.ms - 1) return;
-    __threadfence();
+    if (old & BUSY) return;
   }
-  // ---- fold the roots (leaf 0 of every row group) into the full factor, state column order
   const int nbf = P.nbf;
-  for (int idx = lane; idx < nbf * (nbf + 1) / 2 * 64; idx += 32) rfull[idx] = 0.0;
-  __syncwarp();
-  for (int gg = 0; gg < P.ms; ++gg) {
-    const GqGroup& H = P.grp[gg];
+  for (;;) {
+    unsigned cur = 0, done = 0;
+    if (lane == 0) { cur = atomicOr(fin, 0u); done = atomicAdd(nfolded, 0u); }
+    cur = __shfl_sync(0xffffffffu, cur, 0);
+    done = __shfl_sync(0xffffffffu, done, 0);
+    __threadfence();
+    const int gg = P.ms - 1 - (int)done;
+    if (gg < 0) break;  // every root is in: write the result
+    if (!((cur >> gg) & 1u)) {
+      unsigned seen = 0;
+      if (lane == 0) seen = atomicCAS(fin, cur, cur & ~BUSY);
+      seen = __shfl_sync(0xffffffffu, seen, 0);
+      if (seen == cur) return;
+      continue;
+    }
+    if (done == 0) {
+      for (int idx = lane; idx < nbf * (nbf + 1) / 2 * 64; idx += 32) rfull[idx] = 0.0;
+      __syncwarp();
+    }
+    const GqGroup& H = P.gen.grp[gg];
     const double* Rsrc = r_all + H.r_off;
     for (int t0 = 0; t0 < H.nb; t0 += 4) {
       {
@@ -566,6 +619,10 @@ gq_merge_kernel(const __grid_constant__ GqParams P, double* __restrict__ r_all, 
       __syncwarp();
       gq_fold<true>(tile, nbf, rfull, kmin, scr, offs, lane);
     }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) atomicAdd(nfolded, 1u);
+    __syncwarp();
   }
   __syncwarp();
   // ---- packed upper triangle + squared column norms

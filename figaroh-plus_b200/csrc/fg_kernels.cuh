@@ -450,14 +450,52 @@ __global__ void __launch_bounds__(1024) small_qr_kernel(double* __restrict__ Ag,
 
 // Back substitution on the regrouped factor Rg ((nk+1) x (nk+1) dense, ld = ldr):
 //   X[:, j] = R1^-1 Rg[0:r, r + j]  for j in [0, nrhs)   (nrhs = n_regroup + 1, last = rhs)
-// X is r x nrhs row-major.  One thread per right-hand side.
-__global__ void upper_solve_kernel(const double* __restrict__ Rg, int ldr, int r, int nrhs, double* __restrict__ X) {
+// X is r x nrhs row-major.  One thread per right-hand side (any r).
+__global__ void upper_solve_serial_kernel(const double* __restrict__ Rg, int ldr, int r, int nrhs,
+                                          double* __restrict__ X) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= nrhs) return;
   for (int i = r - 1; i >= 0; --i) {
     double acc = Rg[(size_t)i * ldr + r + j];
     for (int k = i + 1; k < r; ++k) acc = fma(-Rg[(size_t)i * ldr + k], X[(size_t)k * nrhs + j], acc);
     X[(size_t)i * nrhs + j] = acc / Rg[(size_t)i * ldr + i];
+  }
+}
+
+// Same result, one WARP per right-hand side, column-oriented (r <= 128): lane l keeps b[l], b[l + 32], ...;
+// step i divides b_i by R_ii and every lane updates its own entries with column i of R1, which was requested
+// one step earlier.  r dependent steps of ~100 cycles instead of r^2 / 2 dependent global round trips.
+constexpr int US_M = 4;
+__global__ void __launch_bounds__(128) upper_solve_kernel(const double* __restrict__ Rg, int ldr, int r, int nrhs,
+                                                          double* __restrict__ X) {
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j >= nrhs) return;
+  double b[US_M], rc[US_M];
+#pragma unroll
+  for (int m = 0; m < US_M; ++m) {
+    const int k = lane + 32 * m;
+    b[m] = k < r ? Rg[(size_t)k * ldr + r + j] : 0.0;
+    rc[m] = k < r ? Rg[(size_t)k * ldr + (r - 1)] : 0.0;
+  }
+  for (int i = r - 1; i >= 0; --i) {
+    double rn[US_M];
+#pragma unroll
+    for (int m = 0; m < US_M; ++m) {
+      const int k = lane + 32 * m;
+      rn[m] = (i > 0 && k < i) ? Rg[(size_t)k * ldr + (i - 1)] : 0.0;
+    }
+    const int s = i >> 5;
+    const double bs = s == 0 ? b[0] : (s == 1 ? b[1] : (s == 2 ? b[2] : b[3]));
+    const double rs = s == 0 ? rc[0] : (s == 1 ? rc[1] : (s == 2 ? rc[2] : rc[3]));
+    const double xi = __shfl_sync(0xffffffffu, bs, i & 31) / __shfl_sync(0xffffffffu, rs, i & 31);
+    if (lane == 0) X[(size_t)i * nrhs + j] = xi;
+#pragma unroll
+    for (int m = 0; m < US_M; ++m) {
+      const int k = lane + 32 * m;
+      if (k < i) b[m] = fma(-rc[m], xi, b[m]);
+      rc[m] = rn[m];
+    }
   }
 }
 
