@@ -48,6 +48,16 @@ def fp64_peak_tflops():
         return 37.0, "nominal"
 
 
+def ncu_traffic(n):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed ncu
+    capture of this command at the same sample count (profiles/ncu_traffic_r01.json); None if there is none."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")))
+        return d["dram_bytes_per_launch"] if int(d["samples"]) == int(n) else None
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def std_params_and_names(om):
     from oracle import ref_path
     std = ref_path.standard_parameters(om, PARAM)
@@ -310,9 +320,9 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "pipe": "fp64 (DFMA panels + DMMA m8n8k4 trailing updates; tcgen05 has no fp64 mode)",
-                         "kernel": "tq_accumulate_kernel (sample-per-thread regressor + shared-memory tile QR, look-ahead panels, DMMA trailing updates)",
+                         "kernel": "gq_accumulate_kernel (one Householder TSQR stream per (warp, row group): sample-per-lane regressor rows into a 32 x w_g shared-memory tile, 8-column panels, DMMA trailing updates)",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "kernel_ms": kern_ms_avg, "kernel_share_of_step": kern_ms_avg / ms_step,
+                         "traffic": ncu_traffic(N), "kernel_ms": kern_ms_avg, "kernel_share_of_step": kern_ms_avg / ms_step,
                          "flops_per_sample": FLOPS_PER_SAMPLE, "peak_source": peak_src},
         }
         if not args.no_cpu_baseline and world == 1:

@@ -944,8 +944,8 @@ static int run_small_qr(double* A, int mrows, int n, const int* d_ext, cudaStrea
   int sm_count, max_smem;
   int rc = device_limits(&sm_count, &max_smem);
   if (rc) return rc;
-  int smem = (mrows * n + n) * 8, use_smem = 1;
-  if (smem > max_smem) { smem = n * 8; use_smem = 0; }
+  int smem = (mrows * n + n) * 8 + n * 4, use_smem = 1;
+  if (smem > max_smem) { smem = n * 8 + n * 4; use_smem = 0; }
   FG_CUDA(cudaFuncSetAttribute(small_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int threads = n <= 128 ? 128 : (n <= 256 ? 256 : 512);
   small_qr_kernel<<<1, threads, smem, st>>>(A, mrows, n, d_ext, use_smem);

@@ -25,9 +25,9 @@ constexpr int GQ_MAXB = 12;      // 8-column blocks of one row group's local pro
 constexpr int GQ_MAXW = 8 * GQ_MAXB;
 constexpr int GQ_MAXSIMPLE = 16; // input-fed columns (friction / inertia / offset / coupling / rhs) per row group
 constexpr int GQ_BLK = 8 * GQ_S; // doubles of one tile block (8 columns x 32 rows)
-constexpr int GQ_SCRATCH = 64 + 64 + 64 + 16;  // T, diagonal block in / out, taus
+constexpr int GQ_SCRATCH = 64 + 16;  // T / diagonal block (shared), taus + reduction results
 constexpr int GQ_MAXPROC = 12;   // joints walked by the forward pass
-constexpr int GQ_MAXNW = 14;     // warps (independent streams) of one CTA; one CTA per SM
+constexpr int GQ_MAXNW = 15;     // warps (independent streams) of one CTA; one CTA per SM
 
 struct GqSimple {
   short kind;   // COL_EXTRA / COL_COUPLING / COL_RHS

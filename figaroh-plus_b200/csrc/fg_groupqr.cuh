@@ -115,6 +115,7 @@ __device__ __forceinline__ double gq_rcp(double x) {
 // panel sits in registers), lane (value = lane >> 2, part = lane & 3) adds 8 of them and a 2-level
 // butterfly over `part` finishes the sum; the 8 results go back through 8 doubles of scratch (sc[8..15]).
 // Rotating value c's row by 4c doubles and the read order by part >> 1 keeps both sides bank-conflict free.
+// Rin and Rout may be the same 64 doubles (row j is stored only after every lane has read it).
 // On exit x holds the normalised reflectors v = x / (alpha - beta) (LAPACK dlarfg convention), Rout the
 // updated block (upper triangle), sc[0..7] the taus (0 for a skipped / padding column).
 __device__ __forceinline__ void gq_panel_factor(double (&x)[8], const double* Rin, double* Rout, double* sc, double* Pb,
@@ -124,11 +125,16 @@ __device__ __forceinline__ void gq_panel_factor(double (&x)[8], const double* Ri
 #pragma unroll
   for (int k = 0; k < 4; ++k) rd[k] = ci * 32 + ((8 * part + 2 * ((k + (part >> 1)) & 3) + 4 * ci) & 31);
   double* dbuf = sc + 8;
+  double rw[8];  // updated row j - 1 of the diagonal block (lane-uniform), stored once every lane has read it
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
 #pragma unroll
     for (int c = j; c < 8; ++c) Pb[c * 32 + ((lane + 4 * c) & 31)] = x[j] * x[c];
     __syncwarp();
+    if (j > 0 && lane == 0) {
+#pragma unroll
+      for (int c = j - 1; c < 8; ++c) Rout[(j - 1) * 8 + c] = rw[c];
+    }
     double s;
     {
       const double2 p0 = *reinterpret_cast<const double2*>(Pb + rd[0]);
@@ -160,17 +166,20 @@ __device__ __forceinline__ void gq_panel_factor(double (&x)[8], const double* Ri
       inv = gq_rcp(den);
       tauh = fabs(den) * rs;  // (beta - alpha) / beta
     }
-    if (lane == 0) { Rout[j * 8 + j] = beta; sc[j] = tauh; }
+    if (lane == 0) sc[j] = tauh;
+    rw[j] = beta;
 #pragma unroll
     for (int c = j + 1; c < 8; ++c) {
       const double rho = Rin[j * 8 + c];
       const double w = tauh * fma(d[c], inv, rho);  // tau * v^T [rho; b]  (0 when the reflector is skipped)
       const double coef = w * inv;
       x[c] = fma(-coef, x[j], x[c]);
-      if (lane == 0) Rout[j * 8 + c] = rho - w;
+      rw[c] = rho - w;
     }
     x[j] *= inv;  // H = I (dlarfg with xnorm == 0) leaves v = 0
   }
+  __syncwarp();
+  if (lane == 0) Rout[63] = rw[7];
   __syncwarp();
 }
 
@@ -180,10 +189,10 @@ template <bool CG>
 __device__ __forceinline__ void gq_fold(double* tile, int nb, double* Rg, int k0, double* scr, const GqOffs& o,
                                         int lane) {
   const int cq = lane >> 2, rq = lane & 3;
-  double* TS = scr;
-  double* Rin = scr + 64;
-  double* Rout = scr + 128;
-  double* sc = scr + 192;
+  double* TS = scr;   // T of the panel: written after the diagonal block has gone back to global memory
+  double* Rin = scr;  // diagonal block, updated in place
+  double* Rout = scr;
+  double* sc = scr + 64;
   double d0, d1;
   {
     const double* Rd = Rg + (size_t)tq_rblk(nb, k0, k0) * 64;
@@ -506,14 +515,18 @@ __device__ __forceinline__ void gq_merge_into(const GqParams& P, double* tile, i
     __syncwarp();
     for (int m = 0; m < 4 && t0 + m < nb; ++m) {
       const int rb = t0 + m;
-      for (int j = rb; j < nb; ++j) {
-        const double* B = Rsrc + (size_t)tq_rblk(nb, rb, j) * 64;
+      // the blocks of one block row are consecutive: request all of them before the first one is stored
+      const double* B = Rsrc + (size_t)tq_rblk(nb, rb, rb) * 64;
+      double v0[GQ_MAXB], v1[GQ_MAXB];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int e = lane + 32 * h, i = e >> 3, c = e & 7;
-          tile[j * GQ_BLK + tq_idx(c, 8 * m + i)] = __ldcg(B + e);
+      for (int jj = 0; jj < GQ_MAXB; ++jj)
+        if (rb + jj < nb) { v0[jj] = __ldcg(B + jj * 64 + lane); v1[jj] = __ldcg(B + jj * 64 + 32 + lane); }
+#pragma unroll
+      for (int jj = 0; jj < GQ_MAXB; ++jj)
+        if (rb + jj < nb) {
+          tile[(rb + jj) * GQ_BLK + tq_idx(lane & 7, 8 * m + (lane >> 3))] = v0[jj];
+          tile[(rb + jj) * GQ_BLK + tq_idx(lane & 7, 8 * m + 4 + (lane >> 3))] = v1[jj];
         }
-      }
     }
     __syncwarp();
     gq_fold<true>(tile, nb, Rdst, t0, scr, o, lane);
@@ -601,17 +614,19 @@ gq_merge_kernel(const __grid_constant__ GqParams P, double* __restrict__ r_all, 
       int kmin = nbf - 1;
       for (int m = 0; m < 4 && t0 + m < H.nb; ++m) {
         const int rb = t0 + m;
-        for (int j = rb; j < H.nb; ++j) {
-          const double* B = Rsrc + (size_t)tq_rblk(H.nb, rb, j) * 64;
+        const double* B = Rsrc + (size_t)tq_rblk(H.nb, rb, rb) * 64;
+        double v0[GQ_MAXB], v1[GQ_MAXB];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int e = lane + 32 * h, ii = e >> 3, c = e & 7;
-            const int l = 8 * j + c;
-            if (l < H.w) {
-              const int scol = P.gcol[gg][l];
-              tile[(scol >> 3) * GQ_BLK + tq_idx(scol & 7, 8 * m + ii)] = __ldcg(B + e);
-              kmin = min(kmin, scol >> 3);
-            }
+        for (int jj = 0; jj < GQ_MAXB; ++jj)
+          if (rb + jj < H.nb) { v0[jj] = __ldcg(B + jj * 64 + lane); v1[jj] = __ldcg(B + jj * 64 + 32 + lane); }
+#pragma unroll
+        for (int jj = 0; jj < GQ_MAXB; ++jj) {
+          const int l = 8 * (rb + jj) + (lane & 7);
+          if (rb + jj < H.nb && l < H.w) {
+            const int scol = P.gcol[gg][l];
+            tile[(scol >> 3) * GQ_BLK + tq_idx(scol & 7, 8 * m + (lane >> 3))] = v0[jj];
+            tile[(scol >> 3) * GQ_BLK + tq_idx(scol & 7, 8 * m + 4 + (lane >> 3))] = v1[jj];
+            kmin = min(kmin, scol >> 3);
           }
         }
       }

@@ -408,11 +408,14 @@ __global__ void __launch_bounds__(1024) small_qr_kernel(double* __restrict__ Ag,
   } else {
     dg = reinterpret_cast<double*>(smem);
   }
+  // column extents in shared memory: a dependent global load per column would cost more than the column itself
+  int* exts = reinterpret_cast<int*>(dg + n);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) exts[i] = ext[i];
   __syncthreads();
   const int kmax = m < n ? m : n;
   int E = 0;
   for (int c = 0; c < kmax; ++c) {
-    const int e = ext[c] < m ? ext[c] : m;
+    const int e = exts[c] < m ? exts[c] : m;
     E = e > E ? e : E;
     if (E < c + 1) E = c + 1;
     const double alpha = A[(size_t)c * n + c];
