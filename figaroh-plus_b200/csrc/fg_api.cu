@@ -54,7 +54,8 @@ struct DevPlan {
   bool gq_tried = false;
   GqLaunch gql;
   std::unique_ptr<GqParams> gq;
-  ~DevPlan() { if (d_blob) cudaFree(d_blob); }
+  void* d_gq_tab = nullptr;  // warp -> (row group, instance) tables of the full launch
+  ~DevPlan() { if (d_blob) cudaFree(d_blob); if (d_gq_tab) cudaFree(d_gq_tab); }
 };
 
 struct fg_model {
@@ -712,12 +713,18 @@ static int launch_tq(fg_state* s, fg_model* m, DevPlan* pl, const double* q, con
 // (tree per row group, then the roots into the full factor) by gq_merge on the last chunk.
 static int launch_gq(fg_state* s, fg_model* m, DevPlan* pl, const double* q, const double* v, const double* a,
                      const double* tau, int64_t ld_tau, int64_t N, int phase, cudaStream_t st) {
-  const GqLaunch& gl = pl->gql;
+  GqLaunch& gl = pl->gql;
+  if (!pl->d_gq_tab) {
+    const size_t nb_i = gl.tab_i.size() * sizeof(unsigned short), nb_g = (gl.tab_g.size() + 15) / 16 * 16;
+    FG_CUDA(cudaMalloc(&pl->d_gq_tab, nb_g + nb_i));
+    FG_CUDA(cudaMemcpy(pl->d_gq_tab, gl.tab_g.data(), gl.tab_g.size(), cudaMemcpyHostToDevice));
+    FG_CUDA(cudaMemcpy(static_cast<char*>(pl->d_gq_tab) + nb_g, gl.tab_i.data(), nb_i, cudaMemcpyHostToDevice));
+    gl.d_tab_g = static_cast<const unsigned char*>(pl->d_gq_tab);
+    gl.d_tab_i = reinterpret_cast<const unsigned short*>(static_cast<char*>(pl->d_gq_tab) + nb_g);
+  }
   const bool whole = phase == (TQ_PHASE_FIRST | TQ_PHASE_LAST);
-  const int leaves = gq_leaves_for(gl, N, whole);
-  const int64_t r_doubles = (int64_t)leaves * gl.r_leaf_doubles;
-  const int64_t cnt_doubles = ((int64_t)GQ_MAXG * leaves + 2) / 2 + 1;
-  const int64_t need = r_doubles + gl.rfull_doubles + cnt_doubles;
+  const int64_t cnt_doubles = ((int64_t)GQ_MAXG * pl->gq->maxinst + 3) / 2 + 1;
+  const int64_t need = gl.r_doubles + gl.rfull_doubles + cnt_doubles;
   int rc;
   if (phase & TQ_PHASE_FIRST) {
     rc = ensure_gR(s, need);
@@ -729,16 +736,17 @@ static int launch_gq(fg_state* s, fg_model* m, DevPlan* pl, const double* q, con
   if (rc) return rc;
   rc = timing_begin(s, st);
   if (rc) return rc;
-  cudaError_t e = gq_launch(gl, *pl->gq, q, v, a, tau, ld_tau, N, s->d_gR, leaves, (phase & TQ_PHASE_FIRST) ? 1 : 0, st);
+  cudaError_t e = gq_launch(gl, *pl->gq, q, v, a, tau, ld_tau, N, s->d_gR, (phase & TQ_PHASE_FIRST) ? 1 : 0, st);
   rc = timing_end(s, st);
   if (rc) return rc;
   if (e != cudaSuccess) return set_err(FG_ERR_CUDA, "gq_launch failed: %s", cudaGetErrorString(e));
   FG_LAUNCHED();
   s->rows += N * pl->P.ms;
   if (!(phase & TQ_PHASE_LAST)) return FG_OK;
-  double* rfull = s->d_gR + r_doubles;
+  double* rfull = s->d_gR + gl.r_doubles;
   unsigned* counters = reinterpret_cast<unsigned*>(rfull + gl.rfull_doubles);
-  e = gq_merge(gl, *pl->gq, s->d_gR, leaves, counters, rfull, s->d_parts, st);
+  // a single launch over few tiles leaves the higher instances at zero: they are not merged
+  e = gq_merge(gl, *pl->gq, s->d_gR, whole ? (N + GQ_S - 1) / GQ_S : 0, counters, rfull, s->d_parts, st);
   if (e != cudaSuccess) return set_err(FG_ERR_CUDA, "gq_merge failed: %s", cudaGetErrorString(e));
   FG_LAUNCHED();
   return merge_parts_into_state(s, 1, m->max_smem, st);

@@ -65,7 +65,7 @@ GqLaunch gq_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, co
   T.nproc = nproc;
   // ---- the local problem of every row group: per walked body its selected inertial columns in pinocchio
   //      parameter order, then the input-fed columns in the caller's order, then the rhs
-  int r_off = 0, maxnb = 0;
+  int maxnb = 0;
   for (int g = 0; g < ms; ++g) {
     GqGroup& G = T.gen.grp[g];
     for (int k = 0; k < 6; ++k) G.S[k] = rows[g].S[k];
@@ -107,75 +107,119 @@ GqLaunch gq_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, co
     G.w = l;
     G.nb = (l + 7) / 8;
     G.nsimple = ns;
-    G.r_off = r_off;
-    r_off += G.nb * (G.nb + 1) / 2 * 64;
+    G.r_size = G.nb * (G.nb + 1) / 2 * 64;
     maxnb = std::max(maxnb, G.nb);
   }
   if (maxnb > GQ_MAXB || T.nbf > GQ_MAXB) { gq_fail(why, "more than 12 column blocks"); return gl; }
   T.maxnb = maxnb;
-  T.r_leaf_doubles = r_off;
-  // ---- roles: longest-processing-time assignment of the row groups to GQ_ROLES warps
-  {
-    std::vector<std::pair<double, int>> cost;
-    for (int g = 0; g < ms; ++g) {
-      const int nb = T.gen.grp[g].nb;
-      cost.push_back({3000.0 + 1600.0 * nb + 300.0 * nb * (nb - 1) / 2, g});
-    }
-    std::sort(cost.begin(), cost.end(), [](const std::pair<double, int>& a, const std::pair<double, int>& b) {
-      return a.first != b.first ? a.first > b.first : a.second < b.second;
-    });
-    double load[GQ_ROLES] = {0, 0, 0, 0};
-    for (auto& cg : cost) {
-      int best = 0;
-      for (int r = 1; r < GQ_ROLES; ++r)
-        if (load[r] < load[best]) best = r;
-      T.role_g[best][T.role_n[best]++] = cg.second;
-      load[best] += cg.first;
-    }
-  }
-  gl.smem_warp = (maxnb * GQ_BLK + GQ_SCRATCH) * 8;
   gl.smem_merge = (std::max(maxnb, T.nbf) * GQ_BLK + GQ_SCRATCH) * 8;
   if (gl.smem_merge > max_smem) { gq_fail(why, "tile does not fit shared memory"); return gl; }
-  gl.nw = std::min(GQ_MAXNW, (max_smem - (int)sizeof(GqGen)) / gl.smem_warp);
-  if (gl.nw < 1) { gq_fail(why, "tile does not fit shared memory"); return gl; }
+  // ---- warps per row group, proportional to the instruction cost of one tile of that group (forward pass,
+  //      one emit per supported body, nb panels + T factors, nb (nb - 1) / 2 trailing blocks; calibrated on
+  //      the per-line instruction counts of profiles/ncu_gq_r01_v4c.md)
+  std::vector<double> cost(ms);
+  double csum = 0.0;
+  for (int g = 0; g < ms; ++g) {
+    const GqGroup& G = T.gen.grp[g];
+    int emits = 0;
+    for (int t = 0; t < nproc; ++t) emits += T.gen.emit[g][t] != 0;
+    cost[g] = 700.0 + 400.0 * nproc + 233.0 * emits + 20.0 * G.nsimple + 1070.0 * G.nb + 100.0 * G.nb * (G.nb - 1) / 2;
+    csum += cost[g];
+  }
   gl.sm_count = std::max(1, sm_count);
-  gl.leaves = std::max(1, gl.sm_count * gl.nw / GQ_ROLES);
-  gl.r_leaf_doubles = r_off;
+  for (int nw = GQ_MAXNW; nw >= 1; --nw) {
+    const int W = gl.sm_count * nw;
+    if (W < ms) continue;
+    // largest-remainder apportionment, at least one warp per row group
+    std::vector<int> cnt(ms);
+    int left = W;
+    std::vector<std::pair<double, int>> rem;
+    for (int g = 0; g < ms; ++g) {
+      const double t = W * cost[g] / csum;
+      cnt[g] = std::max(1, (int)t);
+      left -= cnt[g];
+      rem.push_back({t - (int)t, g});
+    }
+    std::sort(rem.begin(), rem.end(), [](const std::pair<double, int>& a, const std::pair<double, int>& b) {
+      return a.first != b.first ? a.first > b.first : a.second < b.second;
+    });
+    for (int k = 0; left > 0; k = (k + 1) % ms, --left) ++cnt[rem[k].second];
+    for (int k = 0; left < 0; k = (k + 1) % ms)
+      if (cnt[rem[ms - 1 - k].second] > 1) { --cnt[rem[ms - 1 - k].second]; ++left; }
+    // interleave: position gw goes to the row group that is furthest behind its proportional schedule
+    gl.tab_g.assign(W, 0);
+    gl.tab_i.assign(W, 0);
+    std::vector<int> given(ms, 0);
+    int worst = 0;
+    for (int b = 0; b < gl.sm_count; ++b) {
+      int blocks = 0;
+      for (int w = 0; w < nw; ++w) {
+        const int gw = b * nw + w;
+        int best = -1;
+        double lag = -1e300;
+        for (int g = 0; g < ms; ++g) {
+          if (given[g] >= cnt[g]) continue;
+          const double l = (double)cnt[g] * (gw + 1) / W - given[g];
+          if (l > lag) { lag = l; best = g; }
+        }
+        gl.tab_g[gw] = (unsigned char)best;
+        gl.tab_i[gw] = (unsigned short)given[best]++;
+        blocks += T.gen.grp[best].nb;
+      }
+      worst = std::max(worst, blocks);
+    }
+    const int smem = (GQ_GEN_DOUBLES + worst * GQ_BLK + nw * GQ_SCRATCH) * 8;
+    if (smem > max_smem) continue;
+    gl.nw = nw;
+    gl.smem = smem;
+    int64_t off = 0;
+    int maxinst = 0;
+    for (int g = 0; g < ms; ++g) {
+      GqGroup& G = T.gen.grp[g];
+      G.ninst = cnt[g];
+      G.r_off = (int)off;
+      off += (int64_t)cnt[g] * G.r_size;
+      maxinst = std::max(maxinst, cnt[g]);
+    }
+    if (off > 0x7fffffff || maxinst > 65535) { gq_fail(why, "factor scratch too large"); return gl; }
+    T.maxinst = maxinst;
+    gl.r_doubles = off;
+    break;
+  }
+  if (gl.nw < 1) { gq_fail(why, "tile does not fit shared memory"); return gl; }
   gl.rfull_doubles = (int64_t)T.nbf * (T.nbf + 1) / 2 * 64;
   gl.ok = true;
   return gl;
 }
 
-static int gq_grid_for(const GqLaunch& gl, int64_t N, bool whole) {
-  if (!whole) return gl.sm_count;
-  const int64_t ntiles = std::max<int64_t>(1, (N + GQ_S - 1) / GQ_S);
-  const int64_t warps = std::min<int64_t>(ntiles, gl.leaves) * GQ_ROLES;
-  return (int)std::min<int64_t>(gl.sm_count, (warps + gl.nw - 1) / gl.nw);
-}
-
-int gq_leaves_for(const GqLaunch& gl, int64_t N, bool whole) {
-  return std::max(1, gq_grid_for(gl, N, whole) * gl.nw / GQ_ROLES);
-}
-
 cudaError_t gq_launch(const GqLaunch& gl, const GqParams& prm, const double* q, const double* v, const double* a,
-                      const double* tau, int64_t ld_tau, int64_t N, double* r_all, int leaves, int first,
-                      cudaStream_t st) {
-  const int smem = gl.nw * gl.smem_warp + (int)sizeof(GqGen);
-  cudaError_t e = cudaFuncSetAttribute(gq_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                      const double* tau, int64_t ld_tau, int64_t N, double* r_all, int first, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(gq_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gl.smem);
   if (e != cudaSuccess) return e;
-  const int grid = (leaves * GQ_ROLES + gl.nw - 1) / gl.nw;
-  gq_accumulate_kernel<<<grid, gl.nw * 32, smem, st>>>(prm, q, v, a, tau, ld_tau, N, r_all, leaves, first);
+  gq_accumulate_kernel<<<gl.sm_count, gl.nw * 32, gl.smem, st>>>(prm, gl.d_tab_g, gl.d_tab_i, q, v, a, tau, ld_tau, N,
+                                                                r_all, first);
   return cudaGetLastError();
 }
 
-cudaError_t gq_merge(const GqLaunch& gl, const GqParams& prm, double* r_all, int leaves, unsigned* counters,
+cudaError_t gq_merge(const GqLaunch& gl, const GqParams& prm, double* r_all, int64_t ntiles_hint, unsigned* counters,
                      double* rfull, double* part_out, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(gq_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gl.smem_merge);
   if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync(counters, 0, sizeof(unsigned) * ((size_t)GQ_MAXG * leaves + 2), st);
+  e = cudaMemsetAsync(counters, 0, sizeof(unsigned) * ((size_t)GQ_MAXG * prm.maxinst + 2), st);
   if (e != cudaSuccess) return e;
-  const int npairs = (leaves + 1) / 2;
-  gq_merge_kernel<<<prm.ms * npairs, 32, gl.smem_merge, st>>>(prm, r_all, leaves, npairs, counters, rfull, part_out);
+  GqMergeArgs M;
+  int blocks = 0;
+  for (int g = 0; g < GQ_MAXG; ++g) {
+    M.blk0[g] = blocks;
+    M.leaves[g] = 0;
+    if (g >= prm.ms) continue;
+    int leaves = prm.gen.grp[g].ninst;
+    if (ntiles_hint > 0) leaves = (int)std::max<int64_t>(1, std::min<int64_t>(leaves, ntiles_hint));
+    M.leaves[g] = leaves;
+    blocks += (leaves + 1) / 2;
+  }
+  M.blk0[GQ_MAXG] = blocks;
+  gq_merge_kernel<<<blocks, 32, gl.smem_merge, st>>>(prm, M, r_all, counters, rfull, part_out);
   return cudaGetLastError();
 }
 

@@ -18,7 +18,6 @@
 namespace fg {
 
 constexpr int GQ_S = 32;         // samples (= rows) of one tile: one row per lane
-constexpr int GQ_ROLES = 4;      // warps with different row-group lists that share a leaf index
 constexpr int GQ_MAXJ = 32;      // joints incl. universe
 constexpr int GQ_MAXG = 8;       // row groups per sample
 constexpr int GQ_MAXB = 12;      // 8-column blocks of one row group's local problem (and of the full factor)
@@ -27,7 +26,7 @@ constexpr int GQ_MAXSIMPLE = 16; // input-fed columns (friction / inertia / offs
 constexpr int GQ_BLK = 8 * GQ_S; // doubles of one tile block (8 columns x 32 rows)
 constexpr int GQ_SCRATCH = 64 + 16;  // T / diagonal block (shared), taus + reduction results
 constexpr int GQ_MAXPROC = 12;   // joints walked by the forward pass
-constexpr int GQ_MAXNW = 15;     // warps (independent streams) of one CTA; one CTA per SM
+constexpr int GQ_MAXNW = 16;     // warps (independent streams) of one CTA; one CTA per SM
 
 struct GqSimple {
   short kind;   // COL_EXTRA / COL_COUPLING / COL_RHS
@@ -39,7 +38,9 @@ struct GqSimple {
 struct GqGroup {
   int nb;        // local 8-column blocks (the rhs is the last real column)
   int w;         // real local columns incl. the rhs
-  int r_off;     // offset (doubles) of this group's block-triangular factor inside a leaf's scratch
+  int r_off;     // offset (doubles) of this group's factors in the scratch: instance i at r_off + i * r_size
+  int r_size;    // doubles of one block-triangular factor, nb (nb + 1) / 2 * 64
+  int ninst;     // warps (instances) that work on this row group in a full launch
   int joint;     // joint whose motion axis the rows project on
   int tjoint;    // its position in the forward walk
   int rowblock;  // reference row-block index (add_coupling_TX40 addresses rows by it)
@@ -56,6 +57,8 @@ struct GqGen {
   GqSimple simple[GQ_MAXG][GQ_MAXSIMPLE];
 };
 
+constexpr int GQ_GEN_DOUBLES = (int)((sizeof(GqGen) + 15) / 16) * 2;  // shared-memory doubles reserved for it
+
 // Passed by value as a __grid_constant__ kernel parameter: read through the constant cache with
 // warp-uniform addresses.
 struct GqParams {
@@ -64,37 +67,39 @@ struct GqParams {
   int p1;               // state columns incl. the rhs
   int nbf;              // 8-column blocks of the full factor
   int maxnb;            // largest local block count
-  int r_leaf_doubles;   // scratch doubles of one leaf (all row groups)
-  int role_n[GQ_ROLES];
-  int role_g[GQ_ROLES][GQ_MAXG];
+  int maxinst;          // largest instance count of a row group
   double gravity[3];
   GqGen gen;
   unsigned char gcol[GQ_MAXG][GQ_MAXW]; // local column -> state column
 };
 
+// Which row group a warp works on.  The number of warps per row group is proportional to the group's cost
+// (forward pass + panels + trailing updates), so that all streams finish together; warp gw = blockIdx.x * nw +
+// warp of a full launch reads its row group and its instance index from two small device tables.
 struct GqLaunch {
   bool ok = false;
-  int smem_warp = 0;   // accumulate kernel, bytes per warp (tile + scratch)
-  int nw = 0;          // warps per CTA
-  int smem_merge = 0;  // merge kernel, per warp
-  int sm_count = 0;
-  int leaves = 0;      // leaves of a full launch (4 warps - one per role - share a leaf index)
-  int64_t r_leaf_doubles = 0;
+  int nw = 0;             // warps per CTA
+  int sm_count = 0;       // CTAs of a launch
+  int smem = 0;           // accumulate kernel, dynamic shared memory of a CTA (largest row-group mix)
+  int smem_merge = 0;     // merge kernel, per warp
+  int64_t r_doubles = 0;  // scratch doubles of all factors
   int64_t rfull_doubles = 0;
+  std::vector<unsigned char> tab_g;    // [sm_count * nw] row group of warp gw
+  std::vector<unsigned short> tab_i;   // [sm_count * nw] instance index of warp gw inside its row group
+  const unsigned char* d_tab_g = nullptr;   // device copies (owned by the caller)
+  const unsigned short* d_tab_i = nullptr;
 };
 
 GqLaunch gq_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, const ColDesc* cols, int sm_count,
                   int max_smem, GqParams* out, const char** why);
 
-// accumulate N samples into the per-leaf factors (scratch r_all, `leaves` leaves)
+// accumulate N samples into the per-instance factors (scratch r_all)
 cudaError_t gq_launch(const GqLaunch& gl, const GqParams& prm, const double* q, const double* v, const double* a,
-                      const double* tau, int64_t ld_tau, int64_t N, double* r_all, int leaves, int first,
-                      cudaStream_t st);
-// leaves a launch over N samples uses (a whole number of CTAs)
-int gq_leaves_for(const GqLaunch& gl, int64_t N, bool whole);
-// tree-merge the per-leaf factors of every row group, fold the roots into one full factor and write it as a
-// packed part (upper triangle + squared column norms) to part_out.  counters: GQ_MAXG * leaves + 2 unsigneds.
-cudaError_t gq_merge(const GqLaunch& gl, const GqParams& prm, double* r_all, int leaves, unsigned* counters,
+                      const double* tau, int64_t ld_tau, int64_t N, double* r_all, int first, cudaStream_t st);
+// tree-merge the per-instance factors of every row group (instances that received no tile are skipped when
+// ntiles_hint > 0), fold the roots into one full factor and write it as a packed part (upper triangle +
+// squared column norms) to part_out.  counters: GQ_MAXG * maxinst + 2 unsigneds.
+cudaError_t gq_merge(const GqLaunch& gl, const GqParams& prm, double* r_all, int64_t ntiles_hint, unsigned* counters,
                      double* rfull, double* part_out, cudaStream_t st);
 
 }  // namespace fg

@@ -7,8 +7,8 @@
 //
 // This kernel removes both.  Rows of different row groups are different rows of W, hence
 // R = qr([R_0; ...; R_{ms-1}]) with R_g the factor of row group g's own non-zero columns (fg_gq.h).
-// A warp owns a static list of row groups (its "role") and, per tile of 32 samples and per row
-// group of its role:
+// A warp works on ONE row group for the whole launch (the number of warps per row group is proportional to
+// the group's cost, fg_gq.h) and, per tile of 32 samples:
 //   1. runs the forward pass with one sample per lane and writes that row group's entries
 //      s_g^T B_b (pinocchio::computeJointTorqueRegressor, reference call sites regressor.py:49,93)
 //      into its private 32 x w_g shared-memory tile,
@@ -16,7 +16,7 @@
 //      Householder QR: 8-column panels with one row per lane, compact-WY T, DMMA trailing updates
 //      whose reflector fragments stay in registers for the whole panel.
 // No warp ever waits for another one: a CTA is a single warp, there is no barrier in the kernel.
-// The per-leaf factors are merged by gq_merge_kernel (pairwise tree per row group driven by arrival
+// The per-warp factors are merged by gq_merge_kernel (pairwise tree per row group driven by arrival
 // counters, then the ms roots are folded into the full factor in state column order).
 #pragma once
 #include "fg_tileqr.cuh"
@@ -441,16 +441,17 @@ static __device__ __forceinline__ void gq_generate(const GqParams& P, const GqGe
 
 // ---------------------------------------------------------------------------------------------
 // One CTA per SM, blockDim.x / 32 independent warps; the only CTA-wide synchronisation is the one after the
-// generator tables have been copied to shared memory.  Warp gw = blockIdx.x * nw + warp plays role gw % 4 for
-// leaf gw / 4.
+// generator tables have been copied to shared memory.  Warp gw = blockIdx.x * nw + warp works on row group
+// tab_g[gw] as its instance tab_i[gw]: it folds the tiles inst, inst + ninst, ... into its own factor.  The
+// shared-memory tile of a warp has exactly the width of its row group.
 __global__ void __launch_bounds__(GQ_MAXNW * 32, 1)
-gq_accumulate_kernel(const __grid_constant__ GqParams P, const double* __restrict__ q, const double* __restrict__ qd,
-                     const double* __restrict__ qdd, const double* __restrict__ tau, int64_t ld_tau, int64_t N,
-                     double* __restrict__ r_all, int leaves, int first) {
+gq_accumulate_kernel(const __grid_constant__ GqParams P, const unsigned char* __restrict__ tab_g,
+                     const unsigned short* __restrict__ tab_i, const double* __restrict__ q,
+                     const double* __restrict__ qd, const double* __restrict__ qdd, const double* __restrict__ tau,
+                     int64_t ld_tau, int64_t N, double* __restrict__ r_all, int first) {
   extern __shared__ __align__(16) double gq_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const int wdoubles = P.maxnb * GQ_BLK + GQ_SCRATCH;
-  GqGen* Sg = reinterpret_cast<GqGen*>(gq_smem + (size_t)nw * wdoubles);
+  GqGen* Sg = reinterpret_cast<GqGen*>(gq_smem);
   {
     const int* src = reinterpret_cast<const int*>(&P.gen);
     int* dst = reinterpret_cast<int*>(Sg);
@@ -459,52 +460,51 @@ gq_accumulate_kernel(const __grid_constant__ GqParams P, const double* __restric
   __syncthreads();
   const GqGen& S = *Sg;
   const int gw = blockIdx.x * nw + warp;
-  const int role = gw % GQ_ROLES, leaf = gw / GQ_ROLES;
-  if (leaf >= leaves) return;
-  double* tile = gq_smem + (size_t)warp * wdoubles;
-  double* scr = tile + P.maxnb * GQ_BLK;
-  double* Rleaf = r_all + (size_t)leaf * P.r_leaf_doubles;
-  const int ng = P.role_n[role];
+  const int g = tab_g[gw], inst = tab_i[gw];
+  int boff = 0;
+  for (int w = 0; w < warp; ++w) boff += S.grp[tab_g[blockIdx.x * nw + w]].nb;
+  double* tile = gq_smem + GQ_GEN_DOUBLES + (size_t)boff * GQ_BLK + (size_t)warp * GQ_SCRATCH;
+  const GqGroup& G = S.grp[g];
+  const int nb = G.nb, ninst = G.ninst;
+  double* scr = tile + nb * GQ_BLK;
+  double* Rg = r_all + (size_t)G.r_off + (size_t)inst * G.r_size;
   if (first) {
-    for (int gi = 0; gi < ng; ++gi) {
-      const GqGroup& G = S.grp[P.role_g[role][gi]];
-      const int n = G.nb * (G.nb + 1) / 2 * 64;
-      for (int i = lane; i < n; i += 32) Rleaf[G.r_off + i] = 0.0;
-    }
+    for (int i = lane; i < G.r_size; i += 32) Rg[i] = 0.0;
     __syncwarp();
   }
   GqOffs offs;
   gq_make_offs(offs, lane);
   const int64_t ntiles = (N + GQ_S - 1) / GQ_S;
-  for (int64_t tl = leaf; tl < ntiles; tl += leaves) {
-    if (tl + leaves < ntiles) {  // pull the next tile's inputs into L2 while this one is folded
-      const int64_t sn = (tl + leaves) * GQ_S + lane;
+  for (int64_t tl = inst; tl < ntiles; tl += ninst) {
+    if (tl + ninst < ntiles) {  // pull the next tile's inputs into L2 while this one is folded
+      const int64_t sn = (tl + ninst) * GQ_S + lane;
       if (sn < N) {
         asm volatile("prefetch.global.L2 [%0];" ::"l"(q + sn * P.nq));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(qd + sn * P.nv));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(qdd + sn * P.nv));
       }
     }
-    for (int gi = 0; gi < ng; ++gi) {
-      const int g = P.role_g[role][gi];
-      const int nb = S.grp[g].nb;
-      {
-        double2* t2 = reinterpret_cast<double2*>(tile);
-        for (int i = lane; i < nb * (GQ_BLK / 2); i += 32) t2[i] = make_double2(0.0, 0.0);
-      }
-      __syncwarp();
-      gq_generate(P, S, g, tile, q, qd, qdd, tau, ld_tau, tl * GQ_S, N, lane);
-      __syncwarp();
-      gq_fold<false>(tile, nb, Rleaf + S.grp[g].r_off, 0, scr, offs, lane);
+    {
+      double2* t2 = reinterpret_cast<double2*>(tile);
+      for (int i = lane; i < nb * (GQ_BLK / 2); i += 32) t2[i] = make_double2(0.0, 0.0);
     }
+    __syncwarp();
+    gq_generate(P, S, g, tile, q, qd, qdd, tau, ld_tau, tl * GQ_S, N, lane);
+    __syncwarp();
+    gq_fold<false>(tile, nb, Rg, 0, scr, offs, lane);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Merge of the per-leaf factors.  One warp per (row group g, pair of leaves).  A warp folds leaf i + stride
-// into leaf i, then climbs: at every internal node the first of the two children to arrive leaves, the second
-// one does the node's merge (always "right child into left child", so the result does not depend on who came
-// last).  The warp that completes the last row-group root folds the ms roots into the full factor.
+// Merge of the per-warp factors.  One warp per (row group g, pair of instances).  A warp folds instance
+// i + stride into instance i, then climbs: at every internal node the first of the two children to arrive
+// leaves, the second one does the node's merge (always "right child into left child", so the result does not
+// depend on who came last).
+struct GqMergeArgs {
+  int leaves[GQ_MAXG];    // instances of row group g that take part
+  int blk0[GQ_MAXG + 1];  // first block of row group g (one block = one warp = one pair of instances)
+};
+
 __device__ __forceinline__ void gq_merge_into(const GqParams& P, double* tile, int nb, double* Rdst, const double* Rsrc,
                                               double* scr, const GqOffs& o, int lane) {
   for (int t0 = 0; t0 < nb; t0 += 4) {
@@ -534,12 +534,14 @@ __device__ __forceinline__ void gq_merge_into(const GqParams& P, double* tile, i
 }
 
 __global__ void __launch_bounds__(32)
-gq_merge_kernel(const __grid_constant__ GqParams P, double* __restrict__ r_all, int leaves, int npairs,
+gq_merge_kernel(const __grid_constant__ GqParams P, const __grid_constant__ GqMergeArgs M, double* __restrict__ r_all,
                 unsigned* __restrict__ counters, double* __restrict__ rfull, double* __restrict__ part_out) {
   extern __shared__ __align__(16) double gq_smem[];
   const int lane = threadIdx.x;
-  const int g = blockIdx.x / npairs;
-  int i = 2 * (blockIdx.x % npairs);
+  int g = 0;
+  while (g + 1 < P.ms && (int)blockIdx.x >= M.blk0[g + 1]) ++g;
+  int i = 2 * ((int)blockIdx.x - M.blk0[g]);
+  const int leaves = M.leaves[g];
   const int mb = P.maxnb > P.nbf ? P.maxnb : P.nbf;
   double* tile = gq_smem;
   double* scr = gq_smem + mb * GQ_BLK;
@@ -547,10 +549,10 @@ gq_merge_kernel(const __grid_constant__ GqParams P, double* __restrict__ r_all, 
   gq_make_offs(offs, lane);
   const GqGroup& G = P.gen.grp[g];
   const int nb = G.nb;
+  double* Rgrp = r_all + (size_t)G.r_off;
   for (int stride = 1;; stride *= 2) {
     if (i + stride < leaves)
-      gq_merge_into(P, tile, nb, r_all + (size_t)i * P.r_leaf_doubles + G.r_off,
-                    r_all + (size_t)(i + stride) * P.r_leaf_doubles + G.r_off, scr, offs, lane);
+      gq_merge_into(P, tile, nb, Rgrp + (size_t)i * G.r_size, Rgrp + (size_t)(i + stride) * G.r_size, scr, offs, lane);
     const int s2 = 2 * stride;
     if (s2 >= leaves) break;  // i == 0: the root of this row group is complete
     const int ip = i & ~(2 * s2 - 1);
@@ -559,7 +561,7 @@ gq_merge_kernel(const __grid_constant__ GqParams P, double* __restrict__ r_all, 
       __threadfence();
       __syncwarp();
       unsigned old = 0;
-      if (lane == 0) old = atomicAdd(&counters[(size_t)g * leaves + ip + s2], 1u);
+      if (lane == 0) old = atomicAdd(&counters[(size_t)g * P.maxinst + ip + s2], 1u);
       old = __shfl_sync(0xffffffffu, old, 0);
       if (old == 0) return;
       __threadfence();
@@ -572,7 +574,7 @@ gq_merge_kernel(const __grid_constant__ GqParams P, double* __restrict__ r_all, 
   // and otherwise releases BUSY (compare-and-swap against the value it examined, so a bit that arrives in
   // between makes the release fail and is picked up).  No warp ever spins on another one.  The small row
   // groups finish their trees first, so their folds overlap the trees of the large ones.
-  unsigned* fin = counters + (size_t)GQ_MAXG * leaves;
+  unsigned* fin = counters + (size_t)GQ_MAXG * P.maxinst;
   unsigned* nfolded = fin + 1;
   const unsigned BUSY = 0x80000000u;
   {
