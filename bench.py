@@ -48,6 +48,9 @@ def fp64_peak_tflops():
         return 37.0, "nominal"
 
 
+_REAL_STDOUT = sys.stdout
+
+
 def ncu_traffic(n):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed ncu
     capture of this command at the same sample count (profiles/ncu_traffic_r01.json); None if there is none."""
@@ -165,7 +168,7 @@ def run_reference(args):
                              "sample": f"{n} samples per step (per-sample regressor loop through the C oracle standing in "
                                        "for pinocchio, get_index_eliminate, double_QR with two LAPACK QRs)"},
             "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_REAL_STDOUT, flush=True)
 
 
 def cpu_baseline(n):
@@ -198,6 +201,11 @@ def main():
     ap.add_argument("--cpu-baseline-samples", type=int, default=100_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # Libraries (NCCL prints its version banner) write to fd 1: keep stdout for the ONE JSON line.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
         return
@@ -327,7 +335,7 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(args.cpu_baseline_samples)
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -82,6 +82,7 @@ struct fg_state {
   double* d_Re = nullptr;       // reduced factor (dense, (nk+1)^2)
   double* d_X = nullptr;        // solve output
   int* d_idx = nullptr;         // 2*p1 ints: column map + extents
+  double* d_solve = nullptr;    // output blob of fg_state_solve (4 + 3 p1 + 2 p1^2 doubles)
   int nk = -1;                  // columns kept by the last fg_state_reduce
   std::vector<int> keep;
   // column order of the factor: state column i holds caller column perm[i] (empty = identity).
@@ -410,7 +411,7 @@ extern "C" int fg_state_create(int32_t p, fg_state** out) {
 extern "C" void fg_state_destroy(fg_state* s) {
   if (!s) return;
   cudaFree(s->d_part); cudaFree(s->d_parts); cudaFree(s->d_gR); cudaFree(s->d_A); cudaFree(s->d_Re);
-  cudaFree(s->d_X); cudaFree(s->d_idx); cudaFree(s->d_stage);
+  cudaFree(s->d_X); cudaFree(s->d_idx); cudaFree(s->d_stage); cudaFree(s->d_solve);
   if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
   for (auto& e : s->ev) if (e) cudaEventDestroy(e);
   if (s->t0) cudaEventDestroy(s->t0);
@@ -855,11 +856,15 @@ extern "C" int fg_state_accumulate_samples_host(fg_state* s, const fg_model* mc,
   FG_CUDA(cudaEventRecord(s->ev[3], st));
   int b = 0;
   bool chunkable = false;  // set by the first chunk when the tile-QR kernel took it: later chunks continue its factors
-  for (int64_t i0 = 0; i0 < N; i0 += chunk, b ^= 1) {
-    const int64_t n = std::min(chunk, N - i0);
+  // Chunk sizes ramp up (32 Ki, 64 Ki, ... samples) to the staging size: the first copy, which nothing can
+  // overlap, is short, and the kernel of chunk k runs in the shadow of the copy of chunk k + 1.
+  int64_t ramp = std::min<int64_t>(chunk, 1 << 15);
+  for (int64_t i0 = 0, n = 0; i0 < N; i0 += n, b ^= 1) {
+    n = std::min(ramp, N - i0);
+    ramp = std::min(chunk, 2 * ramp);
     int phase = TQ_PHASE_FIRST | TQ_PHASE_LAST;
-    if (i0 == 0) phase = N > chunk ? TQ_PHASE_FIRST : phase;
-    else if (chunkable) phase = i0 + chunk >= N ? TQ_PHASE_LAST : 0;
+    if (i0 == 0) phase = N > n ? TQ_PHASE_FIRST : phase;
+    else if (chunkable) phase = i0 + n >= N ? TQ_PHASE_LAST : 0;
     double* base = s->d_stage + (int64_t)b * chunk * per_sample;
     double* dq = base;
     double* dv = dq + chunk * m->nq;
@@ -990,6 +995,106 @@ extern "C" int fg_state_reduce(fg_state* s, const int32_t* keep, int32_t nk, dou
   for (int j = 0; j < n; ++j) diag[j] = std::abs(Rh[(size_t)j * n + j]);
   s->nk = nk;
   s->keep.assign(keep, keep + nk);
+  return FG_OK;
+}
+
+// Column-pivoted QR of the kept columns (QR_pivoting, qrdecomposition.py:24-86) on the factor.
+extern "C" int fg_state_pivot_qr(fg_state* s, const int32_t* keep, int32_t nk, int32_t* perm_host, double* R_host,
+                                 void* stream) {
+  if (!s || !keep || nk < 1 || nk > s->p || !perm_host || !R_host)
+    return set_err(FG_ERR_INVALID, "fg_state_pivot_qr: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int p1 = s->p1, n = nk + 1;
+  int sm_count, max_smem;
+  int rc = device_limits(&sm_count, &max_smem);
+  if (rc) return rc;
+  const int smem = (p1 * n + n) * 8 + n * 4 + 16;
+  if (smem > max_smem) return set_err(FG_ERR_UNSUPPORTED, "fg_state_pivot_qr: factor does not fit shared memory");
+  std::vector<int> idx(2 * n);
+  const std::vector<int> inv = inverse_perm(s);
+  for (int j = 0; j < nk; ++j) {
+    if (keep[j] < 0 || keep[j] >= s->p || (j > 0 && keep[j] <= keep[j - 1]))
+      return set_err(FG_ERR_INVALID, "fg_state_pivot_qr: keep must be ascending indices in [0,%d)", s->p);
+    idx[j] = inv[keep[j]];
+  }
+  idx[nk] = s->p;
+  FG_CUDA(cudaMemcpyAsync(s->d_idx, idx.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+  gather_cols_kernel<<<64, 256, 0, st>>>(s->d_part, p1, 1, s->d_idx, p1, n, s->d_A);
+  FG_CUDA(cudaGetLastError());
+  FG_LAUNCHED();
+  FG_CUDA(cudaFuncSetAttribute(pivot_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  pivot_qr_kernel<<<1, 256, smem, st>>>(s->d_A, p1, n, nk, s->d_idx + n);
+  FG_CUDA(cudaGetLastError());
+  FG_LAUNCHED();
+  std::vector<int> perm(n);
+  FG_CUDA(cudaMemcpyAsync(R_host, s->d_A, sizeof(double) * n * n, cudaMemcpyDeviceToHost, st));
+  FG_CUDA(cudaMemcpyAsync(perm.data(), s->d_idx + n, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+  FG_CUDA(cudaStreamSynchronize(st));
+  for (int j = 0; j < nk; ++j) perm_host[j] = perm[j];
+  return FG_OK;
+}
+
+// get_index_eliminate + get_baseIndex + double_QR on the factor in ONE launch and ONE device-to-host copy
+// (fused_solve_kernel); the three-call sequence colsq / reduce / regroup_solve stays for callers that decide
+// the column sets themselves.
+extern "C" int fg_state_solve(fg_state* s, double tol_e, const int32_t* drop, int32_t n_drop, double tol_qr,
+                              int32_t* n_keep, int32_t* keep, double* colsq, double* diag, int32_t* n_base,
+                              int32_t* order, double* beta, double* phi, double* R1, double* resid2, void* stream) {
+  if (!s || !n_keep || !keep || !n_base || !order) return set_err(FG_ERR_INVALID, "fg_state_solve: null argument");
+  if (!s->perm.empty()) return set_err(FG_ERR_UNSUPPORTED, "fg_state_solve: the state holds a permuted factor");
+  const int p = s->p, p1 = s->p1;
+  if (p > 32 * US_M) return set_err(FG_ERR_UNSUPPORTED, "fg_state_solve: p=%d above %d", p, 32 * US_M);
+  int sm_count, max_smem;
+  int rc = device_limits(&sm_count, &max_smem);
+  if (rc) return rc;
+  const int smem = (2 * p1 * p1 + p1) * 8 + 3 * p1 * 4 + 16;
+  if (smem > max_smem) return set_err(FG_ERR_UNSUPPORTED, "fg_state_solve: factor does not fit shared memory");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t blob = 4 + 3 * (size_t)p1 + 2 * (size_t)p1 * p1;
+  if (!s->d_solve) FG_CUDA(cudaMalloc(&s->d_solve, sizeof(double) * blob));
+  std::vector<int> flags(p, 0);
+  for (int i = 0; i < n_drop; ++i) {
+    if (!drop || drop[i] < 0 || drop[i] >= p) return set_err(FG_ERR_INVALID, "fg_state_solve: bad column index in drop");
+    flags[drop[i]] = 1;
+  }
+  FG_CUDA(cudaMemcpyAsync(s->d_idx, flags.data(), sizeof(int) * p, cudaMemcpyHostToDevice, st));
+  FG_CUDA(cudaFuncSetAttribute(fused_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  fused_solve_kernel<<<1, 256, smem, st>>>(s->d_part, p1, s->d_idx, tol_e, tol_qr, s->d_Re, s->d_solve);
+  FG_CUDA(cudaGetLastError());
+  FG_LAUNCHED();
+  std::vector<double> h(blob);
+  FG_CUDA(cudaMemcpyAsync(h.data(), s->d_solve, sizeof(double) * blob, cudaMemcpyDeviceToHost, st));
+  FG_CUDA(cudaStreamSynchronize(st));
+  const int nk = (int)h[0], r = (int)h[1], n = nk + 1, ng = nk - r, nrhs = ng + 1;
+  const double* h_colsq = h.data() + 4;
+  const double* h_diag = h_colsq + p1;
+  const double* h_order = h_diag + p1;
+  const double* h_Rg = h_order + p1;
+  const double* h_X = h_Rg + (size_t)n * n;
+  *n_keep = nk;
+  *n_base = r;
+  s->keep.clear();
+  {
+    int k = 0;
+    for (int c = 0; c < p; ++c)
+      if (!(flags[c] || (tol_e >= 0.0 && h_colsq[c] < tol_e))) { keep[k++] = c; s->keep.push_back(c); }
+    if (k != nk) return set_err(FG_ERR_CUDA, "fg_state_solve: internal: keep count mismatch (%d vs %d)", k, nk);
+  }
+  s->nk = nk;
+  if (colsq) for (int c = 0; c < p1; ++c) colsq[c] = h_colsq[c];
+  if (diag) for (int j = 0; j < n; ++j) diag[j] = h_diag[j];
+  for (int j = 0; j < nk; ++j) order[j] = (int)h_order[j];
+  if (r == 0) return FG_OK;
+  for (int i = 0; i < r; ++i) {
+    if (beta) for (int j = 0; j < ng; ++j) beta[(size_t)i * ng + j] = h_X[(size_t)i * nrhs + j];
+    if (phi) phi[i] = h_X[(size_t)i * nrhs + ng];
+    if (R1) for (int j = 0; j < r; ++j) R1[(size_t)i * r + j] = h_Rg[(size_t)i * n + j];
+  }
+  if (resid2) {
+    double r2 = 0.0;
+    for (int i = r; i < n; ++i) r2 += h_Rg[(size_t)i * n + (n - 1)] * h_Rg[(size_t)i * n + (n - 1)];
+    *resid2 = r2;
+  }
   return FG_OK;
 }
 

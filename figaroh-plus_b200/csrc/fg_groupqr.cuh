@@ -334,6 +334,10 @@ static __device__ __forceinline__ void gq_generate(const GqParams& P, const GqGe
   double v[6] = {0, 0, 0, 0, 0, 0}, a[6] = {0, 0, 0, 0, 0, 0};
   double nq0 = __ldg(qs + S.pj[0].idx_q), nv0 = __ldg(vs + S.pj[0].idx_v), na0 = __ldg(as + S.pj[0].idx_v);
   double nq1 = 0.0, nv1 = 0.0, na1 = 0.0;
+  // rhs entry and the row group's own (dq, ddq): requested / kept now, consumed after the walk
+  const double taug = (valid && tau != nullptr) ? __ldg(tau + (int64_t)g * ld_tau + smp) : 0.0;
+  double vg = 0.0, ag = 0.0;
+  const int vidx_g = S.pj[G.tjoint].idx_v;
   if (nproc > 1) { nq1 = __ldg(qs + S.pj[1].idx_q); nv1 = __ldg(vs + S.pj[1].idx_v); na1 = __ldg(as + S.pj[1].idx_v); }
   for (int t = 0; t < nproc; ++t) {
     const DevJoint& jt = S.pj[t];
@@ -404,6 +408,7 @@ static __device__ __forceinline__ void gq_generate(const GqParams& P, const GqGe
     for (int k = 0; k < 3; ++k) op[k] = np[k];
     for (int k = 0; k < 6; ++k) { v[k] = vn[k]; a[k] = an[k]; }
     if (G.tjoint == t) {  // world-frame motion axis of the row group
+      vg = cv0; ag = ca0;
       for (int k = 0; k < 3; ++k) {
         A[3 + k] = oR[3 * k] * G.S[3] + oR[3 * k + 1] * G.S[4] + oR[3 * k + 2] * G.S[5];
         A[k] = oR[3 * k] * G.S[0] + oR[3 * k + 1] * G.S[1] + oR[3 * k + 2] * G.S[2];
@@ -425,9 +430,10 @@ static __device__ __forceinline__ void gq_generate(const GqParams& P, const GqGe
     const int ix = (s1.slot >> 3) * GQ_BLK + tq_idx(s1.slot & 7, lane);
     double val = 0.0;
     if (s1.kind == COL_RHS) {
-      if (valid && tau != nullptr) val = __ldg(tau + (int64_t)g * ld_tau + smp);
+      val = taug;
     } else if (s1.kind == COL_EXTRA) {
-      const double vv = __ldg(vs + s1.vidx), aa = __ldg(as + s1.vidx);
+      const bool own = s1.vidx == vidx_g;  // uniform
+      const double vv = own ? vg : __ldg(vs + s1.vidx), aa = own ? ag : __ldg(as + s1.vidx);
       val = s1.src == SRC_QDD ? aa : (s1.src == SRC_QD ? vv : (s1.src == SRC_SIGN_QD ? sgn(vv) : 1.0));
     } else {
       // add_coupling_TX40 (regressor.py:216-225): row block 4 <- [a5, v5, sign(v4+v5)], 5 <- [a4, v4, sign(v4+v5)]

@@ -391,27 +391,12 @@ __global__ void gather_cols_kernel(const double* __restrict__ Rsrc, int src_p1, 
   }
 }
 
-// In-place Householder QR of the m x n matrix A (row-major, ld = n), single CTA.
-// ext[j] = 1 + last possibly non-zero row of column j on entry.  Column c's reflector spans
-// rows c .. E_c-1 with E_c = max(ext[0..c]) (fill-in of earlier reflectors).  On exit the
-// upper triangle of A holds R (first min(m,n) rows); entries below the diagonal are zeroed.
-// The matrix is staged in shared memory when `use_smem` (m*n*8 bytes + n*8).
-__global__ void __launch_bounds__(1024) small_qr_kernel(double* __restrict__ Ag, int m, int n,
-                                                        const int* __restrict__ ext, int use_smem) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  double* A = Ag;
-  double* dg;
-  if (use_smem) {
-    A = reinterpret_cast<double*>(smem);
-    dg = A + (size_t)m * n;
-    for (int i = threadIdx.x; i < m * n; i += blockDim.x) A[i] = Ag[i];
-  } else {
-    dg = reinterpret_cast<double*>(smem);
-  }
-  // column extents in shared memory: a dependent global load per column would cost more than the column itself
-  int* exts = reinterpret_cast<int*>(dg + n);
-  for (int i = threadIdx.x; i < n; i += blockDim.x) exts[i] = ext[i];
-  __syncthreads();
+// In-place Householder QR of the m x n matrix A (row-major, ld = n) by one CTA; A, exts (n ints) and dg
+// (n doubles) may live in shared or global memory.  exts[j] = 1 + last possibly non-zero row of column j on
+// entry.  Column c's reflector spans rows c .. E_c-1 with E_c = max(exts[0..c]) (fill-in of earlier
+// reflectors).  On exit the upper triangle of A holds R (first min(m,n) rows, diagonal from dg) and every
+// entry below the diagonal is zero.  Contains __syncthreads(): all threads of the CTA must call it.
+__device__ inline void small_qr_body(double* A, int m, int n, const int* exts, double* dg) {
   const int kmax = m < n ? m : n;
   int E = 0;
   for (int c = 0; c < kmax; ++c) {
@@ -444,36 +429,36 @@ __global__ void __launch_bounds__(1024) small_qr_kernel(double* __restrict__ Ag,
   __syncthreads();
   for (int i = threadIdx.x; i < m * n; i += blockDim.x) {
     const int r = i / n, c = i % n;
-    double v = A[i];
-    if (r > c) v = 0.0;
-    else if (r == c && r < kmax) v = dg[r];
-    Ag[i] = v;
+    if (r > c) A[i] = 0.0;
+    else if (r == c && r < kmax) A[i] = dg[r];
   }
+  __syncthreads();
 }
 
-// Back substitution on the regrouped factor Rg ((nk+1) x (nk+1) dense, ld = ldr):
-//   X[:, j] = R1^-1 Rg[0:r, r + j]  for j in [0, nrhs)   (nrhs = n_regroup + 1, last = rhs)
-// X is r x nrhs row-major.  One thread per right-hand side (any r).
-__global__ void upper_solve_serial_kernel(const double* __restrict__ Rg, int ldr, int r, int nrhs,
-                                          double* __restrict__ X) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= nrhs) return;
-  for (int i = r - 1; i >= 0; --i) {
-    double acc = Rg[(size_t)i * ldr + r + j];
-    for (int k = i + 1; k < r; ++k) acc = fma(-Rg[(size_t)i * ldr + k], X[(size_t)k * nrhs + j], acc);
-    X[(size_t)i * nrhs + j] = acc / Rg[(size_t)i * ldr + i];
+// The matrix is staged in shared memory when `use_smem` (m*n*8 + n*8 + n*4 bytes).
+__global__ void __launch_bounds__(1024) small_qr_kernel(double* __restrict__ Ag, int m, int n,
+                                                        const int* __restrict__ ext, int use_smem) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  double* A = Ag;
+  double* dg;
+  if (use_smem) {
+    A = reinterpret_cast<double*>(smem);
+    dg = A + (size_t)m * n;
+    for (int i = threadIdx.x; i < m * n; i += blockDim.x) A[i] = Ag[i];
+  } else {
+    dg = reinterpret_cast<double*>(smem);
   }
+  int* exts = reinterpret_cast<int*>(dg + n);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) exts[i] = ext[i];
+  __syncthreads();
+  small_qr_body(A, m, n, exts, dg);
+  if (use_smem)
+    for (int i = threadIdx.x; i < m * n; i += blockDim.x) Ag[i] = A[i];
 }
 
-// Same result, one WARP per right-hand side, column-oriented (r <= 128): lane l keeps b[l], b[l + 32], ...;
-// step i divides b_i by R_ii and every lane updates its own entries with column i of R1, which was requested
-// one step earlier.  r dependent steps of ~100 cycles instead of r^2 / 2 dependent global round trips.
+// Back substitution of one right-hand side by one warp (r <= 128), see upper_solve_kernel below.
 constexpr int US_M = 4;
-__global__ void __launch_bounds__(128) upper_solve_kernel(const double* __restrict__ Rg, int ldr, int r, int nrhs,
-                                                          double* __restrict__ X) {
-  const int lane = threadIdx.x & 31;
-  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (j >= nrhs) return;
+__device__ __forceinline__ void upper_solve_warp(const double* Rg, int ldr, int r, int j, int nrhs, double* X, int lane) {
   double b[US_M], rc[US_M];
 #pragma unroll
   for (int m = 0; m < US_M; ++m) {
@@ -500,6 +485,167 @@ __global__ void __launch_bounds__(128) upper_solve_kernel(const double* __restri
       rc[m] = rn[m];
     }
   }
+}
+
+// ------------------------------------------------------------------ kernel (3) in one launch
+// get_index_eliminate + get_baseIndex + double_QR on the factor, one CTA, everything in shared memory:
+//   keep      = columns with colsq >= tol_e (regressor.py:271-274) that the caller did not drop,
+//   Re        = qr(R[:, keep + rhs])                       -> |diag| decides base / regroup (qrdecomposition.py:117-121)
+//   Rg        = qr(Re[:, base + regroup + rhs])            -> X = R1^-1 [R2 | Q1^T tau]  (beta, phi_b)
+// Output blob (doubles): [0] nk, [1] r, [2..3] unused, colsq[p1], diag[p1], order[p1] (kept-column indices:
+// base first, then regroup), Rg[n*n] (n = nk + 1), X[r * (nk - r + 1)].  Re is also written to Re_out (n*n).
+__global__ void __launch_bounds__(256) fused_solve_kernel(const double* __restrict__ part, int p1,
+                                                          const int* __restrict__ force_drop, double tol_e, double tol_qr,
+                                                          double* __restrict__ Re_out, double* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int p = p1 - 1, ntri = p1 * (p1 + 1) / 2;
+  double* A = reinterpret_cast<double*>(smem);          // p1 x n, then the reduced factor in its first n rows
+  double* A2 = A + (size_t)p1 * p1;                      // n x n regrouped
+  double* dg = A2 + (size_t)p1 * p1;                     // p1
+  int* cols = reinterpret_cast<int*>(dg + p1);           // p1: source column of every gathered column
+  int* exts = cols + p1;                                 // p1
+  int* order = exts + p1;                                // p1
+  __shared__ int s_nk, s_r;
+  double* o_colsq = out + 4;
+  double* o_diag = o_colsq + p1;
+  double* o_order = o_diag + p1;
+  double* o_Rg = o_order + p1;
+  for (int c = threadIdx.x; c < p1; c += blockDim.x) {
+    const double sq = part[ntri + c];
+    o_colsq[c] = sq;
+    order[c] = c < p && (force_drop[c] != 0 || (tol_e >= 0.0 && sq < tol_e));  // drop flag, in parallel
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int nk = 0;
+    for (int c = 0; c < p; ++c)
+      if (!order[c]) { cols[nk] = c; exts[nk] = c + 1; ++nk; }
+    cols[nk] = p; exts[nk] = p1;
+    s_nk = nk;
+  }
+  __syncthreads();
+  const int nk = s_nk, n = nk + 1;
+  for (int idx = threadIdx.x; idx < p1 * n; idx += blockDim.x) {
+    const int r = idx / n, j = idx % n, c = cols[j];
+    A[idx] = r <= c ? part[tri_off(r, p1) + c - r] : 0.0;
+  }
+  __syncthreads();
+  small_qr_body(A, p1, n, exts, dg);
+  for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) Re_out[idx] = A[idx];
+  for (int j = threadIdx.x; j < n; j += blockDim.x) o_diag[j] = fabs(A[(size_t)j * n + j]);
+  if (threadIdx.x == 0) {
+    int r = 0;
+    for (int i = 0; i < nk; ++i) if (fabs(A[(size_t)i * n + i]) > tol_qr) order[r++] = i;
+    s_r = r;
+    int k = r;
+    for (int i = 0; i < nk; ++i) if (!(fabs(A[(size_t)i * n + i]) > tol_qr)) order[k++] = i;
+    order[nk] = nk;
+    out[0] = nk; out[1] = r; out[2] = 0.0; out[3] = 0.0;
+  }
+  __syncthreads();
+  const int r = s_r;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) { o_order[j] = order[j]; exts[j] = order[j] + 1; }
+  if (r == 0) return;
+  for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+    const int i = idx / n, j = idx % n, c = order[j];
+    A2[idx] = i <= c ? A[(size_t)i * n + c] : 0.0;
+  }
+  __syncthreads();
+  small_qr_body(A2, n, n, exts, dg);
+  for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) o_Rg[idx] = A2[idx];
+  const int nrhs = nk - r + 1;
+  double* X = o_Rg + (size_t)n * n;
+  const int lane = threadIdx.x & 31;
+  for (int j = threadIdx.x >> 5; j < nrhs; j += blockDim.x >> 5) upper_solve_warp(A2, n, r, j, nrhs, X, lane);
+}
+
+// Back substitution on the regrouped factor Rg ((nk+1) x (nk+1) dense, ld = ldr):
+//   X[:, j] = R1^-1 Rg[0:r, r + j]  for j in [0, nrhs)   (nrhs = n_regroup + 1, last = rhs)
+// X is r x nrhs row-major.  One thread per right-hand side (any r).
+__global__ void upper_solve_serial_kernel(const double* __restrict__ Rg, int ldr, int r, int nrhs,
+                                          double* __restrict__ X) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nrhs) return;
+  for (int i = r - 1; i >= 0; --i) {
+    double acc = Rg[(size_t)i * ldr + r + j];
+    for (int k = i + 1; k < r; ++k) acc = fma(-Rg[(size_t)i * ldr + k], X[(size_t)k * nrhs + j], acc);
+    X[(size_t)i * nrhs + j] = acc / Rg[(size_t)i * ldr + i];
+  }
+}
+
+// Same result, one WARP per right-hand side, column-oriented (r <= 128): lane l keeps b[l], b[l + 32], ...;
+// step i divides b_i by R_ii and every lane updates its own entries with column i of R1, which was requested
+// one step earlier.  r dependent steps of ~100 cycles instead of r^2 / 2 dependent global round trips.
+__global__ void __launch_bounds__(128) upper_solve_kernel(const double* __restrict__ Rg, int ldr, int r, int nrhs,
+                                                          double* __restrict__ X) {
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j >= nrhs) return;
+  upper_solve_warp(Rg, ldr, r, j, nrhs, X, lane);
+}
+
+// ------------------------------------------------------------------ column-pivoted QR of the small factor
+// scipy.linalg.qr(W_e, pivoting=True) of QR_pivoting (qrdecomposition.py:38) on the (reduced) R factor: since
+// R^T R = W_e^T W_e, the partial column norms LAPACK's dgeqp3 pivots on are the same for R as for W_e.
+// A: m x n row-major in global memory (staged in shared memory); the first npiv columns take part in the
+// pivoting, the others (the rhs) are carried along.  perm[j] = source column of pivoted column j.
+// Partial norms are recomputed exactly at every step (dgeqp3 downdates them); ties go to the lowest index.
+__global__ void __launch_bounds__(256) pivot_qr_kernel(double* __restrict__ Ag, int m, int n, int npiv,
+                                                       int* __restrict__ perm_out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  double* A = reinterpret_cast<double*>(smem);
+  double* nrm = A + (size_t)m * n;             // n
+  int* perm = reinterpret_cast<int*>(nrm + n);  // n
+  __shared__ int s_pvt;
+  for (int i = threadIdx.x; i < m * n; i += blockDim.x) A[i] = Ag[i];
+  for (int j = threadIdx.x; j < n; j += blockDim.x) perm[j] = j;
+  __syncthreads();
+  const int kmax = m < npiv ? m : npiv;
+  for (int c = 0; c < kmax; ++c) {
+    for (int j = c + threadIdx.x; j < npiv; j += blockDim.x) {
+      double sacc = 0.0;
+      for (int r = c; r < m; ++r) sacc = fma(A[(size_t)r * n + j], A[(size_t)r * n + j], sacc);
+      nrm[j] = sacc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int best = c;
+      for (int j = c + 1; j < npiv; ++j) if (nrm[j] > nrm[best]) best = j;
+      s_pvt = best;
+      const int t = perm[c]; perm[c] = perm[best]; perm[best] = t;
+    }
+    __syncthreads();
+    const int pv = s_pvt;
+    if (pv != c)
+      for (int r = threadIdx.x; r < m; r += blockDim.x) {
+        const double t = A[(size_t)r * n + c]; A[(size_t)r * n + c] = A[(size_t)r * n + pv]; A[(size_t)r * n + pv] = t;
+      }
+    __syncthreads();
+    const double alpha = A[(size_t)c * n + c];
+    double sigma = 0.0;
+    for (int r = c + 1; r < m; ++r) { const double x = A[(size_t)r * n + c]; sigma = fma(x, x, sigma); }
+    if (sigma != 0.0) {  // uniform
+      const double nr = sqrt(fma(alpha, alpha, sigma));
+      const double beta = alpha >= 0.0 ? -nr : nr;
+      const double inv = 1.0 / (alpha - beta);
+      const double tauh = (beta - alpha) / beta;
+      for (int j = c + 1 + threadIdx.x; j < n; j += blockDim.x) {
+        double d = 0.0;
+        for (int r = c + 1; r < m; ++r) d = fma(A[(size_t)r * n + c], A[(size_t)r * n + j], d);
+        const double rho = A[(size_t)c * n + j];
+        const double sdot = fma(d, inv, rho);
+        A[(size_t)c * n + j] = fma(-tauh, sdot, rho);
+        const double g = tauh * sdot * inv;
+        for (int r = c + 1; r < m; ++r) A[(size_t)r * n + j] = fma(-g, A[(size_t)r * n + c], A[(size_t)r * n + j]);
+      }
+      __syncthreads();
+      for (int r = c + 1 + threadIdx.x; r < m; r += blockDim.x) A[(size_t)r * n + c] = 0.0;
+      if (threadIdx.x == 0) A[(size_t)c * n + c] = beta;
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < m * n; i += blockDim.x) Ag[i] = A[i];
+  for (int j = threadIdx.x; j < n; j += blockDim.x) perm_out[j] = perm[j];
 }
 
 }  // namespace fg

@@ -30,6 +30,31 @@ def _columns(W_e, Wd, idx):
     return np.ascontiguousarray(np.asarray(W_e, dtype=np.float64)[:, list(idx)])
 
 
+def QR_pivoting(tau, W_e, params_r, tol_qr=TOL_QR):
+    """Base parameters from a column-pivoted QR - reference: qrdecomposition.py:24-86.
+
+    The pivoting runs on the GPU on the small R factor of [W_e | tau]; returns (W_b, {expr: phi_b}).
+    Quirk kept (qrdecomposition.py:45-51): the rank is the index of the FIRST diagonal entry with
+    |R_ii| <= tol_qr and stays 0 when there is none."""
+    Wd, st = _state_of(W_e, np.asarray(tau, dtype=np.float64) if not _on_device(tau) else tau)
+    p = Wd.shape[1]
+    perm, R = st.pivot_qr(np.arange(p))
+    params_rsorted = [params_r[int(perm[i])] for i in range(p)]
+    numrank_W = 0
+    for i in range(p):
+        if abs(R[i, i]) > tol_qr:
+            continue
+        numrank_W = i
+        break
+    r = numrank_W
+    R1inv = np.linalg.inv(R[:r, :r])
+    beta = np.around(R1inv @ R[:r, r:p], 6)
+    phi_b = np.round(R1inv @ R[:r, p], 6)
+    W_b = _columns(W_e, Wd, [int(perm[i]) for i in range(r)])
+    params_base = _eng.expressions(params_rsorted[:r], params_rsorted[r:], beta)
+    return W_b, dict(zip(params_base, phi_b))
+
+
 def get_baseIndex(W_e, params_r, tol_qr=TOL_QR):
     """Indices i with |R_ii| > tol_qr in the unpivoted QR of W_e (qrdecomposition.py:274-296)."""
     Wd, st = _state_of(W_e)

@@ -290,6 +290,43 @@ class TsqrState:
         check(_lib.lib().fg_state_reduce(self._h, keep.ctypes.data, len(keep), diag.ctypes.data, _stream()))
         return diag
 
+    def solve(self, tol_e, drop, tol_qr):
+        """The whole N-independent stage in one launch (fg_state_solve).  Returns None when the library
+        cannot take this state (permuted factor / too large): the caller uses the three-call sequence."""
+        p = self.p
+        drop = np.ascontiguousarray(sorted(drop), dtype=np.int32)
+        keep = np.empty(p, dtype=np.int32)
+        order = np.empty(p, dtype=np.int32)
+        colsq = np.empty(p + 1)
+        diag = np.empty(p + 1)
+        beta = np.empty(p * p)
+        phi = np.empty(p)
+        R1 = np.empty(p * p)
+        nk, nb, r2 = C.c_int32(), C.c_int32(), C.c_double()
+        rc = _lib.lib().fg_state_solve(self._h, -1.0 if tol_e is None else float(tol_e),
+                                       drop.ctypes.data if len(drop) else None, len(drop), float(tol_qr),
+                                       C.addressof(nk), keep.ctypes.data, colsq.ctypes.data, diag.ctypes.data,
+                                       C.addressof(nb), order.ctypes.data, beta.ctypes.data, phi.ctypes.data,
+                                       R1.ctypes.data, C.addressof(r2), _stream())
+        if rc == -2:  # FG_ERR_UNSUPPORTED
+            return None
+        check(rc)
+        nk, nb = nk.value, nb.value
+        ng = nk - nb
+        return dict(keep=[int(x) for x in keep[:nk]], colsq=colsq, diag=diag[:nk + 1].copy(),
+                    base=[int(x) for x in order[:nb]], regroup=[int(x) for x in order[nb:nk]],
+                    beta=beta[:nb * ng].reshape(nb, ng).copy(), phi=phi[:nb].copy(),
+                    R1=R1[:nb * nb].reshape(nb, nb).copy(), resid2=r2.value)
+
+    def pivot_qr(self, keep):
+        """Column-pivoted QR of the kept columns, rhs carried along: (perm, R) with R (nk+1) x (nk+1)."""
+        keep = np.ascontiguousarray(keep, dtype=np.int32)
+        nk = len(keep)
+        perm = np.empty(nk, dtype=np.int32)
+        R = np.empty((nk + 1, nk + 1))
+        check(_lib.lib().fg_state_pivot_qr(self._h, keep.ctypes.data, nk, perm.ctypes.data, R.ctypes.data, _stream()))
+        return perm, R
+
     def regroup_solve(self, base, regroup):
         base = np.ascontiguousarray(base, dtype=np.int32)
         regroup = np.ascontiguousarray(regroup, dtype=np.int32)
@@ -398,24 +435,40 @@ def solve_state(state: TsqrState, names, tol_e=None, idx_e=None, tol_qr=TOL_QR, 
         p_full = p
     col_map = np.asarray(col_map, dtype=np.int64)
     if idx_e is None:
-        sq = state.colsq()[:p]
-        drop = set(i for i in range(p) if sq[i] < tol_e) if tol_e is not None else set()
+        fused = state.solve(tol_e, (), tol_qr)
     else:
         inv = {int(c): i for i, c in enumerate(col_map)}
-        drop = set(inv[int(c)] for c in idx_e if int(c) in inv)
-    keep_state = [i for i in range(p) if i not in drop]
-    sol.keep = [int(col_map[i]) for i in keep_state]
-    kept = set(sol.keep)
-    sol.idx_e = [i for i in range(int(p_full)) if i not in kept]
-    sol.params_r = [names[i] for i in sol.keep]
-    diag = state.reduce(keep_state)
-    sol.diag = diag
-    nk = len(sol.keep)
-    sol.idx_base = [i for i in range(nk) if diag[i] > tol_qr]
-    sol.idx_regroup = [i for i in range(nk) if not diag[i] > tol_qr]
-    if not sol.idx_base:
-        raise FgError(-1, "no column of the regressor exceeds tol_qr")
-    beta, phi, R1, r2 = state.regroup_solve(sol.idx_base, sol.idx_regroup)
+        fused = state.solve(None, set(inv[int(c)] for c in idx_e if int(c) in inv), tol_qr)
+    if fused is not None:  # one launch, one device-to-host copy
+        keep_state = fused["keep"]
+        sol.keep = [int(col_map[i]) for i in keep_state]
+        kept = set(sol.keep)
+        sol.idx_e = [i for i in range(int(p_full)) if i not in kept]
+        sol.params_r = [names[i] for i in sol.keep]
+        sol.diag = fused["diag"]
+        sol.idx_base, sol.idx_regroup = fused["base"], fused["regroup"]
+        if not sol.idx_base:
+            raise FgError(-1, "no column of the regressor exceeds tol_qr")
+        beta, phi, R1, r2 = fused["beta"], fused["phi"], fused["R1"], fused["resid2"]
+    else:
+        if idx_e is None:
+            sq = state.colsq()[:p]
+            drop = set(i for i in range(p) if sq[i] < tol_e) if tol_e is not None else set()
+        else:
+            drop = set(inv[int(c)] for c in idx_e if int(c) in inv)
+        keep_state = [i for i in range(p) if i not in drop]
+        sol.keep = [int(col_map[i]) for i in keep_state]
+        kept = set(sol.keep)
+        sol.idx_e = [i for i in range(int(p_full)) if i not in kept]
+        sol.params_r = [names[i] for i in sol.keep]
+        diag = state.reduce(keep_state)
+        sol.diag = diag
+        nk = len(sol.keep)
+        sol.idx_base = [i for i in range(nk) if diag[i] > tol_qr]
+        sol.idx_regroup = [i for i in range(nk) if not diag[i] > tol_qr]
+        if not sol.idx_base:
+            raise FgError(-1, "no column of the regressor exceeds tol_qr")
+        beta, phi, R1, r2 = state.regroup_solve(sol.idx_base, sol.idx_regroup)
     sol.beta_raw, sol.phi_b_raw, sol.R1, sol.resid2 = beta, phi, R1, r2
     sol.beta = np.around(beta, 6)
     sol.phi_b = np.round(phi, 6)

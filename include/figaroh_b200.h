@@ -169,6 +169,29 @@ int fg_state_regroup_solve(fg_state* s, const int32_t* base_host, int32_t n_base
                            int32_t n_regroup, double* beta_host, double* phi_host, double* R1_host,
                            double* resid2_host, void* stream);
 
+/* Column-pivoted QR of the kept columns with the rhs carried along: scipy.linalg.qr(W_e, pivoting=True) of
+ * QR_pivoting (qrdecomposition.py:24-86) evaluated on the factor (R^T R = W_e^T W_e, so the partial column
+ * norms the pivoting looks at are the same).  perm_host[n_keep]: pivoted column j is kept column perm[j];
+ * R_host: (n_keep+1) x (n_keep+1) row-major, [R P | Q^T tau]. */
+int fg_state_pivot_qr(fg_state* s, const int32_t* keep_host, int32_t n_keep, int32_t* perm_host, double* R_host,
+                      void* stream);
+
+/* The whole N-independent stage in one launch and one device-to-host copy:
+ *   keep  = columns with squared norm >= tol_e (get_index_eliminate, regressor.py:258-279; tol_e < 0: none
+ *           dropped by norm) that are not listed in drop_host,
+ *   base  = kept columns with |R_ii| > tol_qr in the re-triangularised factor (get_baseIndex,
+ *           qrdecomposition.py:274-296), regroup = the others,
+ *   beta, phi_b, R1, resid2 as fg_state_regroup_solve (double_QR, qrdecomposition.py:89-187).
+ * keep_host[p], colsq_host[p+1], diag_host[p+1] (n_keep+1 valid), order_host[p]: indices into keep_host, the
+ * n_base base columns first (ascending), then the regroup columns (ascending).  beta_host (n_base x
+ * n_regroup), phi_host (n_base), R1_host (n_base x n_base) must have room for p*p / p doubles.
+ * Returns FG_ERR_UNSUPPORTED for a permuted factor or one that does not fit shared memory: use the
+ * three-call sequence then.  Leaves the state as after fg_state_reduce(keep). */
+int fg_state_solve(fg_state* s, double tol_e, const int32_t* drop_host, int32_t n_drop, double tol_qr,
+                   int32_t* n_keep, int32_t* keep_host, double* colsq_host, double* diag_host, int32_t* n_base,
+                   int32_t* order_host, double* beta_host, double* phi_host, double* R1_host, double* resid2_host,
+                   void* stream);
+
 /* ---- host-buffer conveniences (end-to-end path: H2D copies inside the call) ----------
  * q,v,a,tau are HOST arrays (pinned or pageable); the call stages them through device
  * buffers in chunks, overlapping copies with the fused kernel, and folds them into s. */

@@ -136,3 +136,32 @@ def test_tiago_golden_csv_on_gpu():
     assert base == [g[0] for g in meta["golden_csv"]]
     np.testing.assert_allclose(phi_b, [g[1] for g in meta["golden_csv"]], atol=1.01e-6)
     assert np.mean(phi_b == np.array([g[1] for g in meta["golden_csv"]])) > 0.9
+
+
+def test_qr_pivoting_matches_reference_semantics():
+    """QR_pivoting (qrdecomposition.py:24-86): pivot order, rank quirk, expressions and values against the
+    oracle's restatement (scipy.linalg.qr(pivoting=True) on the tall matrix)."""
+    from figaroh.tools.qrdecomposition import QR_pivoting
+    from oracle import ref_path
+    rng = np.random.default_rng(11)
+    M, p = 4000, 12
+    # well separated column norms (no pivoting ties), three exactly dependent columns
+    W = rng.normal(size=(M, p)) * np.array([9.0, 1.0, 7.5, 3.0, 12.0, 0.5, 2.0, 5.0, 1.5, 4.0, 6.0, 0.8])
+    W[:, 3] = 0.5 * W[:, 0] - 0.25 * W[:, 4]
+    W[:, 8] = 2.0 * W[:, 1]
+    W[:, 10] = W[:, 2] + 0.5 * W[:, 7]  # (equal weights would make the two residuals an exact pivoting tie)
+    names = [f"p{i}" for i in range(p)]
+    tau = W @ rng.normal(size=p) + 0.01 * rng.normal(size=M)
+    W_b, bp = QR_pivoting(tau, W, names)
+    W_b_ref, bp_ref = ref_path.QR_pivoting(tau, W, names)
+    def norm(expr):  # the order of the rank-deficient tail of the pivoting is rounding noise: compare term sets
+        tok = expr.split(" ")
+        return tok[0], sorted(zip(tok[1::2], tok[2::2]))
+    assert [norm(k) for k in bp.keys()] == [norm(k) for k in bp_ref.keys()]
+    np.testing.assert_allclose(np.array(list(bp.values())), np.array(list(bp_ref.values())), atol=2e-6)
+    assert W_b.shape == W_b_ref.shape
+    np.testing.assert_allclose(W_b, W_b_ref, rtol=1e-9, atol=1e-9)
+    # full column rank: the reference's rank stays 0 (quirk Q5) -> empty result
+    Wf = rng.normal(size=(500, 5))
+    W_b0, bp0 = QR_pivoting(Wf @ np.ones(5), Wf, names[:5])
+    assert W_b0.shape == (500, 0) and bp0 == {}

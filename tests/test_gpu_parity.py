@@ -220,3 +220,37 @@ def test_tx40_kat_double_qr():
     assert sol.params_base == meta["params_base"]
     assert [g[0] for g in meta["golden_csv"]] == sol.params_base
     np.testing.assert_allclose(sol.phi_b, meta["phi_b"], atol=2e-6)
+
+
+@pytest.mark.gpu
+def test_fused_solve_matches_three_call_sequence():
+    """fg_state_solve (one launch) == fg_state_colsq + fg_state_reduce + fg_state_regroup_solve."""
+    eng = _eng()
+    fm = load_flat("ur10")
+    N = 3000
+    q, v, a = rand_inputs(fm, N, 5, ((-3, 3), (-3, 3), (-6, 6)))
+    param = make_param(True, True, True, fv=TX40_PARAM["fv"], fs=TX40_PARAM["fs"], Ia=TX40_PARAM["Ia"], off=TX40_PARAM["off"])
+    dm = eng.DeviceModel(fm)
+    cfg = eng.RegressorConfig.from_param(param)
+    _, cols = dm.shape(cfg)
+    rng = np.random.default_rng(3)
+    tau = rng.normal(size=fm.nv * N)
+    st = eng.TsqrState(cols).accumulate_samples(dm, cfg, q, v, a, tau)
+    for tol_e, drop in ((1e-6, ()), (None, (0, 1, 2, 3, 4, 6, 7, 8, 9, 22, 23, 40))):
+        fused = st.solve(tol_e, drop, 1e-8)
+        assert fused is not None
+        sq = st.colsq()[:cols]
+        dropped = set(drop) | (set(i for i in range(cols) if sq[i] < tol_e) if tol_e is not None else set())
+        keep = [i for i in range(cols) if i not in dropped]
+        assert fused["keep"] == keep
+        np.testing.assert_array_equal(fused["colsq"][:cols], sq)
+        diag = st.reduce(keep)
+        np.testing.assert_allclose(fused["diag"], diag, rtol=1e-12, atol=1e-300)
+        base = [i for i in range(len(keep)) if diag[i] > 1e-8]
+        regroup = [i for i in range(len(keep)) if not diag[i] > 1e-8]
+        assert fused["base"] == base and fused["regroup"] == regroup
+        beta, phi, R1, r2 = st.regroup_solve(base, regroup)
+        np.testing.assert_allclose(fused["beta"], beta, rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(fused["phi"], phi, rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(np.abs(fused["R1"]), np.abs(R1), rtol=1e-10, atol=1e-12)
+        assert abs(fused["resid2"] / r2 - 1) < 1e-10
