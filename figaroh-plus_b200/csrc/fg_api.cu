@@ -840,7 +840,7 @@ extern "C" int fg_state_accumulate_samples_host(fg_state* s, const fg_model* mc,
   if (rc) return rc;
   if (N <= 0) return FG_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t chunk = std::min<int64_t>(N, 1 << 18);
+  const int64_t chunk = std::min<int64_t>(N, 1 << 17);  // the copies are the bottleneck (PCIe): a short last chunk keeps the un-overlapped compute tail short
   const int64_t per_sample = m->nq + 2 * m->nv + ms;
   const int64_t need = 2 * chunk * per_sample;
   if (need > s->stage_cap) {

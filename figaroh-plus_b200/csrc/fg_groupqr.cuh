@@ -278,18 +278,12 @@ __device__ __forceinline__ void gq_fold(double* tile, int nb, double* Rg, int k0
 }
 
 // ---------------------------------------------------------------------------------------------
-// regressor entries of (row group g, body): s = oM_body^-1 o A,  value[k] = s^T B[:, k]  (see tq_emit).
+// regressor entries of (row group g, body): value[k] = s^T B[:, k] with s = [sl; sa] the motion axis of the
+// row group expressed in the body's frame (see tq_emit).
 // ed = (first local slot << 10) | mask of the generated pinocchio parameters: the generated entries of one
 // body occupy consecutive local columns in parameter order.
-__device__ __forceinline__ void gq_emit(double* tile, int ed, const double* A, const double* oR, const double* op,
-                                        const double* om, const double* al, const double* ap, bool valid, int lane) {
-  double t[3], sl[3], sa[3];
-  cross3(op, A + 3, t);
-  for (int k = 0; k < 3; ++k) t[k] = A[k] - t[k];
-  for (int k = 0; k < 3; ++k) {
-    sl[k] = oR[k] * t[0] + oR[3 + k] * t[1] + oR[6 + k] * t[2];
-    sa[k] = oR[k] * A[3] + oR[3 + k] * A[4] + oR[6 + k] * A[5];
-  }
+__device__ __forceinline__ void gq_emit(double* tile, int ed, const double* sl, const double* sa, const double* om,
+                                        const double* al, const double* ap, bool valid, int lane) {
   double val[10];
   val[0] = sl[0] * ap[0] + sl[1] * ap[1] + sl[2] * ap[2];
   const double ww = om[0] * om[0] + om[1] * om[1] + om[2] * om[2];
@@ -329,8 +323,7 @@ static __device__ __forceinline__ void gq_generate(const GqParams& P, const GqGe
   const double* as = qdd + sc * P.nv;
   const GqGroup& G = S.grp[g];
   const int nproc = P.nproc;
-  double A[6] = {0, 0, 0, 0, 0, 0};
-  double oR[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, op[3] = {0, 0, 0};
+  double sx[6] = {0, 0, 0, 0, 0, 0};  // motion axis of the row group in the frame of the joint being walked
   double v[6] = {0, 0, 0, 0, 0, 0}, a[6] = {0, 0, 0, 0, 0, 0};
   double nq0 = __ldg(qs + S.pj[0].idx_q), nv0 = __ldg(vs + S.pj[0].idx_v), na0 = __ldg(as + S.pj[0].idx_v);
   double nq1 = 0.0, nv1 = 0.0, na1 = 0.0;
@@ -348,8 +341,6 @@ static __device__ __forceinline__ void gq_generate(const GqParams& P, const GqGe
       nq1 = __ldg(qs + jn.idx_q); nv1 = __ldg(vs + jn.idx_v); na1 = __ldg(as + jn.idx_v);
     }
     if (jt.parent == 0) {  // restart from the universe (the host only admits chains hanging off it)
-      oR[0] = 1; oR[1] = 0; oR[2] = 0; oR[3] = 0; oR[4] = 1; oR[5] = 0; oR[6] = 0; oR[7] = 0; oR[8] = 1;
-      op[0] = op[1] = op[2] = 0.0;
       for (int k = 0; k < 6; ++k) v[k] = 0.0;
       a[0] = -P.gravity[0]; a[1] = -P.gravity[1]; a[2] = -P.gravity[2];
       a[3] = a[4] = a[5] = 0.0;
@@ -398,30 +389,28 @@ static __device__ __forceinline__ void gq_generate(const GqParams& P, const GqGe
       an[k] = l1[k] + l2[k] + aj[k] + R[k] * tt[0] + R[3 + k] * tt[1] + R[6 + k] * tt[2];
       an[3 + k] = l3[k] + aj[3 + k] + R[k] * a[3] + R[3 + k] * a[4] + R[6 + k] * a[5];
     }
-    // world pose oMi = oM_parent * liMi
-    double nR[9], np[3];
-    for (int r = 0; r < 3; ++r) {
-      for (int c = 0; c < 3; ++c) nR[3 * r + c] = oR[3 * r] * R[c] + oR[3 * r + 1] * R[3 + c] + oR[3 * r + 2] * R[6 + c];
-      np[r] = oR[3 * r] * p[0] + oR[3 * r + 1] * p[1] + oR[3 * r + 2] * p[2] + op[r];
-    }
-    for (int k = 0; k < 9; ++k) oR[k] = nR[k];
-    for (int k = 0; k < 3; ++k) op[k] = np[k];
     for (int k = 0; k < 6; ++k) { v[k] = vn[k]; a[k] = an[k]; }
-    if (G.tjoint == t) {  // world-frame motion axis of the row group
+    // the row group's motion axis: its own joint's axis at that joint, transported down the chain afterwards
+    // (liMi.actInv: the same transform the velocity takes) - the product of these transports is oM_body^-1 oM_joint
+    if (t == G.tjoint) {
+      for (int k = 0; k < 6; ++k) sx[k] = G.S[k];
       vg = cv0; ag = ca0;
+    } else if (t > G.tjoint) {
+      cross3(p, sx + 3, tt);
+      for (int k = 0; k < 3; ++k) tt[k] = sx[k] - tt[k];
+      double sn[6];
       for (int k = 0; k < 3; ++k) {
-        A[3 + k] = oR[3 * k] * G.S[3] + oR[3 * k + 1] * G.S[4] + oR[3 * k + 2] * G.S[5];
-        A[k] = oR[3 * k] * G.S[0] + oR[3 * k + 1] * G.S[1] + oR[3 * k + 2] * G.S[2];
+        sn[k] = R[k] * tt[0] + R[3 + k] * tt[1] + R[6 + k] * tt[2];
+        sn[3 + k] = R[k] * sx[3] + R[3 + k] * sx[4] + R[6 + k] * sx[5];
       }
-      cross3(op, A + 3, tt);
-      for (int k = 0; k < 3; ++k) A[k] += tt[k];
+      for (int k = 0; k < 6; ++k) sx[k] = sn[k];
     }
     const int ed = S.emit[g][t];
     if (ed) {
       double ap[3];
       cross3(v + 3, v, ap);  // classical acceleration a' = a_lin + w x v_lin
       for (int k = 0; k < 3; ++k) ap[k] += a[k];
-      gq_emit(tile, ed, A, oR, op, v + 3, a + 3, ap, valid, lane);
+      gq_emit(tile, ed, sx, sx + 3, v + 3, a + 3, ap, valid, lane);
     }
   }
   // columns read straight off the inputs

@@ -254,3 +254,26 @@ def test_fused_solve_matches_three_call_sequence():
         np.testing.assert_allclose(fused["phi"], phi, rtol=1e-10, atol=1e-12)
         np.testing.assert_allclose(np.abs(fused["R1"]), np.abs(R1), rtol=1e-10, atol=1e-12)
         assert abs(fused["resid2"] / r2 - 1) < 1e-10
+
+
+def test_host_chunked_continuation_matches_device():
+    """Host-buffer path (ramped chunks: first / continued / last launch of the fused kernel on the same
+    per-warp factors, one merge at the end) == one device-resident launch."""
+    eng = _eng()
+    fm = load_flat("ur10")
+    N = 120_000  # 32768 + 65536 + 21696 samples: three launches
+    q, v, a = rand_inputs(fm, N, 21, ((-3, 3), (-3, 3), (-6, 6)))
+    param = make_param(True, False, True, fv=TX40_PARAM["fv"], fs=TX40_PARAM["fs"], off=TX40_PARAM["off"])
+    dm = eng.DeviceModel(fm)
+    cfg = eng.RegressorConfig.from_param(param)
+    _, cols = dm.shape(cfg)
+    names = [f"c{i}" for i in range(cols)]
+    rng = np.random.default_rng(2)
+    tau = rng.normal(size=fm.nv * N)
+    sol_d = eng.identify(dm, cfg, q, v, a, tau, names, tol_e=1e-6)
+    sol_h = eng.identify(dm, cfg, q, v, a, tau, names, tol_e=1e-6, host_inputs=True)
+    assert sol_h.rows == sol_d.rows == N * fm.nv
+    assert sol_h.idx_e == sol_d.idx_e and sol_h.idx_base == sol_d.idx_base
+    assert sol_h.params_base == sol_d.params_base
+    np.testing.assert_allclose(sol_h.phi_b_raw, sol_d.phi_b_raw, rtol=1e-9, atol=1e-12)
+    assert abs(sol_h.resid2 / sol_d.resid2 - 1) < 1e-10
