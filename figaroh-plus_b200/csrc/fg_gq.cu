@@ -112,7 +112,7 @@ GqLaunch gq_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, co
   }
   if (maxnb > GQ_MAXB || T.nbf > GQ_MAXB) { gq_fail(why, "more than 12 column blocks"); return gl; }
   T.maxnb = maxnb;
-  gl.smem_merge = (std::max(maxnb, T.nbf) * GQ_BLK + GQ_SCRATCH) * 8;
+  gl.smem_merge = (2 * std::max(maxnb, T.nbf) * GQ_BLK + GQ_SCRATCH) * 8;  // 64-row slabs
   if (gl.smem_merge > max_smem) { gq_fail(why, "tile does not fit shared memory"); return gl; }
   // ---- warps per row group, proportional to the instruction cost of one tile of that group (forward pass,
   //      one emit per supported body, nb panels + T factors, nb (nb - 1) / 2 trailing blocks; calibrated on

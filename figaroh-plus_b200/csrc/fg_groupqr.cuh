@@ -48,15 +48,18 @@ __device__ __forceinline__ double gq_ld(const double* p) {
 // Compact-WY factor from the register fragments of the normalised reflectors:
 // T^-1 = diag(1/tau) + striu(V^T V); V^T V is a DMMA whose A and B fragments are the same register
 // (the row contraction runs over the rows in fragment order).  sc[0..7]: taus; TS: T row-major.
-__device__ __forceinline__ void gq_panel_T(const double (&vc0)[4], const double (&vc1)[4], const double* sc, double* TS,
-                                           int lane) {
+template <int RPL>
+__device__ __forceinline__ void gq_panel_T(const double (&vc0)[RPL][4], const double (&vc1)[RPL][4], const double* sc,
+                                           double* TS, int lane) {
   const int cq = lane >> 2, rq = lane & 3;
   double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
 #pragma unroll
-  for (int nn = 0; nn < 4; ++nn) {
-    tq_dmma(a0, a1, vc0[nn], vc0[nn]);
-    tq_dmma(b0, b1, vc1[nn], vc1[nn]);
-  }
+  for (int sl = 0; sl < RPL; ++sl)
+#pragma unroll
+    for (int nn = 0; nn < 4; ++nn) {
+      tq_dmma(a0, a1, vc0[sl][nn], vc0[sl][nn]);
+      tq_dmma(b0, b1, vc1[sl][nn], vc1[sl][nn]);
+    }
   a0 += b0;
   a1 += b1;
   if (2 * rq < cq) TS[cq * 8 + 2 * rq] = a0;
@@ -118,8 +121,10 @@ __device__ __forceinline__ double gq_rcp(double x) {
 // Rin and Rout may be the same 64 doubles (row j is stored only after every lane has read it).
 // On exit x holds the normalised reflectors v = x / (alpha - beta) (LAPACK dlarfg convention), Rout the
 // updated block (upper triangle), sc[0..7] the taus (0 for a skipped / padding column).
-__device__ __forceinline__ void gq_panel_factor(double (&x)[8], const double* Rin, double* Rout, double* sc, double* Pb,
-                                                int lane) {
+// RPL rows per lane (x[s][c] = entry (row = lane of slab s, column c)): the merge kernel folds 64-row slabs.
+template <int RPL>
+__device__ __forceinline__ void gq_panel_factor(double (&x)[RPL][8], const double* Rin, double* Rout, double* sc,
+                                                double* Pb, int lane) {
   const int ci = lane >> 2, part = lane & 3;
   int rd[4];
 #pragma unroll
@@ -129,7 +134,12 @@ __device__ __forceinline__ void gq_panel_factor(double (&x)[8], const double* Ri
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
 #pragma unroll
-    for (int c = j; c < 8; ++c) Pb[c * 32 + ((lane + 4 * c) & 31)] = x[j] * x[c];
+    for (int c = j; c < 8; ++c) {
+      double pr = x[0][j] * x[0][c];
+#pragma unroll
+      for (int sl = 1; sl < RPL; ++sl) pr = fma(x[sl][j], x[sl][c], pr);
+      Pb[c * 32 + ((lane + 4 * c) & 31)] = pr;
+    }
     __syncwarp();
     if (j > 0 && lane == 0) {
 #pragma unroll
@@ -173,10 +183,12 @@ __device__ __forceinline__ void gq_panel_factor(double (&x)[8], const double* Ri
       const double rho = Rin[j * 8 + c];
       const double w = tauh * fma(d[c], inv, rho);  // tau * v^T [rho; b]  (0 when the reflector is skipped)
       const double coef = w * inv;
-      x[c] = fma(-coef, x[j], x[c]);
+#pragma unroll
+      for (int sl = 0; sl < RPL; ++sl) x[sl][c] = fma(-coef, x[sl][j], x[sl][c]);
       rw[c] = rho - w;
     }
-    x[j] *= inv;  // H = I (dlarfg with xnorm == 0) leaves v = 0
+#pragma unroll
+    for (int sl = 0; sl < RPL; ++sl) x[sl][j] *= inv;  // H = I (dlarfg with xnorm == 0) leaves v = 0
   }
   __syncwarp();
   if (lane == 0) Rout[63] = rw[7];
