@@ -195,9 +195,10 @@ __device__ __forceinline__ void gq_panel_factor(double (&x)[RPL][8], const doubl
   __syncwarp();
 }
 
-// Fold a 32-row tile (nb blocks of 8 columns, shared memory, blocks < k0 all zero) into the
-// block-upper-triangular factor Rg (nb (nb + 1) / 2 blocks of 8 x 8, row-major, global memory).
-template <bool CG>
+// Fold a tile of RPL slabs of 32 rows (slab s, block j at tile + (s nb + j) GQ_BLK; nb blocks of 8 columns,
+// shared memory, blocks < k0 all zero) into the block-upper-triangular factor Rg (nb (nb + 1) / 2 blocks of
+// 8 x 8, row-major, global memory).
+template <bool CG, int RPL>
 __device__ __forceinline__ void gq_fold(double* tile, int nb, double* Rg, int k0, double* scr, const GqOffs& o,
                                         int lane) {
   const int cq = lane >> 2, rq = lane & 3;
@@ -216,15 +217,17 @@ __device__ __forceinline__ void gq_fold(double* tile, int nb, double* Rg, int k0
     double* Xk = tile + k * GQ_BLK;
     Rin[lane] = d0;
     Rin[lane + 32] = d1;
-    double x[8];
+    double x[RPL][8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) x[c] = Xk[tq_idx(c, lane)];
+    for (int sl = 0; sl < RPL; ++sl)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) x[sl][c] = Xk[sl * nb * GQ_BLK + tq_idx(c, lane)];
     // first off-diagonal block of this block row: requested before the panel so that its L2 round trip is hidden
     double* Rb = Rd + 64;
     double r0 = 0.0, r1 = 0.0;
     if (k + 1 < nb) { r0 = gq_ld<CG>(Rb + (2 * rq) * 8 + cq); r1 = gq_ld<CG>(Rb + (2 * rq + 1) * 8 + cq); }
     __syncwarp();
-    gq_panel_factor(x, Rin, Rout, sc, Xk, lane);
+    gq_panel_factor<RPL>(x, Rin, Rout, sc, Xk, lane);
     if ((lane >> 3) <= (lane & 7)) Rd[lane] = Rout[lane];            // rows 0..3 of the upper triangle
     if ((lane >> 3) + 4 <= (lane & 7)) Rd[lane + 32] = Rout[lane + 32];  // rows 4..7
     if (k + 1 == nb) break;
@@ -234,18 +237,22 @@ __device__ __forceinline__ void gq_fold(double* tile, int nb, double* Rg, int k0
       d1 = gq_ld<CG>(Rn + lane + 32);
     }
 #pragma unroll
-    for (int c = 0; c < 8; ++c) Xk[tq_idx(c, lane)] = x[c];
+    for (int sl = 0; sl < RPL; ++sl)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) Xk[sl * nb * GQ_BLK + tq_idx(c, lane)] = x[sl][c];
     __syncwarp();
     // reflector fragments of this panel, kept in registers for every trailing block
-    double vc0[4], vc1[4], vb0[4], vb1[4];
+    double vc0[RPL][4], vc1[RPL][4], vb0[RPL][4], vb1[RPL][4];
 #pragma unroll
-    for (int nn = 0; nn < 4; ++nn) {
-      vc0[nn] = Xk[o.oc0[nn]];
-      vc1[nn] = Xk[o.oc1[nn]];
-      vb0[nn] = Xk[o.ob0[nn]];
-      vb1[nn] = Xk[o.ob1[nn]];
-    }
-    gq_panel_T(vc0, vc1, sc, TS, lane);
+    for (int sl = 0; sl < RPL; ++sl)
+#pragma unroll
+      for (int nn = 0; nn < 4; ++nn) {
+        vc0[sl][nn] = Xk[sl * nb * GQ_BLK + o.oc0[nn]];
+        vc1[sl][nn] = Xk[sl * nb * GQ_BLK + o.oc1[nn]];
+        vb0[sl][nn] = Xk[sl * nb * GQ_BLK + o.ob0[nn]];
+        vb1[sl][nn] = Xk[sl * nb * GQ_BLK + o.ob1[nn]];
+      }
+    gq_panel_T<RPL>(vc0, vc1, sc, TS, lane);
     const double t0 = TS[(2 * rq) * 8 + cq], t1 = TS[(2 * rq + 1) * 8 + cq];
     for (int j = k + 1; j < nb; ++j, Rb += 64) {
       double nr0 = 0.0, nr1 = 0.0;
@@ -254,16 +261,23 @@ __device__ __forceinline__ void gq_fold(double* tile, int nb, double* Rg, int k0
         nr1 = gq_ld<CG>(Rb + 64 + (2 * rq + 1) * 8 + cq);
       }
       double* Bj = tile + j * GQ_BLK;
-      double c0[4], c1[4];
+      double c0[RPL][4], c1[RPL][4];
 #pragma unroll
-      for (int nn = 0; nn < 4; ++nn) { c0[nn] = Bj[o.oc0[nn]]; c1[nn] = Bj[o.oc1[nn]]; }
+      for (int sl = 0; sl < RPL; ++sl)
+#pragma unroll
+        for (int nn = 0; nn < 4; ++nn) {
+          c0[sl][nn] = Bj[sl * nb * GQ_BLK + o.oc0[nn]];
+          c1[sl][nn] = Bj[sl * nb * GQ_BLK + o.oc1[nn]];
+        }
       // Y^T = R_kj^T + B_j^T V   (rows contracted in fragment order: the C fragments are the A operands)
       double y0 = 0.0, y1 = 0.0, z0 = 0.0, z1 = 0.0;
 #pragma unroll
-      for (int nn = 0; nn < 4; ++nn) {
-        tq_dmma(y0, y1, c0[nn], vc0[nn]);
-        tq_dmma(z0, z1, c1[nn], vc1[nn]);
-      }
+      for (int sl = 0; sl < RPL; ++sl)
+#pragma unroll
+        for (int nn = 0; nn < 4; ++nn) {
+          tq_dmma(y0, y1, c0[sl][nn], vc0[sl][nn]);
+          tq_dmma(z0, z1, c1[sl][nn], vc1[sl][nn]);
+        }
       y0 += z0 + r0;
       y1 += z1 + r1;
       // W^T = Y^T T
@@ -275,12 +289,14 @@ __device__ __forceinline__ void gq_fold(double* tile, int nb, double* Rg, int k0
       const double nw0 = -w0, nw1 = -w1;
       // B_j^T -= W^T V^T
 #pragma unroll
-      for (int nn = 0; nn < 4; ++nn) {
-        tq_dmma(c0[nn], c1[nn], nw0, vb0[nn]);
-        tq_dmma(c0[nn], c1[nn], nw1, vb1[nn]);
-        Bj[o.oc0[nn]] = c0[nn];
-        Bj[o.oc1[nn]] = c1[nn];
-      }
+      for (int sl = 0; sl < RPL; ++sl)
+#pragma unroll
+        for (int nn = 0; nn < 4; ++nn) {
+          tq_dmma(c0[sl][nn], c1[sl][nn], nw0, vb0[sl][nn]);
+          tq_dmma(c0[sl][nn], c1[sl][nn], nw1, vb1[sl][nn]);
+          Bj[sl * nb * GQ_BLK + o.oc0[nn]] = c0[sl][nn];
+          Bj[sl * nb * GQ_BLK + o.oc1[nn]] = c1[sl][nn];
+        }
       r0 = nr0;
       r1 = nr1;
     }
@@ -498,7 +514,7 @@ gq_accumulate_kernel(const __grid_constant__ GqParams P, const unsigned char* __
     __syncwarp();
     gq_generate(P, S, g, tile, q, qd, qdd, tau, ld_tau, tl * GQ_S, N, lane);
     __syncwarp();
-    gq_fold<false>(tile, nb, Rg, 0, scr, offs, lane);
+    gq_fold<false, 1>(tile, nb, Rg, 0, scr, offs, lane);
   }
 }
 
@@ -514,14 +530,17 @@ struct GqMergeArgs {
 
 __device__ __forceinline__ void gq_merge_into(const GqParams& P, double* tile, int nb, double* Rdst, const double* Rsrc,
                                               double* scr, const GqOffs& o, int lane) {
-  for (int t0 = 0; t0 < nb; t0 += 4) {
+  // 64-row slabs (two rows per lane): 8 block rows of the source per fold, i.e. ONE fold for nb <= 8
+  for (int t0 = 0; t0 < nb; t0 += 8) {
     {
       double2* t2 = reinterpret_cast<double2*>(tile);
-      for (int i = lane; i < nb * (GQ_BLK / 2); i += 32) t2[i] = make_double2(0.0, 0.0);
+      for (int i = lane; i < 2 * nb * (GQ_BLK / 2); i += 32) t2[i] = make_double2(0.0, 0.0);
     }
     __syncwarp();
-    for (int m = 0; m < 4 && t0 + m < nb; ++m) {
+    for (int m = 0; m < 8 && t0 + m < nb; ++m) {
       const int rb = t0 + m;
+      double* slab = tile + (size_t)(m >> 2) * nb * GQ_BLK;
+      const int mm = m & 3;
       // the blocks of one block row are consecutive: request all of them before the first one is stored
       const double* B = Rsrc + (size_t)tq_rblk(nb, rb, rb) * 64;
       double v0[GQ_MAXB], v1[GQ_MAXB];
@@ -531,12 +550,12 @@ __device__ __forceinline__ void gq_merge_into(const GqParams& P, double* tile, i
 #pragma unroll
       for (int jj = 0; jj < GQ_MAXB; ++jj)
         if (rb + jj < nb) {
-          tile[(rb + jj) * GQ_BLK + tq_idx(lane & 7, 8 * m + (lane >> 3))] = v0[jj];
-          tile[(rb + jj) * GQ_BLK + tq_idx(lane & 7, 8 * m + 4 + (lane >> 3))] = v1[jj];
+          slab[(rb + jj) * GQ_BLK + tq_idx(lane & 7, 8 * mm + (lane >> 3))] = v0[jj];
+          slab[(rb + jj) * GQ_BLK + tq_idx(lane & 7, 8 * mm + 4 + (lane >> 3))] = v1[jj];
         }
     }
     __syncwarp();
-    gq_fold<true>(tile, nb, Rdst, t0, scr, o, lane);
+    gq_fold<true, 2>(tile, nb, Rdst, t0, scr, o, lane);
   }
 }
 
@@ -551,7 +570,7 @@ gq_merge_kernel(const __grid_constant__ GqParams P, const __grid_constant__ GqMe
   const int leaves = M.leaves[g];
   const int mb = P.maxnb > P.nbf ? P.maxnb : P.nbf;
   double* tile = gq_smem;
-  double* scr = gq_smem + mb * GQ_BLK;
+  double* scr = gq_smem + 2 * mb * GQ_BLK;
   GqOffs offs;
   gq_make_offs(offs, lane);
   const GqGroup& G = P.gen.grp[g];
@@ -614,15 +633,17 @@ gq_merge_kernel(const __grid_constant__ GqParams P, const __grid_constant__ GqMe
     }
     const GqGroup& H = P.gen.grp[gg];
     const double* Rsrc = r_all + H.r_off;
-    for (int t0 = 0; t0 < H.nb; t0 += 4) {
+    for (int t0 = 0; t0 < H.nb; t0 += 8) {  // 64-row slabs of the root
       {
         double2* t2 = reinterpret_cast<double2*>(tile);
-        for (int idx = lane; idx < nbf * (GQ_BLK / 2); idx += 32) t2[idx] = make_double2(0.0, 0.0);
+        for (int idx = lane; idx < 2 * nbf * (GQ_BLK / 2); idx += 32) t2[idx] = make_double2(0.0, 0.0);
       }
       __syncwarp();
       int kmin = nbf - 1;
-      for (int m = 0; m < 4 && t0 + m < H.nb; ++m) {
+      for (int m = 0; m < 8 && t0 + m < H.nb; ++m) {
         const int rb = t0 + m;
+        double* slab = tile + (size_t)(m >> 2) * nbf * GQ_BLK;
+        const int mm = m & 3;
         const double* B = Rsrc + (size_t)tq_rblk(H.nb, rb, rb) * 64;
         double v0[GQ_MAXB], v1[GQ_MAXB];
 #pragma unroll
@@ -633,15 +654,15 @@ gq_merge_kernel(const __grid_constant__ GqParams P, const __grid_constant__ GqMe
           const int l = 8 * (rb + jj) + (lane & 7);
           if (rb + jj < H.nb && l < H.w) {
             const int scol = P.gcol[gg][l];
-            tile[(scol >> 3) * GQ_BLK + tq_idx(scol & 7, 8 * m + (lane >> 3))] = v0[jj];
-            tile[(scol >> 3) * GQ_BLK + tq_idx(scol & 7, 8 * m + 4 + (lane >> 3))] = v1[jj];
+            slab[(scol >> 3) * GQ_BLK + tq_idx(scol & 7, 8 * mm + (lane >> 3))] = v0[jj];
+            slab[(scol >> 3) * GQ_BLK + tq_idx(scol & 7, 8 * mm + 4 + (lane >> 3))] = v1[jj];
             kmin = min(kmin, scol >> 3);
           }
         }
       }
       kmin = __reduce_min_sync(0xffffffffu, kmin);
       __syncwarp();
-      gq_fold<true>(tile, nbf, rfull, kmin, scr, offs, lane);
+      gq_fold<true, 2>(tile, nbf, rfull, kmin, scr, offs, lane);
     }
     __threadfence();
     __syncwarp();
