@@ -82,25 +82,63 @@ def standard_phi(fm):
 
 
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: an NVML polling thread (every ~2 ms, the
+    timed region of the default run lasts ~50 ms), nvidia-smi -lms as the fallback when pynvml is missing."""
+
+    _REASONS = (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
+
     def __init__(self, index):
-        self.proc = None
         self.index = index
+        self.proc = None
+        self.thread = None
+        self.stop_flag = False
+        self.sm, self.reason_bits, self.mx = [], 0, None
         self.path = f"/tmp/fg_bench_clocks_{os.getpid()}.csv"
 
+    def _poll(self):
+        import pynvml as nv
+        h = self.handle
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.002)
+
     def start(self):
+        try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            self.handle = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:  # noqa: BLE001
+            self.thread = None
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index),
                  "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
                  "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "100"],
+                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:  # noqa: BLE001
             self.proc = None
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            if self.sm:
+                out = {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": self.mx,
+                       "reasons": sorted(n for n, bit in self._REASONS if self.reason_bits & bit),
+                       "samples": len(self.sm), "source": "nvml"}
+            return out
         if self.proc is None:
             return out
         self.proc.terminate()
@@ -122,7 +160,8 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         if sm:
-            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                   "source": "nvidia-smi"}
         try:
             os.remove(self.path)
         except OSError:
