@@ -277,3 +277,69 @@ def test_host_chunked_continuation_matches_device():
     assert sol_h.params_base == sol_d.params_base
     np.testing.assert_allclose(sol_h.phi_b_raw, sol_d.phi_b_raw, rtol=1e-9, atol=1e-12)
     assert abs(sol_h.resid2 / sol_d.resid2 - 1) < 1e-10
+
+
+def test_fused_tiago_active_joints_tree_matches_dense():
+    """BASELINE config 3 shape: TIAGo, rows of the 8 active joints (torso + arm, examples/tiago/identification.py
+    :157-166) on the 24-DoF tree (grippers and head branch off the chain: the generic fused kernel takes it).
+    Fused path == materialise + row selection + dense TSQR, index sets identical, phi_b within 1e-9."""
+    import torch
+    eng = _eng()
+    fm = load_flat("tiago")
+    N = 700
+    q, v, a = rand_inputs(fm, N, 9, ((-1.5, 1.5), (-2, 2), (-4, 4)))
+    rows = [fm.idx_v[i] for i in range(13, 21)]  # torso_lift + arm_1..7
+    active = set(rows)
+    for j in range(fm.nv):  # the other joints rest, as in the recorded trajectories
+        if j not in active:
+            v[:, j] = 0.0
+            a[:, j] = 0.0
+    for i in range(1, fm.njoints):
+        if fm.idx_v[i] not in active:
+            iq = fm.idx_q[i]
+            if fm.jtype[i] == 2:
+                q[:, iq], q[:, iq + 1] = 1.0, 0.0
+            else:
+                q[:, iq] = 0.1
+    param = make_param(True, True, True)
+    dm = eng.DeviceModel(fm)
+    cfg = eng.RegressorConfig.from_param(param, row_sel=rows)
+    rps, cols = dm.shape(cfg)
+    assert rps == 8
+    names = [f"c{i}" for i in range(cols)]
+    rng = np.random.default_rng(4)
+    tau = rng.normal(size=rps * N)
+    sol = eng.identify(dm, cfg, q, v, a, tau, names, tol_e=1e-3)
+    W = dm.materialize(cfg, q, v, a)                       # all 24 row blocks, reference layout
+    Wsel = W.view(fm.nv, N, cols)[torch.as_tensor(rows, device=W.device)].reshape(rps * N, cols).contiguous()
+    st = eng.TsqrState(cols).accumulate_dense(Wsel, tau)
+    ref = eng.solve_state(st, names, tol_e=1e-3)
+    assert sol.idx_e == ref.idx_e and sol.idx_base == ref.idx_base and sol.params_base == ref.params_base
+    cond = np.linalg.cond(ref.R1)
+    np.testing.assert_allclose(sol.phi_b_raw, ref.phi_b_raw, rtol=1e-9 * max(1.0, cond / 1e3), atol=1e-12)
+
+
+def test_fused_talos_external_wrench_matches_dense():
+    """BASELINE config 4 shape: Talos with free-flyer, external-wrench rows ('All'), flags off.  The generic
+    fused kernel (6 row groups on the root joint, 330 non-zero columns) == materialise + dense TSQR."""
+    eng = _eng()
+    fm = load_flat("talos_ff")
+    N = 400
+    q, v, a = rand_inputs(fm, N, 13, ((-1, 1), (-1, 1), (-1, 1)))
+    param = dict(is_joint_torques=False, is_external_wrench=True, force_torque=["All"], has_friction=False,
+                 has_actuator_inertia=False, has_joint_offset=False, fv=None, fs=None, Ia=None, off=None)
+    dm = eng.DeviceModel(fm)
+    cfg = eng.RegressorConfig.from_param(param)
+    rps, cols = dm.shape(cfg)
+    assert rps == 6 and cols == 14 * (fm.njoints - 1)
+    names = [f"c{i}" for i in range(cols)]
+    rng = np.random.default_rng(8)
+    tau = rng.normal(size=rps * N)
+    sol = eng.identify(dm, cfg, q, v, a, tau, names, tol_e=1e-6)
+    W = dm.materialize(cfg, q, v, a)
+    st = eng.TsqrState(cols).accumulate_dense(W, tau)
+    ref = eng.solve_state(st, names, tol_e=1e-6)
+    assert sol.idx_e == ref.idx_e and len(sol.idx_e) == 132
+    assert sol.idx_base == ref.idx_base and len(sol.idx_base) == 234
+    cond = np.linalg.cond(ref.R1)
+    np.testing.assert_allclose(sol.phi_b_raw, ref.phi_b_raw, rtol=1e-9 * max(1.0, cond / 1e3), atol=1e-11)
