@@ -1057,9 +1057,10 @@ extern "C" int fg_state_solve(fg_state* s, double tol_e, const int32_t* drop, in
     if (!drop || drop[i] < 0 || drop[i] >= p) return set_err(FG_ERR_INVALID, "fg_state_solve: bad column index in drop");
     flags[drop[i]] = 1;
   }
-  FG_CUDA(cudaMemcpyAsync(s->d_idx, flags.data(), sizeof(int) * p, cudaMemcpyHostToDevice, st));
+  if (n_drop > 0) FG_CUDA(cudaMemcpyAsync(s->d_idx, flags.data(), sizeof(int) * p, cudaMemcpyHostToDevice, st));
   FG_CUDA(cudaFuncSetAttribute(fused_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  fused_solve_kernel<<<1, 256, smem, st>>>(s->d_part, p1, s->d_idx, tol_e, tol_qr, s->d_Re, s->d_solve);
+  fused_solve_kernel<<<1, 256, smem, st>>>(s->d_part, p1, n_drop > 0 ? s->d_idx : nullptr, tol_e, tol_qr, s->d_Re,
+                                           s->d_solve);
   FG_CUDA(cudaGetLastError());
   FG_LAUNCHED();
   std::vector<double> h(blob);

@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(256) fused_solve_kernel(const double* __restri
   for (int c = threadIdx.x; c < p1; c += blockDim.x) {
     const double sq = part[ntri + c];
     o_colsq[c] = sq;
-    order[c] = c < p && (force_drop[c] != 0 || (tol_e >= 0.0 && sq < tol_e));  // drop flag, in parallel
+    order[c] = c < p && ((force_drop != nullptr && force_drop[c] != 0) || (tol_e >= 0.0 && sq < tol_e));  // drop flag
   }
   __syncthreads();
   if (threadIdx.x == 0) {
