@@ -15,6 +15,7 @@
 #include "fg_bq.h"
 #include "fg_tq.h"
 #include "fg_gq.h"
+#include "fg_prefilter.cuh"
 
 using namespace fg;
 
@@ -883,6 +884,79 @@ extern "C" int fg_state_accumulate_samples_host(fg_state* s, const fg_model* mc,
     if (rc) return rc;
     FG_CUDA(cudaEventRecord(s->ev[2 + b], st));
   }
+  return FG_OK;
+}
+
+// ---- preprocessing ahead of the regressor
+// scipy.signal.filtfilt(b, a, x, axis=0, padtype="odd", padlen) followed by dropping `trim` rows at both ends
+// (low_pass_filter_data, identification_tools.py:390-424).  b, a, zi are HOST arrays (a[0] != 0; zi =
+// scipy.signal.lfilter_zi(b, a), order entries); x and y are device matrices.
+extern "C" int fg_filtfilt(const double* x, int64_t N, int32_t ncols, int64_t ldx, const double* b, int32_t nb,
+                           const double* a, int32_t na, const double* zi, int32_t padlen, int64_t trim, double* y,
+                           int64_t ldy, void* stream) {
+  if (!x || !y || !b || !a || !zi || N < 1 || ncols < 1 || ldx < ncols || ldy < ncols || nb < 1 || na < 1 || a[0] == 0.0)
+    return set_err(FG_ERR_INVALID, "fg_filtfilt: bad argument");
+  const int n = std::max(nb, na) - 1;
+  if (n < 1 || n > IIR_MAXN) return set_err(FG_ERR_UNSUPPORTED, "fg_filtfilt: filter order %d outside [1,%d]", n, IIR_MAXN);
+  if (padlen < 0 || padlen >= N) return set_err(FG_ERR_INVALID, "fg_filtfilt: padlen=%d needs more than %d samples", padlen, padlen);
+  if (trim < 0 || 2 * trim >= N) return set_err(FG_ERR_INVALID, "fg_filtfilt: trim=%lld leaves no row", (long long)trim);
+  cudaStream_t st = (cudaStream_t)stream;
+  IirCoef F;
+  memset(&F, 0, sizeof F);
+  F.n = n;
+  for (int i = 0; i <= n; ++i) { F.b[i] = (i < nb ? b[i] : 0.0) / a[0]; F.a[i] = (i < na ? a[i] : 0.0) / a[0]; }
+  for (int i = 0; i < n; ++i) F.zi[i] = zi[i];
+  {  // A^L by repeated multiplication (A: homogeneous part of the recurrence)
+    std::vector<double> A(n * n, 0.0), Pw(n * n, 0.0), T(n * n);
+    for (int i = 0; i < n; ++i) { A[i * n] = -F.a[i + 1]; if (i + 1 < n) A[i * n + i + 1] += 1.0; Pw[i * n + i] = 1.0; }
+    for (int l = 0; l < IIR_L; ++l) {
+      for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+          double acc = 0.0;
+          for (int k = 0; k < n; ++k) acc += A[i * n + k] * Pw[k * n + j];
+          T[i * n + j] = acc;
+        }
+      Pw = T;
+    }
+    for (int i = 0; i < n * n; ++i) F.AL[i] = Pw[i];
+  }
+  const int64_t M = N + 2 * (int64_t)padlen;
+  const int64_t nchunks = (M + IIR_L - 1) / IIR_L;
+  double *y1 = nullptr, *S = nullptr, *Z0 = nullptr;
+  FG_CUDA(cudaMallocAsync(&y1, sizeof(double) * M * ncols, st));
+  FG_CUDA(cudaMallocAsync(&S, sizeof(double) * nchunks * ncols * IIR_MAXN, st));
+  FG_CUDA(cudaMallocAsync(&Z0, sizeof(double) * nchunks * ncols * IIR_MAXN, st));
+  const int threads = 128;
+  const int blocks = (int)((nchunks * ncols + threads - 1) / threads);
+  for (int pass = 0; pass < 2; ++pass) {
+    IirIo io;
+    io.N = N; io.M = M; io.padlen = padlen; io.ncols = ncols; io.backward = pass; io.trim = trim;
+    if (pass == 0) { io.x = x; io.ldx = ldx; io.y = y1; io.ldy = ncols; }
+    else { io.x = y1; io.ldx = ncols; io.y = y; io.ldy = ldy; }
+    iir_chunk_kernel<false><<<blocks, threads, 0, st>>>(F, io, S, nullptr);
+    iir_propagate_kernel<<<(ncols + 63) / 64, 64, 0, st>>>(F, io, S, Z0);
+    iir_chunk_kernel<true><<<blocks, threads, 0, st>>>(F, io, nullptr, Z0);
+    FG_CUDA(cudaGetLastError());
+    FG_LAUNCHED(); FG_LAUNCHED(); FG_LAUNCHED();
+  }
+  FG_CUDA(cudaFreeAsync(y1, st));
+  FG_CUDA(cudaFreeAsync(S, st));
+  FG_CUDA(cudaFreeAsync(Z0, st));
+  return FG_OK;
+}
+
+// calculate_first_second_order_differentiation (identification_tools.py:334-387) for vector-space joints
+// (nq == nv): q (N x nq, device) -> dq, ddq ((N - 2) x nq, device); dt_dev == NULL: constant step dt.
+extern "C" int fg_differentiate(const double* q, int64_t N, int32_t nq, int64_t ldq, double dt, const double* dt_dev,
+                                double* dq, double* ddq, int64_t ldo, void* stream) {
+  if (!q || !dq || !ddq || N < 3 || nq < 1 || ldq < nq || ldo < nq || (!dt_dev && dt == 0.0))
+    return set_err(FG_ERR_INVALID, "fg_differentiate: bad argument (needs N >= 3)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t work = (N - 2) * nq;
+  const int blocks = (int)std::min<int64_t>((work + 255) / 256, 148 * 16);
+  differentiate_kernel<<<blocks, 256, 0, st>>>(q, N, nq, ldq, dt, dt_dev, dq, ddq, ldo);
+  FG_CUDA(cudaGetLastError());
+  FG_LAUNCHED();
   return FG_OK;
 }
 

@@ -21,7 +21,7 @@ SYMBOLS = (
     "fg_regressor_materialize", "fg_state_create", "fg_state_destroy", "fg_state_reset", "fg_state_p",
     "fg_state_rows", "fg_state_accumulate_dense", "fg_state_accumulate_samples", "fg_state_packed_doubles",
     "fg_state_export", "fg_state_merge_packed", "fg_state_colsq", "fg_state_reduce", "fg_state_regroup_solve",
-    "fg_state_solve", "fg_state_pivot_qr", "fg_state_accumulate_samples_host", "fg_state_get_perm", "fg_state_set_perm", "fg_launch_count", "fg_state_set_timing", "fg_state_get_timing",
+    "fg_state_solve", "fg_state_pivot_qr", "fg_filtfilt", "fg_differentiate", "fg_state_accumulate_samples_host", "fg_state_get_perm", "fg_state_set_perm", "fg_launch_count", "fg_state_set_timing", "fg_state_get_timing",
 )
 
 
@@ -84,6 +84,8 @@ def lib():
     L.fg_state_colsq.argtypes = [vp, dp, vp]
     L.fg_state_reduce.argtypes = [vp, vp, i32, dp, vp]
     L.fg_state_regroup_solve.argtypes = [vp, vp, i32, vp, i32, dp, dp, dp, dp, vp]
+    L.fg_filtfilt.argtypes = [dp, i64, i32, i64, vp, i32, vp, i32, vp, i32, i64, dp, i64, vp]
+    L.fg_differentiate.argtypes = [dp, i64, i32, i64, C.c_double, dp, dp, dp, i64, vp]
     L.fg_state_pivot_qr.argtypes = [vp, vp, i32, vp, dp, vp]
     L.fg_state_solve.argtypes = [vp, C.c_double, vp, i32, C.c_double, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.fg_launch_count.restype = C.c_longlong

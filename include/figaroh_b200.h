@@ -192,6 +192,21 @@ int fg_state_solve(fg_state* s, double tol_e, const int32_t* drop_host, int32_t 
                    int32_t* order_host, double* beta_host, double* phi_host, double* R1_host, double* resid2_host,
                    void* stream);
 
+/* ---- preprocessing ahead of the regressor (device matrices in, device matrices out) -----------------
+ * fg_filtfilt: scipy.signal.filtfilt(b, a, x, axis=0, padtype="odd", padlen=padlen) and removal of `trim`
+ * rows at both ends = low_pass_filter_data (src/figaroh/identification/identification_tools.py:390-424;
+ * b, a = butter(nbutter, ts*fc/2), padlen = 3*(max(len(a),len(b))-1), trim = 5*nbutter).  b_host, a_host,
+ * zi_host (= scipy.signal.lfilter_zi(b, a)) are host arrays; order <= 8.  y: (N - 2*trim) x ncols.
+ * fg_differentiate: calculate_first_second_order_differentiation (identification_tools.py:334-387) for
+ * models whose configuration is a vector space (nq == nv, pin.difference = subtraction): dq = forward
+ * difference / dt, ddq[:, j] = np.gradient(dq[:, j]) / dt for j < nq-1 and 0 for the last column (the
+ * reference's range(model.nq - 1)), N - 2 rows out; dt_dev (N-1 entries) overrides the constant dt. */
+int fg_filtfilt(const double* x_dev, int64_t N, int32_t ncols, int64_t ldx, const double* b_host, int32_t nb,
+                const double* a_host, int32_t na, const double* zi_host, int32_t padlen, int64_t trim,
+                double* y_dev, int64_t ldy, void* stream);
+int fg_differentiate(const double* q_dev, int64_t N, int32_t nq, int64_t ldq, double dt, const double* dt_dev,
+                     double* dq_dev, double* ddq_dev, int64_t ldo, void* stream);
+
 /* ---- host-buffer conveniences (end-to-end path: H2D copies inside the call) ----------
  * q,v,a,tau are HOST arrays (pinned or pageable); the call stages them through device
  * buffers in chunks, overlapping copies with the fused kernel, and folds them into s. */

@@ -165,3 +165,41 @@ def test_qr_pivoting_matches_reference_semantics():
     Wf = rng.normal(size=(500, 5))
     W_b0, bp0 = QR_pivoting(Wf @ np.ones(5), Wf, names[:5])
     assert W_b0.shape == (500, 0) and bp0 == {}
+
+
+def test_preprocessing_filter_and_differentiation_match_reference():
+    """low_pass_filter_data + calculate_first_second_order_differentiation (identification_tools.py:334-424)
+    on the GPU against the oracle's restatement (scipy.signal.filtfilt, np.gradient): <= 1e-9 relative."""
+    import torch
+    from figaroh.identification.identification_tools import (calculate_first_second_order_differentiation,
+                                                             low_pass_filter_data)
+    from oracle import pre
+    rng = np.random.default_rng(17)
+    for N, ncols, ts, fc, nb in ((5000, 6, 1e-3, 100.0, 5), (777, 3, 1e-2, 10.0, 4), (40, 2, 1e-2, 20.0, 2)):
+        t = np.arange(N)[:, None] * ts
+        x = np.sin(2 * np.pi * (0.7 + np.arange(ncols)) * t) + 0.05 * rng.normal(size=(N, ncols)) + 3.0
+        param = dict(ts=ts, cut_off_frequency_butterworth=fc, is_joint_torques=True, is_external_wrench=False)
+        ref = pre.low_pass_filter_data(x, param, nb)
+        out = low_pass_filter_data(x, param, nb)
+        assert out.shape == ref.shape and out.dtype == np.float64
+        assert np.abs(out - ref).max() <= 1e-9 * np.abs(ref).max()
+        out_d = low_pass_filter_data(torch.from_numpy(x).cuda(), param, nb)      # device in -> device out
+        assert out_d.is_cuda and np.array_equal(out_d.cpu().numpy(), out)
+        out1 = low_pass_filter_data(x[:, 0], param, nb)                          # 1-D signal
+        assert out1.shape == (ref.shape[0],) and np.abs(out1 - ref[:, 0]).max() <= 1e-9 * np.abs(ref).max()
+
+        class M:
+            nq = nv = ncols
+        qf = ref
+        q_r, dq_r, ddq_r = pre.calculate_first_second_order_differentiation(ncols, qf, param)
+        q_o, dq_o, ddq_o = calculate_first_second_order_differentiation(M, qf, param)
+        assert q_o.shape == q_r.shape and dq_o.shape == dq_r.shape and ddq_o.shape == ddq_r.shape
+        assert np.array_equal(q_o, q_r)
+        assert np.abs(dq_o - dq_r).max() <= 1e-9 * np.abs(dq_r).max()
+        assert np.abs(ddq_o - ddq_r).max() <= 1e-9 * np.abs(ddq_r).max()
+        assert np.all(ddq_o[:, -1] == 0.0)                                       # the reference's range(nq - 1)
+        dt = ts * (1.0 + 0.1 * rng.uniform(size=qf.shape[0] - 1))                # variable step
+        _, dq_r2, ddq_r2 = pre.calculate_first_second_order_differentiation(ncols, qf, param, dt)
+        _, dq_o2, ddq_o2 = calculate_first_second_order_differentiation(M, qf, param, dt)
+        assert np.abs(dq_o2 - dq_r2).max() <= 1e-9 * np.abs(dq_r2).max()
+        assert np.abs(ddq_o2 - ddq_r2).max() <= 1e-9 * np.abs(ddq_r2).max()

@@ -84,3 +84,21 @@ def test_free_flyer_in_joint_torque_mode_raises_like_reference():
         reg.build_regressor_basic(robot, q, v, a, make_param(False, False, False))
     with pytest.raises(ValueError):
         ref_path.build_regressor_basic(pinshim._oracle_model(robot.model), q, v, a, make_param(False, False, False))
+
+
+def test_preprocessing_restatement_equals_reference():
+    """oracle/pre.py == the unmodified identification_tools.py (identification_tools.py:334-424)."""
+    from oracle import pre
+    idt = pinshim.load_reference("identification_tools")
+    robot = _robot("ur10")
+    rng = np.random.default_rng(3)
+    N = 400
+    q = np.cumsum(rng.normal(size=(N, robot.model.nq)), axis=0) * 1e-2
+    param = dict(ts=1e-2, cut_off_frequency_butterworth=10.0, is_joint_torques=True, is_external_wrench=False)
+    f0, f1 = idt.low_pass_filter_data(q, param, 5), pre.low_pass_filter_data(q, param, 5)
+    assert np.array_equal(f0, f1)
+    for dt in (None, 1e-2 * (1 + 0.1 * rng.uniform(size=f0.shape[0] - 1))):
+        r0 = idt.calculate_first_second_order_differentiation(robot.model, f0, param, dt)
+        r1 = pre.calculate_first_second_order_differentiation(robot.model.nq, f0, param, dt)
+        for x0, x1 in zip(r0, r1):
+            assert np.array_equal(x0, x1)
