@@ -203,3 +203,31 @@ def test_preprocessing_filter_and_differentiation_match_reference():
         _, dq_o2, ddq_o2 = calculate_first_second_order_differentiation(M, qf, param, dt)
         assert np.abs(dq_o2 - dq_r2).max() <= 1e-9 * np.abs(dq_r2).max()
         assert np.abs(ddq_o2 - ddq_r2).max() <= 1e-9 * np.abs(ddq_r2).max()
+
+
+def test_get_torque_rand_matches_rnea_oracle():
+    """figaroh.tools.randomdata.get_torque_rand (randomdata.py:93-147): regressor identity on the GPU ==
+    the oracle's RNEA + the reference's friction / inertia / offset / coupled-wrist terms."""
+    from figaroh.tools.randomdata import get_torque_rand
+    from oracle import kernels
+    robot, om = _Robot("tx40"), load_oracle_model("tx40")
+    param = dict(TX40_PARAM)
+    N = 300
+    q, v, a = rand_inputs(load_flat("tx40"), N, 31, ((-3, 3), (-5, 5), (-10, 10)))
+    v[3, 2] = 0.0  # sign(0) = 0
+    tau = get_torque_rand(N, robot, q, v, a, param)
+    nv = 6
+    ref = np.zeros(nv * N)
+    for i in range(N):
+        t = kernels.rnea(om, q[i], v[i], a[i])
+        for j in range(nv):
+            ref[j * N + i] = t[j] + v[i, j] * param["fv"][j] + np.sign(v[i, j]) * param["fs"][j] \
+                + param["Ia"][j] * a[i, j] + param["off"][j]
+            if j == nv - 2:
+                ref[j * N + i] += param["Iam6"] * v[i, nv - 1] + param["fvm6"] * v[i, nv - 1] \
+                    + param["fsm6"] * np.sign(v[i, nv - 2] + v[i, nv - 1])
+            if j == nv - 1:
+                ref[j * N + i] += param["Iam6"] * v[i, nv - 2] + param["fvm6"] * v[i, nv - 2] \
+                    + param["fsm6"] * np.sign(v[i, nv - 2] + v[i, nv - 1])
+    assert tau.shape == ref.shape
+    assert np.abs(tau - ref).max() <= 1e-9 * np.abs(ref).max()
