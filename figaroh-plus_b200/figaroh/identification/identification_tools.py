@@ -83,3 +83,63 @@ def calculate_first_second_order_differentiation(model, q, param, dt=None):
     if on_dev:
         return q_out, dq, ddq
     return q_out.cpu().numpy(), dq.cpu().numpy(), ddq.cpu().numpy()
+
+
+def _factor_of(W_b, tau):
+    """(R1, z = Q1^T tau, |residual|^2, rows) of the least-squares problem [W_b | tau], from ONE TSQR pass."""
+    Wd = _eng.as_device(W_b)
+    r = Wd.shape[1]
+    st = _eng.TsqrState(r).accumulate_dense(Wd, _eng.as_device(np.asarray(tau, dtype=np.float64).reshape(-1))
+                                            if not isinstance(tau, torch.Tensor) else tau.reshape(-1))
+    fused = st.solve(None, (), 0.0)   # no elimination; tol_qr = 0: every column with a non-zero pivot is a base column
+    if fused is None:
+        diag = st.reduce(np.arange(r))
+        base = [i for i in range(r) if diag[i] > 0.0]
+        if len(base) != r:
+            raise np.linalg.LinAlgError("Singular matrix")
+        _, phi, R1, r2 = st.regroup_solve(base, [])
+    else:
+        if len(fused["base"]) != r:
+            raise np.linalg.LinAlgError("Singular matrix")   # what np.linalg.inv(W_b^T W_b) raises in the reference
+        phi, R1, r2 = fused["phi"], fused["R1"], fused["resid2"]
+    return R1, R1 @ phi, r2, Wd.shape[0]
+
+
+def relative_stdev(W_b, phi_b, tau):
+    """Relative standard deviation (%) of the base parameters (reference: identification_tools.py:204-234).
+
+    |tau - W_b phi_b|^2 = |R1 phi_b - Q1^T tau|^2 + |residual|^2 and (W_b^T W_b)^-1 = R1^-1 R1^-T: one TSQR pass
+    over [W_b | tau] on the GPU replaces the tall products of the reference."""
+    phi_b = np.asarray(phi_b, dtype=np.float64)
+    R1, z, r2, rows = _factor_of(W_b, tau)
+    sig_ro_sqr = (float(np.sum((R1 @ phi_b - z) ** 2)) + r2) / (rows - phi_b.shape[0])
+    Rinv = np.linalg.inv(R1)
+    std_x_sqr = sig_ro_sqr * np.sum(Rinv * Rinv, axis=1)   # diag(R1^-1 R1^-T)
+    std_xr = np.zeros(std_x_sqr.shape[0])
+    for i in range(std_x_sqr.shape[0]):
+        std_xr[i] = np.round(100 * np.sqrt(std_x_sqr[i]) / np.abs(phi_b[i]), 2)
+    return std_xr
+
+
+def weigthed_least_squares(robot, phi_b, W_b, tau_meas, tau_est, param):
+    """Weighted least squares (reference: identification_tools.py:291-331; the name keeps the reference's
+    spelling).  sigma_j = |tau_meas_j - tau_est_j| / (n_j - len(phi_b)) per joint block, weights 1 / sigma_j on
+    the nb_samples = idx_tau_stop[0] rows of every block; the solution pinv(P W_b) (P tau_meas) of the LAST pass
+    of the reference's loop is the least-squares solution of the row-scaled system: rows are scaled on the
+    device and folded by one TSQR pass."""
+    tau_meas = np.asarray(tau_meas, dtype=np.float64).reshape(-1)
+    tau_est = np.asarray(tau_est, dtype=np.float64).reshape(-1)
+    nq = robot.model.nq
+    nb_samples = int(param["idx_tau_stop"][0])
+    w = np.zeros(len(tau_meas))
+    start_idx = 0
+    for ii in range(nq):
+        stop = int(param["idx_tau_stop"][ii])
+        diff = tau_meas[start_idx:stop] - tau_est[start_idx:stop]
+        sigma = np.linalg.norm(diff) / (len(diff) - len(phi_b))
+        start_idx = stop
+        w[ii * nb_samples:(ii + 1) * nb_samples] = 1 / sigma
+    Wd = _eng.as_device(W_b)
+    wd = torch.from_numpy(w).to(Wd.device)
+    R1, z, _, _ = _factor_of(Wd * wd[:, None], torch.from_numpy(tau_meas).to(Wd.device) * wd)
+    return np.around(np.linalg.solve(R1, z), 6)

@@ -39,3 +39,33 @@ def low_pass_filter_data(data, param, nbutter=5):
     end_slice = slice(data.shape[0] - nbord, data.shape[0])
     data = np.delete(data, end_slice, axis=0)
     return data
+
+
+def relative_stdev(W_b, phi_b, tau):
+    """identification_tools.py:204-234."""
+    sig_ro_sqr = np.linalg.norm((tau - np.dot(W_b, phi_b))) ** 2 / (W_b.shape[0] - phi_b.shape[0])
+    C_x = sig_ro_sqr * np.linalg.inv(np.dot(W_b.T, W_b))
+    std_x_sqr = np.diag(C_x)
+    std_xr = np.zeros(std_x_sqr.shape[0])
+    for i in range(std_x_sqr.shape[0]):
+        std_xr[i] = np.round(100 * np.sqrt(std_x_sqr[i]) / np.abs(phi_b[i]), 2)
+    return std_xr
+
+
+def weigthed_least_squares(nq, phi_b, W_b, tau_meas, tau_est, param):
+    """identification_tools.py:291-331 (dense P as in the reference: small problems only)."""
+    sigma = np.zeros(nq)
+    P = np.zeros((len(tau_meas), len(tau_meas)))
+    nb_samples = int(param["idx_tau_stop"][0])
+    start_idx = int(0)
+    for ii in range(nq):
+        tau_slice = slice(int(start_idx), int(param["idx_tau_stop"][ii]))
+        diff = (tau_meas[tau_slice] - tau_est[tau_slice])
+        denom = len(tau_meas[tau_slice]) - len(phi_b)
+        sigma[ii] = np.linalg.norm(diff) / denom
+        start_idx = param["idx_tau_stop"][ii]
+        for jj in range(nb_samples):
+            idx = jj + ii * nb_samples
+            P[idx, idx] = 1 / sigma[ii]
+        phi_b = np.matmul(np.linalg.pinv(np.matmul(P, W_b)), np.matmul(P, tau_meas))
+    return np.around(phi_b, 6)

@@ -231,3 +231,28 @@ def test_get_torque_rand_matches_rnea_oracle():
                     + param["fsm6"] * np.sign(v[i, nv - 2] + v[i, nv - 1])
     assert tau.shape == ref.shape
     assert np.abs(tau - ref).max() <= 1e-9 * np.abs(ref).max()
+
+
+def test_statistics_on_the_factor_match_reference():
+    """relative_stdev and weigthed_least_squares (identification_tools.py:204-234, 291-331) from one TSQR pass
+    on the GPU against the numpy restatement of the reference."""
+    from figaroh.identification.identification_tools import relative_stdev, weigthed_least_squares
+    from oracle import pre
+    rng = np.random.default_rng(23)
+    nq, n, r = 3, 400, 7
+    W_b = rng.normal(size=(nq * n, r)) * np.array([1.0, 5.0, 0.3, 2.0, 8.0, 0.7, 1.5])
+    phi_true = rng.normal(size=r) * 3
+    noise = np.repeat([0.05, 0.5, 0.01], n)
+    tau = W_b @ phi_true + noise * rng.normal(size=nq * n)
+    phi_ls = np.round(np.linalg.lstsq(W_b, tau, rcond=None)[0], 6)
+    np.testing.assert_allclose(relative_stdev(W_b, phi_ls, tau), pre.relative_stdev(W_b, phi_ls, tau), atol=0.011)
+    param = dict(idx_tau_stop=[n, 2 * n, 3 * n])
+
+    class R:
+        class model:
+            pass
+    R.model.nq = nq
+    tau_est = W_b @ phi_ls
+    out = weigthed_least_squares(R, phi_ls, W_b, tau, tau_est, param)
+    ref = pre.weigthed_least_squares(nq, phi_ls, W_b, tau, tau_est, param)
+    np.testing.assert_allclose(out, ref, atol=2e-6)

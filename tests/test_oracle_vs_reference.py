@@ -102,3 +102,21 @@ def test_preprocessing_restatement_equals_reference():
         r1 = pre.calculate_first_second_order_differentiation(robot.model.nq, f0, param, dt)
         for x0, x1 in zip(r0, r1):
             assert np.array_equal(x0, x1)
+
+
+def test_statistics_restatement_equals_reference():
+    """oracle/pre.py relative_stdev / weigthed_least_squares == the unmodified identification_tools.py:204-331."""
+    from oracle import pre
+    idt = pinshim.load_reference("identification_tools")
+    rng = np.random.default_rng(1)
+    W = rng.normal(size=(300, 4))
+    phi = rng.normal(size=4)
+    tau = W @ phi + 0.1 * rng.normal(size=300)
+    assert np.array_equal(idt.relative_stdev(W, phi, tau), pre.relative_stdev(W, phi, tau))
+
+    class R:
+        class model:
+            nq = 3
+    p = dict(idx_tau_stop=[100, 200, 300])
+    assert np.array_equal(idt.weigthed_least_squares(R, phi, W, tau, W @ phi, p),
+                          pre.weigthed_least_squares(3, phi, W, tau, W @ phi, p))
