@@ -123,7 +123,10 @@ GqLaunch gq_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, co
     const GqGroup& G = T.gen.grp[g];
     int emits = 0;
     for (int t = 0; t < nproc; ++t) emits += T.gen.emit[g][t] != 0;
-    cost[g] = 700.0 + 400.0 * nproc + 233.0 * emits + 20.0 * G.nsimple + 1070.0 * G.nb + 100.0 * G.nb * (G.nb - 1) / 2;
+#ifndef GQ_COST_JOINT
+#define GQ_COST_JOINT 300.0  // A/B on the GPU: 250-320 are 1 % faster than 400, 500 is 1 % slower
+#endif
+    cost[g] = 700.0 + GQ_COST_JOINT * nproc + 233.0 * emits + 20.0 * G.nsimple + 1070.0 * G.nb + 100.0 * G.nb * (G.nb - 1) / 2;
     csum += cost[g];
   }
   gl.sm_count = std::max(1, sm_count);
