@@ -66,7 +66,9 @@ __device__ __forceinline__ void gq_panel_T(const double (&vc0)[RPL][4], const do
   if (2 * rq + 1 < cq) TS[cq * 8 + 2 * rq + 1] = a1;
   if (lane < 8) TS[lane * 8 + lane] = sc[lane];
   __syncwarp();
-  double t[8];
+  // Column `lane` of T by back substitution (lanes 0..7).  The results go straight into the UPPER part of TS
+  // (T[m][lane], m <= lane) while the strictly lower part still holds the dot products the other lanes read;
+  // consumers mask the lower part to zero when they load T.
   if (lane < 8) {
     double acc[8];
 #pragma unroll
@@ -75,16 +77,11 @@ __device__ __forceinline__ void gq_panel_T(const double (&vc0)[RPL][4], const do
     for (int m = 7; m >= 0; --m) {
       const double taum = TS[m * 8 + m];
       const double tm = (m == lane) ? taum : (m < lane ? -taum * acc[m] : 0.0);
-      t[m] = tm;
+      if (m < lane) TS[m * 8 + lane] = tm;
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         if (i < m) acc[i] = fma(TS[m * 8 + i], tm, acc[i]);
     }
-  }
-  __syncwarp();
-  if (lane < 8) {
-#pragma unroll
-    for (int m = 0; m < 8; ++m) TS[m * 8 + lane] = t[m];
   }
   __syncwarp();
 }
@@ -256,7 +253,7 @@ __device__ __forceinline__ void gq_fold(double* tile, int nb, double* Rg, int k0
         vb1[sl][nn] = Xk[sl * nb * GQ_BLK + o.ob1[nn]];
       }
     gq_panel_T<RPL>(vc0, vc1, sc, TS, lane);
-    const double t0 = TS[(2 * rq) * 8 + cq], t1 = TS[(2 * rq + 1) * 8 + cq];
+    const double t0 = 2 * rq <= cq ? TS[(2 * rq) * 8 + cq] : 0.0, t1 = 2 * rq + 1 <= cq ? TS[(2 * rq + 1) * 8 + cq] : 0.0;
     for (int j = k + 1; j < nb; ++j, Rb += 64) {
       double nr0 = 0.0, nr1 = 0.0;
       if (j + 1 < nb) {  // R blocks of one block row are consecutive: request the next one a block ahead
@@ -356,20 +353,19 @@ static __device__ __forceinline__ void gq_generate(const GqParams& P, const GqGe
   const int nproc = P.nproc;
   double sx[6] = {0, 0, 0, 0, 0, 0};  // motion axis of the row group in the frame of the joint being walked
   double v[6] = {0, 0, 0, 0, 0, 0}, a[6] = {0, 0, 0, 0, 0, 0};
+  // one-joint-ahead input queue (a deeper queue rotated by register moves adds no cover: the move is the first
+  // touch of the load, measured)
   double nq0 = __ldg(qs + S.pj[0].idx_q), nv0 = __ldg(vs + S.pj[0].idx_v), na0 = __ldg(as + S.pj[0].idx_v);
-  double nq1 = 0.0, nv1 = 0.0, na1 = 0.0;
   // rhs entry and the row group's own (dq, ddq): requested / kept now, consumed after the walk
   const double taug = (valid && tau != nullptr) ? __ldg(tau + (int64_t)g * ld_tau + smp) : 0.0;
   double vg = 0.0, ag = 0.0;
   const int vidx_g = S.pj[G.tjoint].idx_v;
-  if (nproc > 1) { nq1 = __ldg(qs + S.pj[1].idx_q); nv1 = __ldg(vs + S.pj[1].idx_v); na1 = __ldg(as + S.pj[1].idx_v); }
   for (int t = 0; t < nproc; ++t) {
     const DevJoint& jt = S.pj[t];
     const double cq0 = nq0, cv0 = nv0, ca0 = na0;
-    nq0 = nq1; nv0 = nv1; na0 = na1;
-    if (t + 2 < nproc) {
-      const DevJoint& jn = S.pj[t + 2];
-      nq1 = __ldg(qs + jn.idx_q); nv1 = __ldg(vs + jn.idx_v); na1 = __ldg(as + jn.idx_v);
+    if (t + 1 < nproc) {
+      const DevJoint& jn = S.pj[t + 1];
+      nq0 = __ldg(qs + jn.idx_q); nv0 = __ldg(vs + jn.idx_v); na0 = __ldg(as + jn.idx_v);
     }
     if (jt.parent == 0) {  // restart from the universe (the host only admits chains hanging off it)
       for (int k = 0; k < 6; ++k) v[k] = 0.0;
