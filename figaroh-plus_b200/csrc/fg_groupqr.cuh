@@ -356,9 +356,8 @@ static __device__ __forceinline__ void gq_generate(const GqParams& P, const GqGe
   // one-joint-ahead input queue (a deeper queue rotated by register moves adds no cover: the move is the first
   // touch of the load, measured)
   double nq0 = __ldg(qs + S.pj[0].idx_q), nv0 = __ldg(vs + S.pj[0].idx_v), na0 = __ldg(as + S.pj[0].idx_v);
-  // rhs entry and the row group's own (dq, ddq): requested / kept now, consumed after the walk
-  const double taug = (valid && tau != nullptr) ? __ldg(tau + (int64_t)g * ld_tau + smp) : 0.0;
-  double vg = 0.0, ag = 0.0;
+  // rhs entry and the row group's own (dq, ddq): requested while the LAST joint is walked, consumed after the walk
+  double taug = 0.0, vg = 0.0, ag = 0.0;
   const int vidx_g = S.pj[G.tjoint].idx_v;
   for (int t = 0; t < nproc; ++t) {
     const DevJoint& jt = S.pj[t];
@@ -419,9 +418,13 @@ static __device__ __forceinline__ void gq_generate(const GqParams& P, const GqGe
     for (int k = 0; k < 6; ++k) { v[k] = vn[k]; a[k] = an[k]; }
     // the row group's motion axis: its own joint's axis at that joint, transported down the chain afterwards
     // (liMi.actInv: the same transform the velocity takes) - the product of these transports is oM_body^-1 oM_joint
+    if (t == nproc - 1) {
+      if (valid && tau != nullptr) taug = __ldg(tau + (int64_t)g * ld_tau + smp);
+      vg = __ldg(vs + vidx_g);
+      ag = __ldg(as + vidx_g);
+    }
     if (t == G.tjoint) {
       for (int k = 0; k < 6; ++k) sx[k] = G.S[k];
-      vg = cv0; ag = ca0;
     } else if (t > G.tjoint) {
       cross3(p, sx + 3, tt);
       for (int k = 0; k < 3; ++k) tt[k] = sx[k] - tt[k];
