@@ -355,8 +355,9 @@ def main():
             "metric": METRIC, "value": total / (ms_step * 1e-3), "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "UR10 6-DoF, friction+actuator inertia+joint offsets, 1M synthetic samples per GPU "
-                                   "(BASELINE.json configs[1])",
+            "config": {"workload": "UR10 6-DoF, friction+actuator inertia+joint offsets, %s synthetic samples per GPU "
+                                   "(BASELINE.json configs[1]%s)" % ("1M" if N == 1_000_000 else str(N),
+                                                                    "" if N == 1_000_000 else "; sample count overridden: configs[4] sweep"),
                        "samples_per_gpu": N, "rows_per_sample": rps, "columns": cols, "columns_folded": int(len(sel)), "parallelism": f"dp{world}",
                        "l2": "inputs (192 B/sample x N = %.0f MB per step) exceed the 126 MB L2" % (N * 192 / 1e6),
                        "eliminated": len(sol.idx_e), "base_parameters": len(sol.idx_base)},
