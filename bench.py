@@ -61,12 +61,6 @@ def ncu_traffic(n):
         return None
 
 
-def std_params_and_names(om):
-    from oracle import ref_path
-    std = ref_path.standard_parameters(om, PARAM)
-    return std
-
-
 def standard_phi(fm):
     """phi_std in FIGAROH column order from the flattened model (no oracle involved)."""
     pin2fig = [9, 6, 7, 8, 0, 1, 3, 2, 4, 5]
