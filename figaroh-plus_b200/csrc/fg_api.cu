@@ -15,6 +15,7 @@
 #include "fg_bq.h"
 #include "fg_tq.h"
 #include "fg_gq.h"
+#include "fg_rq.h"
 #include "fg_prefilter.cuh"
 
 using namespace fg;
@@ -56,7 +57,12 @@ struct DevPlan {
   GqLaunch gql;
   std::unique_ptr<GqParams> gq;
   void* d_gq_tab = nullptr;  // warp -> (row group, instance) tables of the full launch
-  ~DevPlan() { if (d_blob) cudaFree(d_blob); if (d_gq_tab) cudaFree(d_gq_tab); }
+  // fifth-generation kernel (fg_ringqr.cuh)
+  bool rq_tried = false;
+  RqLaunch rql;
+  std::unique_ptr<RqParams> rq;
+  void* d_rq_tab = nullptr;
+  ~DevPlan() { if (d_blob) cudaFree(d_blob); if (d_gq_tab) cudaFree(d_gq_tab); if (d_rq_tab) cudaFree(d_rq_tab); }
 };
 
 struct fg_model {
@@ -79,6 +85,10 @@ struct fg_state {
   int64_t parts_cap = 0;        // in parts
   double* d_gR = nullptr;       // per-warp factors in HBM (only when they do not fit shared memory)
   int64_t gR_cap = 0;           // in doubles
+  double* d_ring = nullptr;     // generation 5: ring of regressor tiles + its control words (L2 resident)
+  int64_t ring_cap = 0;         // in doubles
+  const void* ring_plan = nullptr;  // the plan whose tile layout the ring currently holds (padding columns stay zero)
+  unsigned* h_rq_err = nullptr; // pinned: error flag of the last generation-5 launch
   double* d_A = nullptr;        // (p1 x p1) dense scratch of the small stage
   double* d_Re = nullptr;       // reduced factor (dense, (nk+1)^2)
   double* d_X = nullptr;        // solve output
@@ -101,6 +111,8 @@ struct fg_state {
   long long main_launches = 0;
   bool t_pending = false;
 };
+
+static int check_rq_error(fg_state* s);
 
 static int timing_begin(fg_state* s, cudaStream_t st) {
   if (!s->timing) return FG_OK;
@@ -126,11 +138,10 @@ static const int FIG2PIN[10] = {4, 5, 7, 6, 8, 9, 1, 2, 3, 0};  // figaroh slot 
 extern "C" const char* fg_last_error(void) { return g_err; }
 extern "C" int fg_abi_version(void) { return FG_ABI_VERSION; }
 
-extern "C" int fg_model_create(const fg_model_desc* d, fg_model** out) {
-  if (!d || !out) return set_err(FG_ERR_INVALID, "fg_model_create: null argument");
+// host part of fg_model_create: validate and flatten the description (no device work)
+static int model_from_desc(const fg_model_desc* d, fg_model* m) {
   if (d->njoints < 2 || d->njoints > kMaxJoints)
     return set_err(FG_ERR_UNSUPPORTED, "fg_model_create: njoints=%d outside [2,%d]", d->njoints, kMaxJoints);
-  std::unique_ptr<fg_model> m(new fg_model);
   m->njoints = d->njoints; m->nq = d->nq; m->nv = d->nv;
   m->joints.resize(d->njoints);
   m->mass.assign(d->njoints, 1.0);
@@ -157,6 +168,14 @@ extern "C" int fg_model_create(const fg_model_desc* d, fg_model** out) {
   }
   if (nq != d->nq || nv != d->nv) return set_err(FG_ERR_INVALID, "nq/nv (%d,%d) do not match joints (%d,%d)", d->nq, d->nv, nq, nv);
   if (d->gravity) for (int k = 0; k < 3; ++k) m->gravity[k] = d->gravity[k];
+  return FG_OK;
+}
+
+extern "C" int fg_model_create(const fg_model_desc* d, fg_model** out) {
+  if (!d || !out) return set_err(FG_ERR_INVALID, "fg_model_create: null argument");
+  std::unique_ptr<fg_model> m(new fg_model);
+  int rc0 = model_from_desc(d, m.get());
+  if (rc0) return rc0;
   FG_CUDA(cudaMalloc(&m->d_joints, sizeof(DevJoint) * d->njoints));
   FG_CUDA(cudaMemcpy(m->d_joints, m->joints.data(), sizeof(DevJoint) * d->njoints, cudaMemcpyHostToDevice));
   int dev = 0;
@@ -207,20 +226,11 @@ extern "C" int fg_regressor_shape(const fg_model* m, const fg_regressor_cfg* cfg
   return FG_OK;
 }
 
-// Build (or fetch) the device plan of (model, cfg, column selection).
-static int get_plan(fg_model* m, const fg_regressor_cfg* cfg, const int32_t* col_sel, int n_col_sel, DevPlan** out) {
-  int rc = check_cfg(m, cfg);
-  if (rc) return rc;
-  std::string key = std::to_string(cfg->mode) + ":" + std::to_string(cfg->flags) + ":" + std::to_string(cfg->ft_mask) + ":";
-  for (int i = 0; i < cfg->n_row_sel; ++i) key += std::to_string(cfg->row_sel[i]) + ",";
-  key += ":";
-  for (int i = 0; i < n_col_sel; ++i) key += std::to_string(col_sel[i]) + ",";
-  auto it = m->plans.find(key);
-  if (it != m->plans.end()) { *out = it->second.get(); return FG_OK; }
-
+// Host part of a plan: row groups, column descriptors, first-active columns (no device work).
+static int build_plan_host(const fg_model* m, const fg_regressor_cfg* cfg, const int32_t* col_sel, int n_col_sel,
+                           DevPlan* pl) {
   const int nb = m->njoints - 1;
   const int ncols_full = 14 * nb + ((cfg->flags & FG_FLAG_TX40_COUPLING) ? 3 : 0);
-  std::unique_ptr<DevPlan> pl(new DevPlan);
   // ---- rows
   std::vector<int> vsel;
   if (cfg->mode == FG_MODE_JOINT_TORQUES) {
@@ -323,6 +333,24 @@ static int get_plan(fg_model* m, const fg_regressor_cfg* cfg, const int32_t* col
   P.nj = m->njoints; P.nq = m->nq; P.nv = m->nv; P.ms = (int)pl->rows.size();
   P.ncols = ncols; P.p1 = p1; P.mode = cfg->mode; P.flags = cfg->flags;
   for (int k = 0; k < 3; ++k) P.gravity[k] = m->gravity[k];
+  return FG_OK;
+}
+
+// Build (or fetch) the device plan of (model, cfg, column selection).
+static int get_plan(fg_model* m, const fg_regressor_cfg* cfg, const int32_t* col_sel, int n_col_sel, DevPlan** out) {
+  int rc = check_cfg(m, cfg);
+  if (rc) return rc;
+  std::string key = std::to_string(cfg->mode) + ":" + std::to_string(cfg->flags) + ":" + std::to_string(cfg->ft_mask) + ":";
+  for (int i = 0; i < cfg->n_row_sel; ++i) key += std::to_string(cfg->row_sel[i]) + ",";
+  key += ":";
+  for (int i = 0; i < n_col_sel; ++i) key += std::to_string(col_sel[i]) + ",";
+  auto it = m->plans.find(key);
+  if (it != m->plans.end()) { *out = it->second.get(); return FG_OK; }
+  std::unique_ptr<DevPlan> pl(new DevPlan);
+  rc = build_plan_host(m, cfg, col_sel, n_col_sel, pl.get());
+  if (rc) return rc;
+  const Plan& P = pl->P;
+  const int p1 = P.p1;
   // ---- upload as one blob
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   const size_t o_plan = 0, o_rows = al(sizeof(Plan)), o_cols = o_rows + al(sizeof(RowDesc) * pl->rows.size());
@@ -345,6 +373,82 @@ static int get_plan(fg_model* m, const fg_regressor_cfg* cfg, const int32_t* col
   pl->ptrs.fullcol = (const int*)(db + o_full);
   *out = pl.get();
   m->plans[key] = std::move(pl);
+  return FG_OK;
+}
+
+// Host-only description of how the fused path would run (model, cfg): the producers' walk program, the local
+// problem of every row group and the split of the warps.  Needs no device; used by the CPU tests of the
+// symbolic pass and by DESIGN.md's tables.  JSON into buf.
+extern "C" int fg_plan_describe(const fg_model_desc* d, const fg_regressor_cfg* cfg, int32_t sm_count, int32_t max_smem,
+                                char* buf, int32_t buflen) {
+  if (!d || !cfg || !buf || buflen < 64) return set_err(FG_ERR_INVALID, "fg_plan_describe: bad argument");
+  fg_model m;
+  int rc = model_from_desc(d, &m);
+  if (rc) return rc;
+  rc = check_cfg(&m, cfg);
+  if (rc) return rc;
+  DevPlan pl;
+  rc = build_plan_host(&m, cfg, cfg->col_sel, cfg->n_col_sel, &pl);
+  if (rc) return rc;
+  std::unique_ptr<RqParams> rq(new RqParams);
+  const char* why = "";
+  const RqLaunch rl = rq_build(pl.P, m.joints.data(), pl.rows.data(), pl.cols.data(), sm_count, max_smem, rq.get(), &why);
+  std::string o = "{";
+  char t[256];
+  snprintf(t, sizeof t, "\"ms\": %d, \"ncols\": %d, \"ring_kernel\": %s, \"why\": \"%s\"", pl.P.ms, pl.P.ncols,
+           rl.ok ? "true" : "false", why);
+  o += t;
+  if (rl.ok) {
+    const GqParams& G = rq->gq;
+    snprintf(t, sizeof t, ", \"nw\": %d, \"npc\": %d, \"smem\": %d, \"nproc\": %d, \"ring\": %d, \"slot_doubles\": %d, "
+             "\"nvslots\": %d, \"nmslots\": %d, \"r_doubles\": %lld, \"nbf\": %d", rl.nw, rq->npc, rl.smem, G.nproc,
+             rq->ring, rq->slot_doubles, rq->nvslots, rq->nmslots, (long long)rl.r_doubles, G.nbf);
+    o += t;
+    o += ", \"walk\": [";
+    for (int i = 0; i < G.nproc; ++i) {
+      int joint = -1;
+      for (int b = 1; b < m.njoints; ++b)
+        if (m.joints[b].idx_v == G.gen.pj[i].idx_v && m.joints[b].idx_q == G.gen.pj[i].idx_q) joint = b;
+      snprintf(t, sizeof t, "%s%d", i ? ", " : "", joint);
+      o += t;
+    }
+    o += "], \"ops\": [";
+    for (int i = 0; i < rq->nops; ++i) {
+      const RqOp& op = rq->ops[i];
+      snprintf(t, sizeof t, "%s[%d, %d, %d, %d, %d, %d, %d, %u, %u, %d]", i ? ", " : "", op.kind, op.t, op.vsave, op.msave,
+               op.vload, op.mslot, op.from_universe, op.live, op.own, op.pad);
+      o += t;
+    }
+    o += "], \"groups\": [";
+    for (int g = 0; g < G.ms; ++g) {
+      const GqGroup& H = G.gen.grp[g];
+      snprintf(t, sizeof t, "%s{\"joint\": %d, \"w\": %d, \"nb\": %d, \"ninst\": %d, \"nsimple\": %d, \"cols\": [", g ? ", " : "",
+               H.joint, H.w, H.nb, H.ninst, H.nsimple);
+      o += t;
+      for (int l = 0; l < H.w; ++l) { snprintf(t, sizeof t, "%s%d", l ? ", " : "", (int)G.gcol[g][l]); o += t; }
+      snprintf(t, sizeof t, "], \"rowblock\": %d, \"S\": [%.17g, %.17g, %.17g, %.17g, %.17g, %.17g], \"emit\": [", H.rowblock,
+               H.S[0], H.S[1], H.S[2], H.S[3], H.S[4], H.S[5]);
+      o += t;
+      bool firste = true;
+      for (int i = 0; i < G.nproc; ++i)
+        if (G.gen.emit[g][i]) {
+          snprintf(t, sizeof t, "%s[%d, %d, %d]", firste ? "" : ", ", i, G.gen.emit[g][i] >> 10, G.gen.emit[g][i] & 1023);
+          o += t;
+          firste = false;
+        }
+      o += "], \"simple\": [";
+      for (int i = 0; i < H.nsimple; ++i) {
+        const GqSimple& sp = G.gen.simple[g][i];
+        snprintf(t, sizeof t, "%s[%d, %d, %d, %d]", i ? ", " : "", sp.kind, sp.src, sp.vidx, sp.slot);
+        o += t;
+      }
+      o += "]}";
+    }
+    o += "]";
+  }
+  o += "}";
+  if ((int)o.size() + 1 > buflen) return set_err(FG_ERR_INVALID, "fg_plan_describe: buffer too small (%d needed)", (int)o.size() + 1);
+  memcpy(buf, o.c_str(), o.size() + 1);
   return FG_OK;
 }
 
@@ -412,7 +516,8 @@ extern "C" int fg_state_create(int32_t p, fg_state** out) {
 extern "C" void fg_state_destroy(fg_state* s) {
   if (!s) return;
   cudaFree(s->d_part); cudaFree(s->d_parts); cudaFree(s->d_gR); cudaFree(s->d_A); cudaFree(s->d_Re);
-  cudaFree(s->d_X); cudaFree(s->d_idx); cudaFree(s->d_stage); cudaFree(s->d_solve);
+  cudaFree(s->d_X); cudaFree(s->d_idx); cudaFree(s->d_stage); cudaFree(s->d_solve); cudaFree(s->d_ring);
+  if (s->h_rq_err) cudaFreeHost(s->h_rq_err);
   if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
   for (auto& e : s->ev) if (e) cudaEventDestroy(e);
   if (s->t0) cudaEventDestroy(s->t0);
@@ -754,6 +859,81 @@ static int launch_gq(fg_state* s, fg_model* m, DevPlan* pl, const double* q, con
   return merge_parts_into_state(s, 1, m->max_smem, st);
 }
 
+// fifth-generation fused kernel (fg_ringqr.cuh): producer warps write every row group's tile into an L2-resident
+// ring, consumer warps (one TSQR stream per (warp, row group)) pull their blocks with bulk copies.  Factors and
+// merge exactly as generation 4.
+static int check_rq_error(fg_state* s) {
+  if (s->h_rq_err && *s->h_rq_err != 0u) {
+    const unsigned code = *s->h_rq_err;
+    *s->h_rq_err = 0u;
+    if (s->d_ring) cudaMemset(s->d_ring, 0, sizeof(double) * s->ring_cap);  // also clears the device flag
+    return set_err(FG_ERR_CUDA, "fused kernel: ring hand-over timed out (code %u: 1 consumer, 2 producer, 3 mbarrier)", code);
+  }
+  return FG_OK;
+}
+
+static int launch_rq(fg_state* s, fg_model* m, DevPlan* pl, const double* q, const double* v, const double* a,
+                     const double* tau, int64_t ld_tau, int64_t N, int phase, cudaStream_t st) {
+  RqLaunch& rl = pl->rql;
+  const RqParams& prm = *pl->rq;
+  if (!pl->d_rq_tab) {
+    const size_t nb_i = rl.tab_i.size() * sizeof(unsigned short), nb_g = (rl.tab_g.size() + 15) / 16 * 16;
+    FG_CUDA(cudaMalloc(&pl->d_rq_tab, nb_g + nb_i));
+    FG_CUDA(cudaMemcpy(pl->d_rq_tab, rl.tab_g.data(), rl.tab_g.size(), cudaMemcpyHostToDevice));
+    FG_CUDA(cudaMemcpy(static_cast<char*>(pl->d_rq_tab) + nb_g, rl.tab_i.data(), nb_i, cudaMemcpyHostToDevice));
+    rl.d_tab_g = static_cast<const unsigned char*>(pl->d_rq_tab);
+    rl.d_tab_i = reinterpret_cast<const unsigned short*>(static_cast<char*>(pl->d_rq_tab) + nb_g);
+  }
+  const bool whole = phase == (TQ_PHASE_FIRST | TQ_PHASE_LAST);
+  const int64_t cnt_doubles = ((int64_t)GQ_MAXG * prm.gq.maxinst + 3) / 2 + 1;
+  const int64_t need = rl.r_doubles + rl.rfull_doubles + cnt_doubles;
+  int rc;
+  if (phase & TQ_PHASE_FIRST) {
+    rc = ensure_gR(s, need);
+    if (rc) return rc;
+  } else if (s->gR_cap < need) {
+    return set_err(FG_ERR_INVALID, "internal: continued launch without a first one");
+  }
+  const int64_t ctl_doubles = (2 * (int64_t)prm.ring + 4 + 1) / 2;
+  const int64_t ring_need = rl.ring_doubles + ctl_doubles;
+  if (ring_need > s->ring_cap) {
+    if (s->d_ring) cudaFree(s->d_ring);
+    s->d_ring = nullptr; s->ring_cap = 0; s->ring_plan = nullptr;
+    FG_CUDA(cudaMalloc(&s->d_ring, sizeof(double) * ring_need));
+    s->ring_cap = ring_need;
+  }
+  if (s->ring_plan != (const void*)pl) {  // the padding columns of a slot are never written: they must read as zero
+    FG_CUDA(cudaMemsetAsync(s->d_ring, 0, sizeof(double) * s->ring_cap, st));
+    s->ring_plan = (const void*)pl;
+  }
+  if (!s->h_rq_err) {
+    FG_CUDA(cudaMallocHost(&s->h_rq_err, sizeof(unsigned)));
+    *s->h_rq_err = 0u;
+  }
+  rc = ensure_parts(s, 2);
+  if (rc) return rc;
+  unsigned* ctl = reinterpret_cast<unsigned*>(s->d_ring + rl.ring_doubles);
+  rc = timing_begin(s, st);
+  if (rc) return rc;
+  cudaError_t e = rq_launch(rl, prm, q, v, a, tau, ld_tau, N, s->d_gR, s->d_ring, ctl, (phase & TQ_PHASE_FIRST) ? 1 : 0, st);
+  rc = timing_end(s, st);
+  if (rc) return rc;
+  if (e != cudaSuccess) return set_err(FG_ERR_CUDA, "rq_launch failed: %s", cudaGetErrorString(e));
+  FG_LAUNCHED();
+  s->rows += N * pl->P.ms;
+  // the flag of every launch is OR-ed into the pinned word by the copy of the last one; a timeout aborts all warps
+  FG_CUDA(cudaMemcpyAsync(s->h_rq_err, ctl + 2 * (size_t)prm.ring, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+  if (!(phase & TQ_PHASE_LAST)) return FG_OK;
+  double* rfull = s->d_gR + rl.r_doubles;
+  unsigned* counters = reinterpret_cast<unsigned*>(rfull + rl.rfull_doubles);
+  GqLaunch gl;
+  gl.smem_merge = rl.smem_merge;
+  e = gq_merge(gl, prm.gq, s->d_gR, whole ? (N + GQ_S - 1) / GQ_S : 0, counters, rfull, s->d_parts, st);
+  if (e != cudaSuccess) return set_err(FG_ERR_CUDA, "gq_merge failed: %s", cudaGetErrorString(e));
+  FG_LAUNCHED();
+  return merge_parts_into_state(s, 1, m->max_smem, st);
+}
+
 static int accumulate_samples_dev(fg_state* s, fg_model* m, const fg_regressor_cfg* cfg, const double* q,
                                   const double* v, const double* a, const double* tau, int64_t ld_tau, int64_t N,
                                   cudaStream_t st, int phase = TQ_PHASE_FIRST | TQ_PHASE_LAST, bool* chunkable = nullptr) {
@@ -765,6 +945,22 @@ static int accumulate_samples_dev(fg_state* s, fg_model* m, const fg_regressor_c
   if (N <= 0) return FG_OK;
   if (tau && ld_tau < N) return set_err(FG_ERR_INVALID, "ld_tau=%lld smaller than N=%lld", (long long)ld_tau, (long long)N);
   const int ms = pl->P.ms, nslot = (pl->P.p1 + 31) / 32;
+  {
+    const char* e = getenv("FG_USE_RQ");
+    const bool use_rq = !(e && e[0] == '0');
+    if (use_rq && !pl->rq_tried) {
+      pl->rq_tried = true;
+      pl->rq.reset(new RqParams);
+      const char* why = "";
+      pl->rql = rq_build(pl->P, m->joints.data(), pl->rows.data(), pl->cols.data(), m->sm_count, m->max_smem,
+                         pl->rq.get(), &why);
+      if (!pl->rql.ok) pl->rq.reset();
+    }
+    if (use_rq && pl->rql.ok && s->perm.empty()) {
+      if (chunkable) *chunkable = true;
+      return launch_rq(s, m, pl, q, v, a, tau, ld_tau, N, phase, st);
+    }
+  }
   {
     const char* e = getenv("FG_USE_GQ");
     const bool use_gq = !(e && e[0] == '0');
@@ -1021,6 +1217,7 @@ extern "C" int fg_state_colsq(fg_state* s, double* out, void* stream) {
   std::vector<double> tmp(s->p1);
   FG_CUDA(cudaMemcpyAsync(tmp.data(), s->d_part + ntri, sizeof(double) * s->p1, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   FG_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  if (int rc = check_rq_error(s)) return rc;
   const std::vector<int> inv = inverse_perm(s);
   for (int i = 0; i < s->p; ++i) out[i] = tmp[inv[i]];
   out[s->p] = tmp[s->p];
@@ -1066,6 +1263,7 @@ extern "C" int fg_state_reduce(fg_state* s, const int32_t* keep, int32_t nk, dou
   std::vector<double> Rh((size_t)n * n);
   FG_CUDA(cudaMemcpyAsync(Rh.data(), s->d_Re, sizeof(double) * n * n, cudaMemcpyDeviceToHost, st));
   FG_CUDA(cudaStreamSynchronize(st));
+  if (int rc2 = check_rq_error(s)) return rc2;
   for (int j = 0; j < n; ++j) diag[j] = std::abs(Rh[(size_t)j * n + j]);
   s->nk = nk;
   s->keep.assign(keep, keep + nk);
@@ -1104,6 +1302,7 @@ extern "C" int fg_state_pivot_qr(fg_state* s, const int32_t* keep, int32_t nk, i
   FG_CUDA(cudaMemcpyAsync(R_host, s->d_A, sizeof(double) * n * n, cudaMemcpyDeviceToHost, st));
   FG_CUDA(cudaMemcpyAsync(perm.data(), s->d_idx + n, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
   FG_CUDA(cudaStreamSynchronize(st));
+  if (int rc2 = check_rq_error(s)) return rc2;
   for (int j = 0; j < nk; ++j) perm_host[j] = perm[j];
   return FG_OK;
 }
@@ -1140,6 +1339,7 @@ extern "C" int fg_state_solve(fg_state* s, double tol_e, const int32_t* drop, in
   std::vector<double> h(blob);
   FG_CUDA(cudaMemcpyAsync(h.data(), s->d_solve, sizeof(double) * blob, cudaMemcpyDeviceToHost, st));
   FG_CUDA(cudaStreamSynchronize(st));
+  if (int rc2 = check_rq_error(s)) return rc2;
   const int nk = (int)h[0], r = (int)h[1], n = nk + 1, ng = nk - r, nrhs = ng + 1;
   const double* h_colsq = h.data() + 4;
   const double* h_diag = h_colsq + p1;

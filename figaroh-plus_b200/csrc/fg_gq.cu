@@ -20,7 +20,7 @@ GqLaunch gq_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, co
   const int ms = P.ms, nj = P.nj, ncols = P.ncols;
   if (ms < 1 || ms > GQ_MAXG) { gq_fail(why, "more than 8 row groups"); return gl; }
   if (nj > GQ_MAXJ) { gq_fail(why, "more than 32 joints"); return gl; }
-  if (ncols + 1 > GQ_MAXW) { gq_fail(why, "too many columns"); return gl; }
+  if (ncols + 1 > 8 * GQ_MAXBF) { gq_fail(why, "too many columns"); return gl; }
   GqParams& T = *out;
   memset(&T, 0, sizeof T);
   T.nj = nj; T.nq = P.nq; T.nv = P.nv; T.ms = ms; T.p1 = ncols + 1;
@@ -110,7 +110,7 @@ GqLaunch gq_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, co
     G.r_size = G.nb * (G.nb + 1) / 2 * 64;
     maxnb = std::max(maxnb, G.nb);
   }
-  if (maxnb > GQ_MAXB || T.nbf > GQ_MAXB) { gq_fail(why, "more than 12 column blocks"); return gl; }
+  if (maxnb > GQ_MAXB || T.nbf > GQ_MAXBF) { gq_fail(why, "too many column blocks"); return gl; }
   T.maxnb = maxnb;
   gl.smem_merge = (2 * std::max(maxnb, T.nbf) * GQ_BLK + GQ_SCRATCH) * 8;  // 64-row slabs
   if (gl.smem_merge > max_smem) { gq_fail(why, "tile does not fit shared memory"); return gl; }

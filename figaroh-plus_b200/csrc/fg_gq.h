@@ -20,12 +20,13 @@ namespace fg {
 constexpr int GQ_S = 32;         // samples (= rows) of one tile: one row per lane
 constexpr int GQ_MAXJ = 32;      // joints incl. universe
 constexpr int GQ_MAXG = 8;       // row groups per sample
-constexpr int GQ_MAXB = 12;      // 8-column blocks of one row group's local problem (and of the full factor)
+constexpr int GQ_MAXB = 16;      // 8-column blocks of one row group's local problem
+constexpr int GQ_MAXBF = 24;     // 8-column blocks of the full factor (state columns incl. the rhs <= 192)
 constexpr int GQ_MAXW = 8 * GQ_MAXB;
 constexpr int GQ_MAXSIMPLE = 16; // input-fed columns (friction / inertia / offset / coupling / rhs) per row group
 constexpr int GQ_BLK = 8 * GQ_S; // doubles of one tile block (8 columns x 32 rows)
 constexpr int GQ_SCRATCH = 64 + 16;  // T / diagonal block (shared), taus + reduction results
-constexpr int GQ_MAXPROC = 12;   // joints walked by the forward pass
+constexpr int GQ_MAXPROC = 16;   // joints walked by the forward pass
 constexpr int GQ_MAXNW = 16;     // warps (independent streams) of one CTA; one CTA per SM
 
 struct GqSimple {

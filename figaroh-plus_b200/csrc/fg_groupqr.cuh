@@ -198,9 +198,14 @@ __device__ __forceinline__ void gq_panel_factor(double (&x)[RPL][8], const doubl
 // Fold a tile of RPL slabs of 32 rows (slab s, block j at tile + (s nb + j) GQ_BLK; nb blocks of 8 columns,
 // shared memory, blocks < k0 all zero) into the block-upper-triangular factor Rg (nb (nb + 1) / 2 blocks of
 // 8 x 8, row-major, global memory).
-template <bool CG, int RPL>
-__device__ __forceinline__ void gq_fold(double* tile, int nb, double* Rg, int k0, double* scr, const GqOffs& o,
-                                        int lane) {
+// hook(k) is called by every lane once block k of the tile is dead (its panel is factored and applied to all the
+// blocks to its right): generation 5 refills that block with the next tile's data while the fold goes on.
+struct GqNoHook {
+  __device__ __forceinline__ void operator()(int) const {}
+};
+template <bool CG, int RPL, class Hook>
+__device__ __forceinline__ void gq_fold_h(double* tile, int nb, double* Rg, int k0, double* scr, const GqOffs& o,
+                                          int lane, Hook& hook) {
   const int cq = lane >> 2, rq = lane & 3;
   double* TS = scr;   // T of the panel: written after the diagonal block has gone back to global memory
   double* Rin = scr;  // diagonal block, updated in place
@@ -230,7 +235,11 @@ __device__ __forceinline__ void gq_fold(double* tile, int nb, double* Rg, int k0
     gq_panel_factor<RPL>(x, Rin, Rout, sc, Xk, lane);
     if ((lane >> 3) <= (lane & 7)) Rd[lane] = Rout[lane];            // rows 0..3 of the upper triangle
     if ((lane >> 3) + 4 <= (lane & 7)) Rd[lane + 32] = Rout[lane + 32];  // rows 4..7
-    if (k + 1 == nb) break;
+    if (k + 1 == nb) {
+      __syncwarp();
+      hook(k);
+      break;
+    }
     {  // the next diagonal block is only touched by the next panel: request it now
       const double* Rn = Rg + (size_t)tq_rblk(nb, k + 1, k + 1) * 64;
       d0 = gq_ld<CG>(Rn + lane);
@@ -301,8 +310,16 @@ __device__ __forceinline__ void gq_fold(double* tile, int nb, double* Rg, int k0
       r1 = nr1;
     }
     __syncwarp();
+    hook(k);
   }
   __syncwarp();
+}
+
+template <bool CG, int RPL>
+__device__ __forceinline__ void gq_fold(double* tile, int nb, double* Rg, int k0, double* scr, const GqOffs& o,
+                                        int lane) {
+  GqNoHook nh;
+  gq_fold_h<CG, RPL, GqNoHook>(tile, nb, Rg, k0, scr, o, lane, nh);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -464,6 +481,7 @@ static __device__ __forceinline__ void gq_generate(const GqParams& P, const GqGe
   }
 }
 
+#ifndef FG_GQ_DEVICE_ONLY  // fg_rq.cu reuses the device functions above, not the generation-4 kernels
 // ---------------------------------------------------------------------------------------------
 // One CTA per SM, blockDim.x / 32 independent warps; the only CTA-wide synchronisation is the one after the
 // generator tables have been copied to shared memory.  Warp gw = blockIdx.x * nw + warp works on row group
@@ -545,16 +563,18 @@ __device__ __forceinline__ void gq_merge_into(const GqParams& P, double* tile, i
       const int mm = m & 3;
       // the blocks of one block row are consecutive: request all of them before the first one is stored
       const double* B = Rsrc + (size_t)tq_rblk(nb, rb, rb) * 64;
-      double v0[GQ_MAXB], v1[GQ_MAXB];
+      for (int j0 = 0; rb + j0 < nb; j0 += 8) {
+        double v0[8], v1[8];
 #pragma unroll
-      for (int jj = 0; jj < GQ_MAXB; ++jj)
-        if (rb + jj < nb) { v0[jj] = __ldcg(B + jj * 64 + lane); v1[jj] = __ldcg(B + jj * 64 + 32 + lane); }
+        for (int jj = 0; jj < 8; ++jj)
+          if (rb + j0 + jj < nb) { v0[jj] = __ldcg(B + (j0 + jj) * 64 + lane); v1[jj] = __ldcg(B + (j0 + jj) * 64 + 32 + lane); }
 #pragma unroll
-      for (int jj = 0; jj < GQ_MAXB; ++jj)
-        if (rb + jj < nb) {
-          slab[(rb + jj) * GQ_BLK + tq_idx(lane & 7, 8 * mm + (lane >> 3))] = v0[jj];
-          slab[(rb + jj) * GQ_BLK + tq_idx(lane & 7, 8 * mm + 4 + (lane >> 3))] = v1[jj];
-        }
+        for (int jj = 0; jj < 8; ++jj)
+          if (rb + j0 + jj < nb) {
+            slab[(rb + j0 + jj) * GQ_BLK + tq_idx(lane & 7, 8 * mm + (lane >> 3))] = v0[jj];
+            slab[(rb + j0 + jj) * GQ_BLK + tq_idx(lane & 7, 8 * mm + 4 + (lane >> 3))] = v1[jj];
+          }
+      }
     }
     __syncwarp();
     gq_fold<true, 2>(tile, nb, Rdst, t0, scr, o, lane);
@@ -647,18 +667,20 @@ gq_merge_kernel(const __grid_constant__ GqParams P, const __grid_constant__ GqMe
         double* slab = tile + (size_t)(m >> 2) * nbf * GQ_BLK;
         const int mm = m & 3;
         const double* B = Rsrc + (size_t)tq_rblk(H.nb, rb, rb) * 64;
-        double v0[GQ_MAXB], v1[GQ_MAXB];
+        for (int j0 = 0; rb + j0 < H.nb; j0 += 8) {
+          double v0[8], v1[8];
 #pragma unroll
-        for (int jj = 0; jj < GQ_MAXB; ++jj)
-          if (rb + jj < H.nb) { v0[jj] = __ldcg(B + jj * 64 + lane); v1[jj] = __ldcg(B + jj * 64 + 32 + lane); }
+          for (int jj = 0; jj < 8; ++jj)
+            if (rb + j0 + jj < H.nb) { v0[jj] = __ldcg(B + (j0 + jj) * 64 + lane); v1[jj] = __ldcg(B + (j0 + jj) * 64 + 32 + lane); }
 #pragma unroll
-        for (int jj = 0; jj < GQ_MAXB; ++jj) {
-          const int l = 8 * (rb + jj) + (lane & 7);
-          if (rb + jj < H.nb && l < H.w) {
-            const int scol = P.gcol[gg][l];
-            slab[(scol >> 3) * GQ_BLK + tq_idx(scol & 7, 8 * mm + (lane >> 3))] = v0[jj];
-            slab[(scol >> 3) * GQ_BLK + tq_idx(scol & 7, 8 * mm + 4 + (lane >> 3))] = v1[jj];
-            kmin = min(kmin, scol >> 3);
+          for (int jj = 0; jj < 8; ++jj) {
+            const int l = 8 * (rb + j0 + jj) + (lane & 7);
+            if (rb + j0 + jj < H.nb && l < H.w) {
+              const int scol = P.gcol[gg][l];
+              slab[(scol >> 3) * GQ_BLK + tq_idx(scol & 7, 8 * mm + (lane >> 3))] = v0[jj];
+              slab[(scol >> 3) * GQ_BLK + tq_idx(scol & 7, 8 * mm + 4 + (lane >> 3))] = v1[jj];
+              kmin = min(kmin, scol >> 3);
+            }
           }
         }
       }
@@ -688,5 +710,6 @@ gq_merge_kernel(const __grid_constant__ GqParams P, const __grid_constant__ GqMe
     part_out[ntri + c] = sacc;
   }
 }
+#endif  // FG_GQ_DEVICE_ONLY
 
 }  // namespace fg

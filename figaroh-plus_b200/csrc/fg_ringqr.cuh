@@ -1,0 +1,469 @@
+// fg_ringqr.cuh - kernel (1)+(2), fifth generation: regressor producers and TSQR consumers in one persistent
+// kernel, connected by an L2-resident ring of regressor tiles (design: fg_rq.h).
+//
+//   producer warp : one sample per lane; depth-first walk of the kinematic tree (descend / ascend program
+//                   built by the host), motion axes of all live row groups kept in shared memory and
+//                   transported frame to frame, entries s_g^T B_b of pinocchio::computeJointTorqueRegressor
+//                   (reference call sites regressor.py:49,93) written for EVERY row group into the ring slot of
+//                   the tile, in the consumers' tile layout (a warp store = one 256-byte row of a column).
+//   consumer warp : one row group for the whole launch (as in generation 4); pulls its blocks of the tile
+//                   from the ring with cp.async.bulk (completion on a per-warp mbarrier) and folds them into
+//                   its private block-triangular factor (gq_fold_h).  Block k of the NEXT tile is requested as
+//                   soon as panel k of the current one has retired.
+#pragma once
+#define FG_GQ_DEVICE_ONLY
+#include "fg_groupqr.cuh"
+#include "fg_rq.h"
+
+namespace fg {
+
+constexpr unsigned RQ_SPIN_LIMIT = 1u << 22;  // bounded waits: ~1 s, then the error flag is raised
+constexpr int RQ_ERR_CONSUMER = 1, RQ_ERR_PRODUCER = 2, RQ_ERR_MBAR = 3;
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers: mbarrier, bulk copy (TMA engine, SASS UBLKCP), acquire / release flags
+__device__ __forceinline__ uint32_t rq_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void rq_mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rq_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void rq_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rq_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool rq_mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      " .reg .pred p;\n"
+      " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      " selp.u32 %0, 1, 0, p;\n"
+      "}"
+      : "=r"(ok)
+      : "r"(rq_smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void rq_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   rq_smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(rq_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void rq_fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ unsigned rq_ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void rq_st_release(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// lane 0 waits until *flag >= want (monotonic counters); false = gave up (error flag raised by the caller)
+__device__ __forceinline__ bool rq_spin_ge(const unsigned* flag, unsigned want, const unsigned* err) {
+  for (unsigned it = 0; it < RQ_SPIN_LIMIT; ++it) {
+    if (rq_ld_acquire(flag) >= want) return true;
+    if ((it & 255u) == 255u && rq_ld_acquire(err) != 0u) return false;
+    __nanosleep(it < 32 ? 20 : 200);
+  }
+  return false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// spatial transforms with M = (R, p) the child-in-parent placement
+//   actInv (into the child frame):  ang' = R^T ang,  lin' = R^T (lin - p x ang)
+//   act    (back to the parent):    ang' = R ang,    lin' = R lin + p x (R ang)
+__device__ __forceinline__ void rq_actinv(const double* R, const double* p, const double* lin, const double* ang,
+                                          double* lo, double* ao) {
+  double t[3];
+  cross3(p, ang, t);
+  for (int k = 0; k < 3; ++k) t[k] = lin[k] - t[k];
+  for (int k = 0; k < 3; ++k) {
+    lo[k] = R[k] * t[0] + R[3 + k] * t[1] + R[6 + k] * t[2];
+    ao[k] = R[k] * ang[0] + R[3 + k] * ang[1] + R[6 + k] * ang[2];
+  }
+}
+__device__ __forceinline__ void rq_act(const double* R, const double* p, const double* lin, const double* ang,
+                                       double* lo, double* ao) {
+  double ra[3], rl[3], x[3];
+  for (int k = 0; k < 3; ++k) {
+    ra[k] = R[3 * k] * ang[0] + R[3 * k + 1] * ang[1] + R[3 * k + 2] * ang[2];
+    rl[k] = R[3 * k] * lin[0] + R[3 * k + 1] * lin[1] + R[3 * k + 2] * lin[2];
+  }
+  cross3(p, ra, x);
+  for (int k = 0; k < 3; ++k) { ao[k] = ra[k]; lo[k] = rl[k] + x[k]; }
+}
+
+// entries of (row group, body) into the ring slot (same arithmetic as gq_emit; padding samples store zeros)
+__device__ __forceinline__ void rq_emit(double* gslot, int ed, const double* sl, const double* sa, const double* om,
+                                        const double* al, const double* ap, bool valid, int lane) {
+  double val[10];
+  val[0] = sl[0] * ap[0] + sl[1] * ap[1] + sl[2] * ap[2];
+  const double ww = om[0] * om[0] + om[1] * om[1] + om[2] * om[2];
+  const double so = sl[0] * om[0] + sl[1] * om[1] + sl[2] * om[2];
+  double x1[3], x2[3], h[3];
+  cross3(sl, al, x1);
+  cross3(ap, sa, x2);
+  for (int j = 0; j < 3; ++j) val[1 + j] = x1[j] + so * om[j] - ww * sl[j] + x2[j];
+  cross3(sa, om, h);
+  val[4] = sa[0] * al[0] + h[0] * om[0];                                   // Ixx
+  val[5] = sa[0] * al[1] + sa[1] * al[0] + h[0] * om[1] + h[1] * om[0];   // Ixy
+  val[6] = sa[1] * al[1] + h[1] * om[1];                                   // Iyy
+  val[7] = sa[0] * al[2] + sa[2] * al[0] + h[0] * om[2] + h[2] * om[0];   // Ixz
+  val[8] = sa[1] * al[2] + sa[2] * al[1] + h[1] * om[2] + h[2] * om[1];   // Iyz
+  val[9] = sa[2] * al[2] + h[2] * om[2];                                   // Izz
+  int slot = ed >> 10;
+#pragma unroll
+  for (int k = 0; k < 10; ++k) {
+    if ((ed >> k) & 1) {  // uniform
+      gslot[(slot >> 3) * GQ_BLK + tq_idx(slot & 7, lane)] = valid ? val[k] : 0.0;
+      ++slot;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One tile (32 samples, one per lane) of EVERY row group into a ring slot.
+// ps: this producer warp's shared memory: axes [ms][6][32], saved (v, a) [nvslots][12][32], saved joint
+// transforms [nmslots][12][32].
+static __device__ __forceinline__ void rq_produce_tile(const RqParams& P, const GqGen& S, const RqOp* ops, double* ps,
+                                                       double* slot, const double* __restrict__ q,
+                                                       const double* __restrict__ qd, const double* __restrict__ qdd,
+                                                       const double* __restrict__ tau, int64_t ld_tau, int64_t s0,
+                                                       int64_t N, int lane) {
+  const int ms = P.gq.ms;
+  const int64_t smp = s0 + lane;
+  const bool valid = smp < N;
+  const int64_t sc = valid ? smp : N - 1;
+  const double* qs = q + sc * P.gq.nq;
+  const double* vs = qd + sc * P.gq.nv;
+  const double* as = qdd + sc * P.gq.nv;
+  double* AX = ps + lane;                         // AX[(g * 6 + k) * 32]
+  double* VS = ps + ms * 6 * 32 + lane;           // VS[(slot * 12 + k) * 32]
+  double* MS = VS + P.nvslots * 12 * 32;          // MS[(slot * 12 + k) * 32]
+  double v[6] = {0, 0, 0, 0, 0, 0}, a[6] = {0, 0, 0, 0, 0, 0};
+  double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0};
+  // inputs of the first joint; afterwards requested one descend ahead
+  double nq0 = 0.0, nv0 = 0.0, na0 = 0.0;
+  {
+    const DevJoint& j0 = S.pj[ops[0].t];
+    nq0 = __ldg(qs + j0.idx_q); nv0 = __ldg(vs + j0.idx_v); na0 = __ldg(as + j0.idx_v);
+  }
+  const int nops = P.nops;
+  for (int o = 0; o < nops; ++o) {
+    const RqOp op = ops[o];
+    if (op.kind == 0) {
+      const DevJoint& jt = S.pj[op.t];
+      if (op.vsave != 255) {
+        for (int k = 0; k < 6; ++k) { VS[(op.vsave * 12 + k) * 32] = v[k]; VS[(op.vsave * 12 + 6 + k) * 32] = a[k]; }
+      }
+      if (op.from_universe) {
+        for (int k = 0; k < 6; ++k) v[k] = 0.0;
+        a[0] = -P.gq.gravity[0]; a[1] = -P.gq.gravity[1]; a[2] = -P.gq.gravity[2];
+        a[3] = a[4] = a[5] = 0.0;
+      }
+      const double cq0 = nq0, cv0 = nv0, ca0 = na0;
+      if (op.pad != 255) {  // the next descend's joint
+        const DevJoint& jn = S.pj[op.pad];
+        nq0 = __ldg(qs + jn.idx_q); nv0 = __ldg(vs + jn.idx_v); na0 = __ldg(as + jn.idx_v);
+      }
+      double Rj[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, pj[3] = {0, 0, 0};
+      double vj[6] = {0, 0, 0, 0, 0, 0}, aj[6] = {0, 0, 0, 0, 0, 0};
+      const int iq = jt.idx_q, iv = jt.idx_v;
+      const double ax[3] = {jt.axis[0], jt.axis[1], jt.axis[2]};
+      if (jt.jtype == 1) {
+        double s, c;
+        sincos(cq0, &s, &c);
+        axis_rot(ax, c, s, Rj);
+        for (int k = 0; k < 3; ++k) { vj[3 + k] = ax[k] * cv0; aj[3 + k] = ax[k] * ca0; }
+      } else if (jt.jtype == 2) {
+        axis_rot(ax, cq0, __ldg(qs + iq + 1), Rj);
+        for (int k = 0; k < 3; ++k) { vj[3 + k] = ax[k] * cv0; aj[3 + k] = ax[k] * ca0; }
+      } else if (jt.jtype == 3) {
+        for (int k = 0; k < 3; ++k) { pj[k] = ax[k] * cq0; vj[k] = ax[k] * cv0; aj[k] = ax[k] * ca0; }
+      } else {  // free-flyer
+        quat_rot(__ldg(qs + iq + 3), __ldg(qs + iq + 4), __ldg(qs + iq + 5), __ldg(qs + iq + 6), Rj);
+        for (int k = 0; k < 3; ++k) pj[k] = __ldg(qs + iq + k);
+        for (int k = 0; k < 6; ++k) { vj[k] = __ldg(vs + iv + k); aj[k] = __ldg(as + iv + k); }
+      }
+      // liMi = placement * Mj
+      for (int r = 0; r < 3; ++r) {
+        const double m0 = jt.plcR[3 * r], m1 = jt.plcR[3 * r + 1], m2 = jt.plcR[3 * r + 2];
+        for (int c = 0; c < 3; ++c) R[3 * r + c] = m0 * Rj[c] + m1 * Rj[3 + c] + m2 * Rj[6 + c];
+        p[r] = m0 * pj[0] + m1 * pj[1] + m2 * pj[2] + jt.plcp[r];
+      }
+      if (op.msave != 255) {
+        for (int k = 0; k < 9; ++k) MS[(op.msave * 12 + k) * 32] = R[k];
+        for (int k = 0; k < 3; ++k) MS[(op.msave * 12 + 9 + k) * 32] = p[k];
+      }
+      // v = vJ + liMi.actInv(v_parent);  a = v x vJ + S qdd + liMi.actInv(a_parent)
+      double vn[6], an[6], tl[3], ta[3];
+      rq_actinv(R, p, v, v + 3, tl, ta);
+      for (int k = 0; k < 3; ++k) { vn[k] = vj[k] + tl[k]; vn[3 + k] = vj[3 + k] + ta[k]; }
+      double l1[3], l2[3], l3[3];
+      cross3(vn + 3, vj, l1);
+      cross3(vn, vj + 3, l2);
+      cross3(vn + 3, vj + 3, l3);
+      rq_actinv(R, p, a, a + 3, tl, ta);
+      for (int k = 0; k < 3; ++k) {
+        an[k] = l1[k] + l2[k] + aj[k] + tl[k];
+        an[3 + k] = l3[k] + aj[3 + k] + ta[k];
+      }
+      for (int k = 0; k < 6; ++k) { v[k] = vn[k]; a[k] = an[k]; }
+      double ap[3];
+      cross3(v + 3, v, ap);  // classical acceleration a' = a_lin + w x v_lin
+      for (int k = 0; k < 3; ++k) ap[k] += a[k];
+      // row groups whose axis is live: transport into this frame and emit; then the groups that start here
+      for (unsigned m = op.live; m; m &= m - 1) {
+        const int g = __ffs(m) - 1;
+        double sl[3], sa[3], nl[3], na[3];
+        for (int k = 0; k < 3; ++k) { sl[k] = AX[(g * 6 + k) * 32]; sa[k] = AX[(g * 6 + 3 + k) * 32]; }
+        rq_actinv(R, p, sl, sa, nl, na);
+        for (int k = 0; k < 3; ++k) { AX[(g * 6 + k) * 32] = nl[k]; AX[(g * 6 + 3 + k) * 32] = na[k]; }
+        const int ed = S.emit[g][op.t];
+        if (ed) rq_emit(slot + P.goff[g], ed, nl, na, v + 3, a + 3, ap, valid, lane);
+      }
+      for (unsigned m = op.own; m; m &= m - 1) {
+        const int g = __ffs(m) - 1;
+        double sl[3], sa[3];
+        for (int k = 0; k < 3; ++k) { sl[k] = S.grp[g].S[k]; sa[k] = S.grp[g].S[3 + k]; }
+        for (int k = 0; k < 3; ++k) { AX[(g * 6 + k) * 32] = sl[k]; AX[(g * 6 + 3 + k) * 32] = sa[k]; }
+        const int ed = S.emit[g][op.t];
+        if (ed) rq_emit(slot + P.goff[g], ed, sl, sa, v + 3, a + 3, ap, valid, lane);
+      }
+    } else {
+      for (int k = 0; k < 9; ++k) R[k] = MS[(op.mslot * 12 + k) * 32];
+      for (int k = 0; k < 3; ++k) p[k] = MS[(op.mslot * 12 + 9 + k) * 32];
+      for (unsigned m = op.live; m; m &= m - 1) {
+        const int g = __ffs(m) - 1;
+        double sl[3], sa[3], nl[3], na[3];
+        for (int k = 0; k < 3; ++k) { sl[k] = AX[(g * 6 + k) * 32]; sa[k] = AX[(g * 6 + 3 + k) * 32]; }
+        rq_act(R, p, sl, sa, nl, na);
+        for (int k = 0; k < 3; ++k) { AX[(g * 6 + k) * 32] = nl[k]; AX[(g * 6 + 3 + k) * 32] = na[k]; }
+      }
+      if (op.vload != 255) {
+        for (int k = 0; k < 6; ++k) { v[k] = VS[(op.vload * 12 + k) * 32]; a[k] = VS[(op.vload * 12 + 6 + k) * 32]; }
+      }
+    }
+  }
+  // columns read straight off the inputs (friction / actuator inertia / offset / coupling / rhs)
+  for (int g = 0; g < ms; ++g) {
+    const GqGroup& G = S.grp[g];
+    double* gs = slot + P.goff[g];
+    for (int t = 0; t < G.nsimple; ++t) {
+      const GqSimple s1 = S.simple[g][t];
+      const int ix = (s1.slot >> 3) * GQ_BLK + tq_idx(s1.slot & 7, lane);
+      double val = 0.0;
+      if (s1.kind == COL_RHS) {
+        if (valid && tau != nullptr) val = __ldg(tau + (int64_t)g * ld_tau + smp);
+      } else if (s1.kind == COL_EXTRA) {
+        const double vv = __ldg(vs + s1.vidx), aa = __ldg(as + s1.vidx);
+        val = s1.src == SRC_QDD ? aa : (s1.src == SRC_QD ? vv : (s1.src == SRC_SIGN_QD ? sgn(vv) : 1.0));
+      } else {
+        // add_coupling_TX40 (regressor.py:216-225): row block 4 <- [a5, v5, sign(v4+v5)], 5 <- [a4, v4, sign(v4+v5)]
+        const double v4 = __ldg(vs + 4), v5 = __ldg(vs + 5), a4 = __ldg(as + 4), a5 = __ldg(as + 5);
+        const double sg = sgn(v4 + v5);
+        val = G.rowblock == 4 ? (s1.src == 0 ? a5 : (s1.src == 1 ? v5 : sg)) : (s1.src == 0 ? a4 : (s1.src == 1 ? v4 : sg));
+      }
+      gs[ix] = valid ? val : 0.0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// consumer-side refill of the shared-memory tile with the next tile's blocks (called from gq_fold_h)
+struct RqRefill {
+  bool has_next;
+  bool armed;
+  int issued, nb, lane;
+  const unsigned* ready;
+  unsigned want;
+  const double* src;
+  double* dst;
+  uint64_t* bar;
+  __device__ __forceinline__ void arm() {
+    armed = true;
+    rq_mbar_expect_tx(bar, (uint32_t)nb * GQ_BLK * 8);
+  }
+  __device__ __forceinline__ void issue_upto(int k) {
+    while (issued <= k) {
+      rq_bulk_g2s(dst + issued * GQ_BLK, src + issued * GQ_BLK, GQ_BLK * 8, bar);
+      ++issued;
+    }
+  }
+  __device__ __forceinline__ void operator()(int k) {
+    if (!has_next) return;  // uniform
+    rq_fence_proxy_async();  // every lane: its generic-proxy writes to block k precede the bulk copy
+    __syncwarp();
+    if (lane == 0) {
+      if (!armed && rq_ld_acquire(ready) >= want) {
+        rq_fence_proxy_async();
+        arm();
+      }
+      if (armed) issue_upto(k);
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// ctl: ready[ring] | done[ring] | err
+__global__ void __launch_bounds__(GQ_MAXNW * 32, 1)
+rq_accumulate_kernel(const __grid_constant__ RqParams P, const unsigned char* __restrict__ tab_g,
+                     const unsigned short* __restrict__ tab_i, const double* __restrict__ q,
+                     const double* __restrict__ qd, const double* __restrict__ qdd, const double* __restrict__ tau,
+                     int64_t ld_tau, int64_t N, double* __restrict__ r_all, double* __restrict__ ring,
+                     unsigned* __restrict__ ctl, int first) {
+  extern __shared__ __align__(16) double gq_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  GqGen* Sg = reinterpret_cast<GqGen*>(gq_smem);
+  RqOp* ops = reinterpret_cast<RqOp*>(gq_smem + GQ_GEN_DOUBLES);
+  constexpr int OPS_DOUBLES = (int)(sizeof(RqOp) * RQ_MAXOPS / 8);
+  {
+    const int* src = reinterpret_cast<const int*>(&P.gq.gen);
+    int* dst = reinterpret_cast<int*>(Sg);
+    for (int i = threadIdx.x; i < (int)(sizeof(GqGen) / 4); i += blockDim.x) dst[i] = src[i];
+    const int* so = reinterpret_cast<const int*>(P.ops);
+    int* dop = reinterpret_cast<int*>(ops);
+    for (int i = threadIdx.x; i < (int)(sizeof(RqOp) * RQ_MAXOPS / 4); i += blockDim.x) dop[i] = so[i];
+  }
+  const int gw = blockIdx.x * nw + warp;
+  const int role = tab_g[gw], inst = tab_i[gw];
+  // this warp's shared memory: consumers [tile nb*GQ_BLK | scratch GQ_SCRATCH | mbarrier 2], producers [prod_smem]
+  int off = GQ_GEN_DOUBLES + OPS_DOUBLES;
+  for (int w = 0; w < warp; ++w) {
+    const int rw = tab_g[blockIdx.x * nw + w];
+    off += rw == 255 ? P.prod_smem_doubles : P.gq.gen.grp[rw].nb * GQ_BLK + GQ_SCRATCH + 2;
+  }
+  double* mine = gq_smem + off;
+  unsigned* ready = ctl;
+  unsigned* done = ctl + P.ring;
+  unsigned* err = ctl + 2 * P.ring;
+  uint64_t* bar = nullptr;
+  if (role != 255) {
+    bar = reinterpret_cast<uint64_t*>(mine + P.gq.gen.grp[role].nb * GQ_BLK + GQ_SCRATCH);
+    if (lane == 0) {
+      rq_mbar_init(bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      rq_fence_proxy_async();
+    }
+  }
+  __syncthreads();
+  const GqGen& S = *Sg;
+  const int64_t ntiles = (N + GQ_S - 1) / GQ_S;
+  const int ms = P.gq.ms;
+
+  if (role == 255) {
+    // ------------------------------------------------------------------ producer
+    for (int64_t tl = inst; tl < ntiles; tl += P.nprod) {
+      const int s = (int)(tl % P.ring);
+      const unsigned round = (unsigned)(tl / P.ring);
+      if (round > 0) {  // every row group must have copied the tile that used this slot before
+        unsigned ok = 1;
+        if (lane == 0) ok = rq_spin_ge(done + s, (unsigned)ms * round, err) ? 1u : 0u;
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        if (!ok) {
+          if (lane == 0) atomicCAS(err, 0u, (unsigned)RQ_ERR_PRODUCER);
+          return;
+        }
+      }
+      if (tl + P.nprod < ntiles) {  // pull the next tile's inputs towards L2
+        const int64_t sn = (tl + P.nprod) * GQ_S + lane;
+        if (sn < N) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(q + sn * P.gq.nq));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(qd + sn * P.gq.nv));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(qdd + sn * P.gq.nv));
+        }
+      }
+      rq_produce_tile(P, S, ops, mine, ring + (size_t)s * P.slot_doubles, q, qd, qdd, tau, ld_tau, tl * GQ_S, N, lane);
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) rq_st_release(ready + s, (unsigned)(tl + 1));
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- consumer of row group `role`
+  const int g = role;
+  const GqGroup& G = S.grp[g];
+  const int nb = G.nb, ninst = G.ninst;
+  double* tile = mine;
+  double* scr = tile + nb * GQ_BLK;
+  double* Rg = r_all + (size_t)G.r_off + (size_t)inst * G.r_size;
+  if (first) {
+    for (int i = lane; i < G.r_size; i += 32) Rg[i] = 0.0;
+    __syncwarp();
+  }
+  GqOffs offs;
+  gq_make_offs(offs, lane);
+  const int goff = P.goff[g];
+  uint32_t parity = 0;
+  int64_t tl = inst;
+  if (tl < ntiles) {  // first tile: wait, then request every block
+    const int s = (int)(tl % P.ring);
+    unsigned ok = 1;
+    if (lane == 0) {
+      ok = rq_spin_ge(ready + s, (unsigned)(tl + 1), err) ? 1u : 0u;
+      if (ok) {
+        rq_fence_proxy_async();
+        rq_mbar_expect_tx(bar, (uint32_t)nb * GQ_BLK * 8);
+        const double* src = ring + (size_t)s * P.slot_doubles + goff;
+        for (int b = 0; b < nb; ++b) rq_bulk_g2s(tile + b * GQ_BLK, src + b * GQ_BLK, GQ_BLK * 8, bar);
+      }
+    }
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    if (!ok) {
+      if (lane == 0) atomicCAS(err, 0u, (unsigned)RQ_ERR_CONSUMER);
+      return;
+    }
+  }
+  for (; tl < ntiles; tl += ninst) {
+    {  // the tile's bytes have landed
+      unsigned it = 0;
+      while (!rq_mbar_try_wait(bar, parity)) {
+        if (++it > RQ_SPIN_LIMIT) {
+          if (lane == 0) atomicCAS(err, 0u, (unsigned)RQ_ERR_MBAR);
+          return;
+        }
+      }
+      parity ^= 1u;
+    }
+    const int s = (int)(tl % P.ring);
+    if (lane == 0) {
+      __threadfence();
+      atomicAdd(done + s, 1u);
+    }
+    const int64_t nx = tl + ninst;
+    RqRefill rf;
+    rf.has_next = nx < ntiles;
+    rf.armed = false;
+    rf.issued = 0;
+    rf.nb = nb;
+    rf.lane = lane;
+    const int sn = (int)(nx % P.ring);
+    rf.ready = ready + sn;
+    rf.want = (unsigned)(nx + 1);
+    rf.src = ring + (size_t)sn * P.slot_doubles + goff;
+    rf.dst = tile;
+    rf.bar = bar;
+    gq_fold_h<false, 1, RqRefill>(tile, nb, Rg, 0, scr, offs, lane, rf);
+    if (rf.has_next) {
+      unsigned ok = 1;
+      if (lane == 0) {
+        if (!rf.armed) {
+          ok = rq_spin_ge(rf.ready, rf.want, err) ? 1u : 0u;
+          if (ok) {
+            rq_fence_proxy_async();
+            rf.arm();
+          }
+        }
+        if (ok) rf.issue_upto(nb - 1);
+      }
+      ok = __shfl_sync(0xffffffffu, ok, 0);
+      if (!ok) {
+        if (lane == 0) atomicCAS(err, 0u, (unsigned)RQ_ERR_CONSUMER);
+        return;
+      }
+    }
+  }
+}
+
+}  // namespace fg

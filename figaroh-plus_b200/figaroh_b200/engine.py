@@ -116,21 +116,35 @@ class RegressorConfig:
         return c
 
 
+def _model_desc(fm: FlatModel):
+    """fg_model_desc over the arrays of a FlatModel (returned with the arrays that must stay alive)."""
+    d = ModelDesc()
+    d.njoints, d.nq, d.nv = fm.njoints, fm.nq, fm.nv
+    keep = [np.ascontiguousarray(fm.parent, np.int32), np.ascontiguousarray(fm.jtype, np.int32),
+            np.ascontiguousarray(fm.axis), np.ascontiguousarray(fm.plc_R), np.ascontiguousarray(fm.plc_p),
+            np.ascontiguousarray(fm.idx_q, np.int32), np.ascontiguousarray(fm.idx_v, np.int32),
+            np.ascontiguousarray(fm.gravity), np.ascontiguousarray(fm.mass)]
+    (d.parent, d.jtype, d.axis, d.plc_R, d.plc_p, d.idx_q, d.idx_v, d.gravity, d.mass) = [a.ctypes.data for a in keep]
+    return d, keep
+
+
+def describe_plan(model, cfg: "RegressorConfig", sm_count=148, max_smem=227 * 1024) -> dict:
+    """Host-only: the fused path's symbolic pass for (model, cfg) - walk program, row-group problems, warp split."""
+    import json
+    d, keep = _model_desc(flatten_model(model))
+    cs = cfg.cstruct()
+    buf = C.create_string_buffer(1 << 16)
+    check(_lib.lib().fg_plan_describe(C.byref(d), C.byref(cs), sm_count, max_smem, buf, len(buf)))
+    return json.loads(buf.value.decode())
+
+
 class DeviceModel:
     """A flattened kinematic tree resident on the current CUDA device (fg_model)."""
 
     def __init__(self, model):
         _require_cuda()
         self.flat: FlatModel = flatten_model(model)
-        fm = self.flat
-        d = ModelDesc()
-        d.njoints, d.nq, d.nv = fm.njoints, fm.nq, fm.nv
-        self._keep = [np.ascontiguousarray(fm.parent, np.int32), np.ascontiguousarray(fm.jtype, np.int32),
-                      np.ascontiguousarray(fm.axis), np.ascontiguousarray(fm.plc_R), np.ascontiguousarray(fm.plc_p),
-                      np.ascontiguousarray(fm.idx_q, np.int32), np.ascontiguousarray(fm.idx_v, np.int32),
-                      np.ascontiguousarray(fm.gravity), np.ascontiguousarray(fm.mass)]
-        (d.parent, d.jtype, d.axis, d.plc_R, d.plc_p, d.idx_q, d.idx_v, d.gravity, d.mass) = \
-            [a.ctypes.data for a in self._keep]
+        d, self._keep = _model_desc(self.flat)
         self._h = C.c_void_p()
         check(_lib.lib().fg_model_create(C.byref(d), C.byref(self._h)))
 

@@ -220,6 +220,12 @@ int fg_state_accumulate_samples_host(fg_state* s, const fg_model* m, const fg_re
  * (accumulate_samples / accumulate_dense) with CUDA events on the caller's stream;
  * fg_state_get_timing returns the summed duration in ms and the number of launches. */
 long long fg_launch_count(void);
+/* Host-only (no device needed): JSON description of the fused path's symbolic pass for (model, cfg) - the
+ * producers' depth-first walk program over the kinematic tree, the local column problem of every row group
+ * (the non-zero columns of the rows of regressor.py:49-70 for that joint) and the warp split.  There is no
+ * reference counterpart; it exposes the plan for tests and documentation. */
+int fg_plan_describe(const fg_model_desc* desc, const fg_regressor_cfg* cfg, int32_t sm_count, int32_t max_smem,
+                     char* buf, int32_t buflen);
 int fg_state_set_timing(fg_state* s, int on);
 int fg_state_get_timing(fg_state* s, double* total_ms, long long* launches);
 
