@@ -16,6 +16,7 @@
 #include "fg_tq.h"
 #include "fg_gq.h"
 #include "fg_rq.h"
+#include "fg_wide.h"
 #include "fg_prefilter.cuh"
 
 using namespace fg;
@@ -400,7 +401,7 @@ extern "C" int fg_plan_describe(const fg_model_desc* d, const fg_regressor_cfg* 
   o += t;
   if (rl.ok) {
     const GqParams& G = rq->gq;
-    snprintf(t, sizeof t, ", \"nw\": %d, \"npc\": %d, \"smem\": %d, \"nproc\": %d, \"ring\": %d, \"slot_doubles\": %d, "
+    snprintf(t, sizeof t, ", \"nw\": %d, \"producer_ctas\": %d, \"smem\": %d, \"nproc\": %d, \"ring\": %d, \"slot_doubles\": %d, "
              "\"nvslots\": %d, \"nmslots\": %d, \"r_doubles\": %lld, \"nbf\": %d", rl.nw, rq->npc, rl.smem, G.nproc,
              rq->ring, rq->slot_doubles, rq->nvslots, rq->nmslots, (long long)rl.r_doubles, G.nbf);
     o += t;
@@ -499,7 +500,7 @@ extern "C" int fg_state_p(const fg_state* s) { return s ? s->p : -1; }
 extern "C" int64_t fg_state_rows(const fg_state* s) { return s ? s->rows : -1; }
 
 extern "C" int fg_state_create(int32_t p, fg_state** out) {
-  if (p < 1 || p > 479 || !out) return set_err(FG_ERR_INVALID, "fg_state_create: p=%d outside [1,479]", p);
+  if (p < 1 || p + 1 > WD_MAX_P1 || !out) return set_err(FG_ERR_INVALID, "fg_state_create: p=%d outside [1,%d]", p, WD_MAX_P1 - 1);
   std::unique_ptr<fg_state> s(new fg_state);
   s->p = p; s->p1 = p + 1;
   const int p1 = s->p1;
@@ -622,6 +623,12 @@ static int launch_merge_level(double* parts, int nparts, int stride, int p1, int
 }
 
 static int merge_level(double* parts, int nparts, int stride, int p1, int max_smem, cudaStream_t st) {
+  if (p1 > 128) {  // wide factors: the whole CTA folds one pair (fg_wide.cuh)
+    cudaError_t e = wide_launch_merge_level(parts, nparts, stride, p1, st);
+    if (e != cudaSuccess) return set_err(FG_ERR_CUDA, "wide merge failed: %s", cudaGetErrorString(e));
+    FG_LAUNCHED();
+    return FG_OK;
+  }
   const int nslot = (p1 + 31) / 32;
   if (nslot <= 1) return launch_merge_level<1, 24>(parts, nparts, stride, p1, max_smem, st);
   if (nslot <= 2) return launch_merge_level<2, 24>(parts, nparts, stride, p1, max_smem, st);
@@ -707,6 +714,27 @@ extern "C" int fg_state_accumulate_dense(fg_state* s, const double* W, int64_t l
     return set_err(FG_ERR_UNSUPPORTED, "fg_state_accumulate_dense: the state holds a permuted factor (fused samples); use a fresh state");
   cudaStream_t st = (cudaStream_t)stream;
   const int nslot = (s->p1 + 31) / 32;
+  if (s->p1 > 96) {  // CTA-wide register tile (fg_wide.cuh)
+    int sm_count, max_smem;
+    int rc = device_limits(&sm_count, &max_smem);
+    if (rc) return rc;
+    const int tr = wide_dense_tile_rows(s->p1);
+    if (tr <= 0) return set_err(FG_ERR_UNSUPPORTED, "fg_state_accumulate_dense: %d columns are too many", s->p);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((rows + tr - 1) / tr, sm_count));
+    rc = ensure_parts(s, grid + 1);
+    if (rc) return rc;
+    rc = timing_begin(s, st);
+    if (rc) return rc;
+    cudaError_t e = wide_launch_dense(W, ldw, tau, rows, s->p1, s->d_parts, grid, st);
+    rc = timing_end(s, st);
+    if (rc) return rc;
+    if (e != cudaSuccess) return set_err(FG_ERR_CUDA, "wide dense kernel failed: %s", cudaGetErrorString(e));
+    FG_LAUNCHED();
+    rc = merge_parts_into_state(s, grid, max_smem, st);
+    if (rc) return rc;
+    s->rows += rows;
+    return FG_OK;
+  }
   if (nslot <= 1) return launch_dense<1, 24>(s, W, ldw, tau, rows, st);
   if (nslot <= 2) return launch_dense<2, 24>(s, W, ldw, tau, rows, st);
   if (nslot <= 3) return launch_dense<3, 24>(s, W, ldw, tau, rows, st);
@@ -1008,6 +1036,28 @@ static int accumulate_samples_dev(fg_state* s, fg_model* m, const fg_regressor_c
     const char* e = getenv("FG_USE_BQ");
     const bool use_bq = !(e && e[0] == '0');
     if (use_bq && bq_supported(pl->P)) return launch_bq(s, m, pl, q, v, a, tau, ld_tau, N, st);
+  }
+  {
+    const char* e = getenv("FG_USE_WIDE");
+    const bool use_wide = !(e && e[0] == '0');
+    const int spt = wide_samples_per_tile(ms, pl->P.p1);
+    if (use_wide && spt > 0 && s->perm.empty()) {
+      const int64_t ntiles = (N + spt - 1) / spt;
+      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, m->sm_count));
+      rc = ensure_parts(s, grid + 1);
+      if (rc) return rc;
+      rc = timing_begin(s, st);
+      if (rc) return rc;
+      cudaError_t ce = wide_launch_samples(pl->P, pl->ptrs, q, v, a, tau, ld_tau, N, s->d_parts, grid, m->max_smem, st);
+      rc = timing_end(s, st);
+      if (rc) return rc;
+      if (ce != cudaSuccess) return set_err(FG_ERR_CUDA, "wide fused kernel failed: %s", cudaGetErrorString(ce));
+      FG_LAUNCHED();
+      rc = merge_parts_into_state(s, grid, m->max_smem, st);
+      if (rc) return rc;
+      s->rows += N * ms;
+      return FG_OK;
+    }
   }
   if (ms == 6 && nslot <= 3) return launch_fused<3, 6, 4>(s, m, pl, q, v, a, tau, ld_tau, N, st);
   if (ms == 6 && nslot <= 11) return launch_fused<11, 6, 1>(s, m, pl, q, v, a, tau, ld_tau, N, st);

@@ -49,6 +49,9 @@ __device__ __forceinline__ void rq_bulk_g2s(void* dst_smem, const void* src_gmem
                : "memory");
 }
 __device__ __forceinline__ void rq_fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// shared-memory only: orders this thread's generic-proxy accesses to the tile before a bulk copy into it, without
+// waiting for the thread's outstanding global stores (the R blocks)
+__device__ __forceinline__ void rq_fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ unsigned rq_ld_acquire(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -292,7 +295,7 @@ struct RqRefill {
   }
   __device__ __forceinline__ void operator()(int k) {
     if (!has_next) return;  // uniform
-    rq_fence_proxy_async();  // every lane: its generic-proxy writes to block k precede the bulk copy
+    rq_fence_proxy_async_smem();  // every lane: its generic-proxy writes to block k precede the bulk copy
     __syncwarp();
     if (lane == 0) {
       if (!armed && rq_ld_acquire(ready) >= want) {
@@ -427,10 +430,7 @@ rq_accumulate_kernel(const __grid_constant__ RqParams P, const unsigned char* __
       parity ^= 1u;
     }
     const int s = (int)(tl % P.ring);
-    if (lane == 0) {
-      __threadfence();
-      atomicAdd(done + s, 1u);
-    }
+    if (lane == 0) atomicAdd(done + s, 1u);  // the copy has read the slot: it may be refilled
     const int64_t nx = tl + ninst;
     RqRefill rf;
     rf.has_next = nx < ntiles;

@@ -222,12 +222,18 @@ RqLaunch rq_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, co
   const double pcost = 400.0 + 420.0 * nproc + 45.0 * n_transports + 190.0 * n_emits + 25.0 * n_simple + 60.0 * (nops - nproc);
   rl.sm_count = std::max(1, sm_count);
   const int gen_doubles = GQ_GEN_DOUBLES + (int)(sizeof(RqOp) * RQ_MAXOPS / 8);
-  for (int nw = GQ_MAXNW; nw >= 2; --nw) {
-    int npc = (int)(nw * pcost / (pcost + csum) + 0.5);
-    npc = env_int("FG_RQ_NPC", npc);
-    npc = std::max(1, std::min(npc, nw - 1));
-    const int nc = nw - npc;
-    const int W = rl.sm_count * nc;
+  // Roles are assigned per CTA (= per SM): a producer SM runs only the generator, a consumer SM only the fold, so
+  // each SM's instruction cache holds one of the two code paths and the 16 producer warps of an SM hide each
+  // other's load latencies.  (First version: producers and consumers mixed inside every CTA - the generator's code
+  // was evicted between two uses, `no_instruction` became the top stall, profiles/ncu_rq_r02_v5a.md.)
+  int npcta = (int)(rl.sm_count * pcost / (pcost + csum) + 0.5);
+  npcta = env_int("FG_RQ_NPCTA", npcta);
+  npcta = std::max(1, std::min(npcta, rl.sm_count - 1));
+  if (rl.sm_count < 2) { rq_fail(why, "needs at least two SMs"); return rl; }
+  const int ncta = rl.sm_count - npcta;
+  for (int nw = GQ_MAXNW; nw >= 1; --nw) {
+    if (R.prod_smem_doubles * nw * 8 + gen_doubles * 8 > max_smem) continue;
+    const int W = ncta * nw;
     if (W < ms) continue;
     // largest-remainder apportionment of the consumer warps, at least one per row group
     std::vector<int> cnt(ms);
@@ -245,18 +251,20 @@ RqLaunch rq_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, co
     for (int k = 0; left > 0; k = (k + 1) % ms, --left) ++cnt[rem[k].second];
     for (int k = 0; left < 0; k = (k + 1) % ms)
       if (cnt[rem[ms - 1 - k].second] > 1) { --cnt[rem[ms - 1 - k].second]; ++left; }
-    // interleave: consumer position cw goes to the row group that is furthest behind its proportional schedule
+    // interleave: consumer position cw goes to the row group that is furthest behind its proportional schedule;
+    // producer CTAs are spread evenly over the grid
     rl.tab_g.assign((size_t)rl.sm_count * nw, 0);
     rl.tab_i.assign((size_t)rl.sm_count * nw, 0);
     std::vector<int> given(ms, 0);
-    int worst = 0, cw = 0;
+    int worst = 0, cw = 0, pw = 0;
     for (int b = 0; b < rl.sm_count; ++b) {
+      const bool prod = (int64_t)(b + 1) * npcta / rl.sm_count > (int64_t)b * npcta / rl.sm_count;
       int doubles = 0;
       for (int w = 0; w < nw; ++w) {
         const int gw = b * nw + w;
-        if (w < npc) {
+        if (prod) {
           rl.tab_g[gw] = 255;
-          rl.tab_i[gw] = (unsigned short)(b * npc + w);
+          rl.tab_i[gw] = (unsigned short)pw++;
           doubles += R.prod_smem_doubles;
           continue;
         }
@@ -278,8 +286,8 @@ RqLaunch rq_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, co
     if (smem > max_smem) continue;
     rl.nw = nw;
     rl.smem = smem;
-    R.npc = npc;
-    R.nprod = rl.sm_count * npc;
+    R.npc = npcta;
+    R.nprod = pw;
     int64_t off = 0;
     int maxinst = 0;
     for (int g = 0; g < ms; ++g) {
@@ -294,8 +302,8 @@ RqLaunch rq_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, co
     rl.r_doubles = off;
     break;
   }
-  if (rl.nw < 2) { rq_fail(why, "tile does not fit shared memory"); return rl; }
-  R.ring = std::max(8, env_int("FG_RQ_RING", 512));
+  if (rl.nw < 1) { rq_fail(why, "tile does not fit shared memory"); return rl; }
+  R.ring = std::max(8, env_int("FG_RQ_RING", 1024));
   rl.ring_doubles = (int64_t)R.ring * R.slot_doubles;
   rl.rfull_doubles = (int64_t)T.nbf * (T.nbf + 1) / 2 * 64;
   rl.ok = true;

@@ -59,7 +59,7 @@ struct RqParams {
   int slot_doubles;        // doubles of one ring slot (sum_g nb_g * GQ_BLK)
   int ring;                // slots
   int nprod;               // producer warps of the whole launch
-  int npc;                 // producer warps per CTA
+  int npc;                 // producer CTAs (a CTA is all producers or all consumers)
   int prod_smem_doubles;   // shared memory of one producer warp
   int nvslots, nmslots;
 };

@@ -1,0 +1,94 @@
+// fg_wide.cu - launchers of the CTA-wide register-tile kernels (fg_wide.cuh): fused samples -> factor for any
+// tree / row-group count / up to 767 columns, dense matrix -> factor, and the pairwise merge of wide parts.
+#include <algorithm>
+
+#include "fg_wide.cuh"
+#include "fg_wide.h"
+
+namespace fg {
+
+template <int MSMAX, int S, int NSLOT>
+static cudaError_t launch_samples(const Plan& P, const DevPlanPtrs& pp, const double* q, const double* v,
+                                  const double* a, const double* tau, int64_t ld_tau, int64_t N, double* parts,
+                                  int grid, int max_smem, cudaStream_t st) {
+  constexpr int TR = MSMAX * S;
+  const WideLayout L = wide_layout(P.nj, P.ms, P.nv, S, TR);
+  if (L.total > max_smem) return cudaErrorInvalidConfiguration;
+  auto kern = wide_accumulate_samples_kernel<MSMAX, S, NSLOT, 1>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, WD_THREADS + 32, L.total, st>>>(pp, q, v, a, tau, ld_tau, N, parts);
+  return cudaGetLastError();
+}
+
+int wide_samples_per_tile(int ms, int p1) {
+  const int nslot = (p1 + WD_THREADS - 1) / WD_THREADS;
+  if (nslot > 3 || ms > 48) return 0;
+  if (nslot == 1) return ms <= 6 ? 8 : (ms <= 8 ? 6 : (ms <= 24 ? 2 : 1));
+  if (nslot == 2) return ms <= 6 ? 6 : (ms <= 8 ? 4 : 1);
+  return ms <= 6 ? 4 : (ms <= 8 ? 3 : (ms <= 24 ? 1 : 0));
+}
+
+cudaError_t wide_launch_samples(const Plan& P, const DevPlanPtrs& pp, const double* q, const double* v, const double* a,
+                                const double* tau, int64_t ld_tau, int64_t N, double* parts, int grid, int max_smem,
+                                cudaStream_t st) {
+  const int nslot = (P.p1 + WD_THREADS - 1) / WD_THREADS, ms = P.ms;
+#define FG_WD(MS_, S_, NS_) return launch_samples<MS_, S_, NS_>(P, pp, q, v, a, tau, ld_tau, N, parts, grid, max_smem, st)
+  if (nslot == 1) {
+    if (ms <= 6) FG_WD(6, 8, 1);
+    if (ms <= 8) FG_WD(8, 6, 1);
+    if (ms <= 24) FG_WD(24, 2, 1);
+    if (ms <= 48) FG_WD(48, 1, 1);
+  } else if (nslot == 2) {
+    if (ms <= 6) FG_WD(6, 6, 2);
+    if (ms <= 8) FG_WD(8, 4, 2);
+    if (ms <= 24) FG_WD(24, 1, 2);
+    if (ms <= 48) FG_WD(48, 1, 2);
+  } else if (nslot == 3) {
+    if (ms <= 6) FG_WD(6, 4, 3);
+    if (ms <= 8) FG_WD(8, 3, 3);
+    if (ms <= 24) FG_WD(24, 1, 3);
+  }
+#undef FG_WD
+  return cudaErrorInvalidConfiguration;
+}
+
+template <int TR, int NSLOT>
+static cudaError_t launch_dense_t(const double* W, int64_t ldw, const double* tau, int64_t rows, int p1, double* parts,
+                                  int grid, cudaStream_t st) {
+  const int smem = 2 * (((TR + 7) / 8) * 8 + 4) * 8;
+  wide_accumulate_dense_kernel<TR, NSLOT, 1><<<grid, WD_THREADS, smem, st>>>(W, ldw, tau, rows, p1, parts);
+  return cudaGetLastError();
+}
+
+int wide_dense_tile_rows(int p1) {
+  const int nslot = (p1 + WD_THREADS - 1) / WD_THREADS;
+  return nslot == 1 ? 64 : (nslot == 2 ? 40 : (nslot == 3 ? 24 : 0));
+}
+
+cudaError_t wide_launch_dense(const double* W, int64_t ldw, const double* tau, int64_t rows, int p1, double* parts,
+                              int grid, cudaStream_t st) {
+  const int nslot = (p1 + WD_THREADS - 1) / WD_THREADS;
+  if (nslot == 1) return launch_dense_t<64, 1>(W, ldw, tau, rows, p1, parts, grid, st);
+  if (nslot == 2) return launch_dense_t<40, 2>(W, ldw, tau, rows, p1, parts, grid, st);
+  if (nslot == 3) return launch_dense_t<24, 3>(W, ldw, tau, rows, p1, parts, grid, st);
+  return cudaErrorInvalidConfiguration;
+}
+
+template <int TR, int NSLOT>
+static cudaError_t launch_merge_t(double* parts, int nparts, int stride, int p1, cudaStream_t st) {
+  const int pairs = (nparts + 2 * stride - 1) / (2 * stride);
+  const int smem = 2 * (((TR + 7) / 8) * 8 + 4) * 8;
+  wide_merge_pairs_kernel<TR, NSLOT><<<pairs, WD_THREADS, smem, st>>>(parts, nparts, stride, p1);
+  return cudaGetLastError();
+}
+
+cudaError_t wide_launch_merge_level(double* parts, int nparts, int stride, int p1, cudaStream_t st) {
+  const int nslot = (p1 + WD_THREADS - 1) / WD_THREADS;
+  if (nslot == 1) return launch_merge_t<64, 1>(parts, nparts, stride, p1, st);
+  if (nslot == 2) return launch_merge_t<40, 2>(parts, nparts, stride, p1, st);
+  if (nslot == 3) return launch_merge_t<24, 3>(parts, nparts, stride, p1, st);
+  return cudaErrorInvalidConfiguration;
+}
+
+}  // namespace fg

@@ -1,0 +1,327 @@
+// fg_wide.cuh - kernel (1)+(2) for WIDE problems: any kinematic tree, any number of row groups, up to 767
+// columns (Talos with free-flyer in external-wrench mode: 6 rows x 330 columns per sample, regressor.py:89-192;
+// the full 24-row-block TIAGo tree; the drop-in double_QR on a dense matrix that is already in HBM).
+//
+// The row-group streams of fg_ringqr.cuh keep one 32 x w_g tile per WARP in shared memory; at w_g = 331 that
+// is 85 KB per warp and two warps per SM.  Here the whole CTA works on ONE tile that lives in registers:
+//   * 256 threads, thread t owns columns t, t + 256, ...  (NSLOT of them) of a TR-row tile: B[TR][NSLOT];
+//   * column step c: the owner of column c takes the Householder reflector of [R_cc; B[:, c]] (LAPACK dlarfg
+//     convention) from its own registers, publishes (v, tau, 1/(alpha-beta)) through shared memory, ONE named
+//     barrier, then every thread applies it to its own columns: the dot products and the rank-1 update never
+//     leave the thread - no shuffles, no reductions, pure DFMA;
+//   * the CTA's triangular factor lives in an L2-resident global scratch (its part slot): row c is read and
+//     written exactly once per tile, requested one step ahead;
+//   * the regressor entries of a tile are generated column by column (gen_column, fg_device.cuh: body column
+//     in the body frame, carried up the tree to the row group's joint) from per-sample forward kinematics that
+//     a ninth warp computes for the NEXT tile while the other eight fold the current one.
+#pragma once
+#include "fg_device.cuh"
+
+namespace fg {
+
+constexpr int WD_THREADS = 256;   // consumer threads (column owners)
+constexpr int WD_BAR = 1;         // named barrier of the 256 column owners
+
+__device__ __forceinline__ void wd_bar() { asm volatile("bar.sync %0, %1;" ::"n"(WD_BAR), "n"(WD_THREADS) : "memory"); }
+
+// Fold the register tile B (TR rows; thread `tid` owns columns tid + 256 s) into the packed upper-triangular
+// factor Rt (p1 columns, global memory, private to this CTA).  Columns < c_begin of the tile are zero.
+// xs: 2 * (ceil8(TR) + 4) doubles of shared memory.
+template <int TR, int NSLOT>
+__device__ __forceinline__ void wide_fold(double (&B)[TR][NSLOT], double* __restrict__ Rt, int p1, int c_begin,
+                                          double* xs, int tid) {
+  constexpr int XS = ((TR + 7) / 8) * 8 + 4;  // reflector (padded to whole 8-row chunks) + scalars
+  double rho[NSLOT];
+#pragma unroll
+  for (int s = 0; s < NSLOT; ++s) {
+    const int col = tid + WD_THREADS * s;
+    rho[s] = (col >= c_begin && col < p1) ? __ldcg(Rt + tri_off(c_begin, p1) + col - c_begin) : 0.0;
+  }
+  for (int c = c_begin; c < p1; ++c) {
+    double rho_n[NSLOT];
+    const int roff = tri_off(c, p1);
+    {
+      const int rn = roff + (p1 - c);  // tri_off(c + 1, p1)
+#pragma unroll
+      for (int s = 0; s < NSLOT; ++s) {
+        const int col = tid + WD_THREADS * s;
+        rho_n[s] = (c + 1 < p1 && col > c && col < p1) ? __ldcg(Rt + rn + col - c - 1) : 0.0;
+      }
+    }
+    const int tc = c & (WD_THREADS - 1), sc = c / WD_THREADS;
+    double* xb = xs + (c & 1) * XS;
+    if (tid == tc) {
+      double alpha = 0.0;
+      double sg[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int s = 0; s < NSLOT; ++s)
+        if (s == sc) {
+          alpha = rho[s];
+#pragma unroll
+          for (int r = 0; r < TR; ++r) {
+            const double x = B[r][s];
+            xb[r] = x;
+            sg[r & 3] = fma(x, x, sg[r & 3]);
+          }
+        }
+      const double sigma = (sg[0] + sg[1]) + (sg[2] + sg[3]);
+      double inv = 0.0, tauh = 0.0;
+      if (sigma != 0.0) {  // else H = I (dlarfg with xnorm == 0)
+        const double mu = fma(alpha, alpha, sigma);
+        const double nrm = sqrt(mu);
+        const double beta = alpha >= 0.0 ? -nrm : nrm;
+        const double den = alpha - beta;
+        inv = 1.0 / den;
+        tauh = (beta - alpha) / beta;
+        __stcg(Rt + roff, beta);
+      }
+      xb[TR] = inv;
+      xb[TR + 1] = tauh;
+    }
+    wd_bar();
+    const double inv = xb[TR], tauh = xb[TR + 1];
+    if (tauh != 0.0) {  // uniform
+      // v is streamed from shared memory in chunks of 8 rows (broadcast reads), once for the dot products of all
+      // the thread's columns and once for their updates: the tile owns the registers, not the reflector
+      double dd[NSLOT];
+#pragma unroll
+      for (int s = 0; s < NSLOT; ++s) dd[s] = 0.0;
+#pragma unroll
+      for (int r0 = 0; r0 < TR; r0 += 8) {
+        double v[8];
+#pragma unroll
+        for (int r = 0; r < 8; r += 2) {
+          const double2 t2 = *reinterpret_cast<const double2*>(xb + r0 + r);
+          v[r] = t2.x;
+          v[r + 1] = t2.y;
+        }
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) {
+          double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+          for (int r = 0; r < 8; r += 2) {
+            if (r0 + r < TR) d0 = fma(v[r], B[r0 + r][s], d0);
+            if (r0 + r + 1 < TR) d1 = fma(v[r + 1], B[r0 + r + 1][s], d1);
+          }
+          dd[s] += d0 + d1;
+        }
+      }
+      double gco[NSLOT];
+#pragma unroll
+      for (int s = 0; s < NSLOT; ++s) {
+        const int col = tid + WD_THREADS * s;
+        gco[s] = 0.0;
+        if (col > c && col < p1) {
+          const double sdot = fma(dd[s], inv, rho[s]);  // w^T [rho; b],  w = [1; x * inv]
+          __stcg(Rt + roff + col - c, fma(-tauh, sdot, rho[s]));
+          gco[s] = tauh * sdot * inv;
+        }
+      }
+#pragma unroll
+      for (int r0 = 0; r0 < TR; r0 += 8) {
+        double v[8];
+#pragma unroll
+        for (int r = 0; r < 8; r += 2) {
+          const double2 t2 = *reinterpret_cast<const double2*>(xb + r0 + r);
+          v[r] = t2.x;
+          v[r + 1] = t2.y;
+        }
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s)
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+            if (r0 + r < TR) B[r0 + r][s] = fma(-gco[s], v[r], B[r0 + r][s]);
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) rho[s] = rho_n[s];
+  }
+  wd_bar();  // the last step's reads of xs are done before the next tile's first owner writes
+}
+
+// ------------------------------------------------------------------ fused: samples -> factor
+// grid: persistent; CTA b folds tiles b, b + gridDim.x, ... into its own part slot parts[b].
+// blockDim = 288: warps 0..7 own columns, warp 8 runs the forward kinematics of the next tile.
+// shared memory: plan tables | 2 x (fw [S][nj][27] | vs [S][nv] | as [S][nv]) | xs
+struct WideLayout {
+  int off_plan, off_joints, off_rows, off_fw[2], off_vs[2], off_as[2], off_xs, total;
+};
+__host__ __device__ inline WideLayout wide_layout(int nj, int ms, int nv, int S, int TR) {
+  WideLayout L;
+  int o = 0;
+  L.off_plan = o;   o = align16(o + (int)sizeof(Plan));
+  L.off_joints = o; o = align16(o + nj * (int)sizeof(DevJoint));
+  L.off_rows = o;   o = align16(o + ms * (int)sizeof(RowDesc));
+  for (int b = 0; b < 2; ++b) {
+    L.off_fw[b] = o; o = align16(o + S * nj * FW_STRIDE * 8);
+    L.off_vs[b] = o; o = align16(o + S * nv * 8);
+    L.off_as[b] = o; o = align16(o + S * nv * 8);
+  }
+  L.off_xs = o; o = align16(o + 2 * (((TR + 7) / 8) * 8 + 4) * 8);
+  L.total = o;
+  return L;
+}
+
+// (__launch_bounds__(288) makes ptxas budget for 384 threads = 168 registers; nine warps fit with 224.)
+template <int MSMAX, int S, int NSLOT, int MINB>
+__global__ void __maxnreg__(224)
+wide_accumulate_samples_kernel(DevPlanPtrs pp, const double* __restrict__ q, const double* __restrict__ qd,
+                               const double* __restrict__ qdd, const double* __restrict__ tau, int64_t ld_tau,
+                               int64_t N, double* __restrict__ parts) {
+  constexpr int TR = MSMAX * S;
+  extern __shared__ __align__(16) unsigned char wd_smem[];
+  const Plan P0 = *pp.plan;
+  const WideLayout L = wide_layout(P0.nj, P0.ms, P0.nv, S, TR);
+  const int tid = threadIdx.x;
+  {
+    if (tid == 0) *reinterpret_cast<Plan*>(wd_smem + L.off_plan) = P0;
+    double* J = reinterpret_cast<double*>(wd_smem + L.off_joints);
+    for (int i = tid; i < P0.nj * (int)(sizeof(DevJoint) / 8); i += blockDim.x) J[i] = reinterpret_cast<const double*>(pp.joints)[i];
+    double* Rw = reinterpret_cast<double*>(wd_smem + L.off_rows);
+    for (int i = tid; i < P0.ms * (int)(sizeof(RowDesc) / 8); i += blockDim.x) Rw[i] = reinterpret_cast<const double*>(pp.rows)[i];
+  }
+  __syncthreads();
+  const Plan& P = *reinterpret_cast<const Plan*>(wd_smem + L.off_plan);
+  const DevJoint* J = reinterpret_cast<const DevJoint*>(wd_smem + L.off_joints);
+  const RowDesc* rows = reinterpret_cast<const RowDesc*>(wd_smem + L.off_rows);
+  double* xs = reinterpret_cast<double*>(wd_smem + L.off_xs);
+  const int p1 = P.p1, ntri = p1 * (p1 + 1) / 2;
+  double* Rt = parts + (size_t)blockIdx.x * part_doubles(p1);
+  for (int i = tid; i < ntri; i += blockDim.x) Rt[i] = 0.0;
+  const bool kin = tid >= WD_THREADS;  // warp 8
+  const int lane = tid & 31;
+  const int64_t ntiles = (N + S - 1) / S;
+
+  ColDesc cd[NSLOT];
+  uint64_t anc[NSLOT];
+  double csq[NSLOT];
+#pragma unroll
+  for (int s = 0; s < NSLOT; ++s) {
+    const int col = tid + WD_THREADS * s;
+    cd[s].kind = COL_ZERO; cd[s].body = 0; cd[s].k = 0; cd[s].vidx = 0; cd[s].grp = -2;
+    anc[s] = 0;
+    csq[s] = 0.0;
+    if (!kin && col < p1) {
+      cd[s] = pp.cols[col];
+      anc[s] = col_ancmask(cd[s]);
+    }
+  }
+  auto forward_tile = [&](int64_t tile, int buf) {
+    if (lane < S) {
+      const int64_t smp = tile * S + lane;
+      const bool valid = smp < N;
+      const int64_t scl = valid ? smp : 0;
+      forward_sample(P, J, q + scl * P.nq, qd + scl * P.nv, qdd + scl * P.nv,
+                     reinterpret_cast<double*>(wd_smem + L.off_fw[buf]) + (size_t)lane * P.nj * FW_STRIDE,
+                     reinterpret_cast<double*>(wd_smem + L.off_vs[buf]) + lane * P.nv,
+                     reinterpret_cast<double*>(wd_smem + L.off_as[buf]) + lane * P.nv, valid);
+    }
+  };
+  int64_t tile = blockIdx.x;
+  if (kin && tile < ntiles) forward_tile(tile, 0);
+  __syncthreads();
+  int buf = 0;
+  for (; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+    if (kin) {
+      if (tile + gridDim.x < ntiles) forward_tile(tile + gridDim.x, buf ^ 1);
+    } else {
+      const double* fw = reinterpret_cast<const double*>(wd_smem + L.off_fw[buf]);
+      const double* vs = reinterpret_cast<const double*>(wd_smem + L.off_vs[buf]);
+      const double* as = reinterpret_cast<const double*>(wd_smem + L.off_as[buf]);
+      double B[TR][NSLOT];
+#pragma unroll
+      for (int s = 0; s < NSLOT; ++s) {
+        double out[TR];
+        gen_column<MSMAX, S>(P, J, rows, cd[s], anc[s], fw, vs, as, tau, ld_tau, tile * S, N, out);
+#pragma unroll
+        for (int r = 0; r < TR; ++r) {
+          B[r][s] = out[r];
+          csq[s] = fma(out[r], out[r], csq[s]);
+        }
+      }
+      wide_fold<TR, NSLOT>(B, Rt, p1, 0, xs, tid);
+    }
+    __syncthreads();
+  }
+  if (!kin) {
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) {
+      const int col = tid + WD_THREADS * s;
+      if (col < p1) Rt[ntri + col] = csq[s];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ dense: rows x p matrix in HBM -> factor
+template <int TR, int NSLOT, int MINB>
+__global__ void __launch_bounds__(WD_THREADS, MINB)
+wide_accumulate_dense_kernel(const double* __restrict__ W, int64_t ldw, const double* __restrict__ tau, int64_t nrows,
+                             int p1, double* __restrict__ parts) {
+  extern __shared__ __align__(16) unsigned char wd_smem[];
+  double* xs = reinterpret_cast<double*>(wd_smem);
+  const int tid = threadIdx.x;
+  const int ntri = p1 * (p1 + 1) / 2, p = p1 - 1;
+  double* Rt = parts + (size_t)blockIdx.x * part_doubles(p1);
+  for (int i = tid; i < ntri; i += blockDim.x) Rt[i] = 0.0;
+  __syncthreads();
+  double csq[NSLOT];
+#pragma unroll
+  for (int s = 0; s < NSLOT; ++s) csq[s] = 0.0;
+  const int64_t ntiles = (nrows + TR - 1) / TR;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t r0 = tile * TR;
+    double B[TR][NSLOT];
+#pragma unroll
+    for (int r = 0; r < TR; ++r) {
+      const int64_t row = r0 + r;
+#pragma unroll
+      for (int s = 0; s < NSLOT; ++s) {
+        const int col = tid + WD_THREADS * s;
+        double val = 0.0;
+        if (row < nrows) {
+          if (col < p) val = __ldcs(W + row * ldw + col);
+          else if (col == p && tau != nullptr) val = __ldcs(tau + row);
+        }
+        B[r][s] = val;
+        csq[s] = fma(val, val, csq[s]);
+      }
+    }
+    wide_fold<TR, NSLOT>(B, Rt, p1, 0, xs, tid);
+  }
+#pragma unroll
+  for (int s = 0; s < NSLOT; ++s) {
+    const int col = tid + WD_THREADS * s;
+    if (col < p1) Rt[ntri + col] = csq[s];
+  }
+}
+
+// ------------------------------------------------------------------ pairwise merge of parts (one tree level)
+// CTA b folds part (2b + 1) * stride into part 2b * stride (packed triangles + norms), if it exists.
+template <int TR, int NSLOT>
+__global__ void __launch_bounds__(WD_THREADS, 1)
+wide_merge_pairs_kernel(double* __restrict__ parts, int nparts, int stride, int p1) {
+  extern __shared__ __align__(16) unsigned char wd_smem[];
+  double* xs = reinterpret_cast<double*>(wd_smem);
+  const int tid = threadIdx.x;
+  const int a = 2 * blockIdx.x * stride, b = a + stride;
+  if (b >= nparts) return;
+  const int ntri = p1 * (p1 + 1) / 2;
+  double* pa = parts + (size_t)a * part_doubles(p1);
+  const double* pb = parts + (size_t)b * part_doubles(p1);
+  for (int r0 = 0; r0 < p1; r0 += TR) {
+    double B[TR][NSLOT];
+#pragma unroll
+    for (int r = 0; r < TR; ++r) {
+      const int row = r0 + r;
+#pragma unroll
+      for (int s = 0; s < NSLOT; ++s) {
+        const int col = tid + WD_THREADS * s;
+        B[r][s] = (row < p1 && col >= row && col < p1) ? __ldcg(pb + tri_off(row, p1) + col - row) : 0.0;
+      }
+    }
+    wide_fold<TR, NSLOT>(B, pa, p1, r0, xs, tid);
+  }
+  for (int i = tid; i < p1; i += blockDim.x) pa[ntri + i] += pb[ntri + i];
+}
+
+}  // namespace fg

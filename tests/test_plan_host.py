@@ -187,7 +187,7 @@ def test_ur10_chain_program_matches_oracle():
     assert d["walk"] == [1, 2, 3, 4, 5, 6] and d["nvslots"] == 0 and d["nmslots"] == 0
     w = [g["w"] for g in d["groups"]]
     assert w[2:] == [45, 35, 25, 15] and w[0] in (54, 55) and w[1] in (53, 54)  # 1e-17 leaks of the pi/2 roundings
-    assert sum(g["ninst"] for g in d["groups"]) == 148 * (d["nw"] - d["npc"])
+    assert sum(g["ninst"] for g in d["groups"]) == (148 - d["producer_ctas"]) * d["nw"]
 
 
 def test_tx40_coupling_program_matches_oracle():

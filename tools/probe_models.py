@@ -72,7 +72,7 @@ def main():
                       "samples_per_s": N / ms * 1e3, "qr_flops_per_sample": flops,
                       "tflops_dense_formula": flops * N / ms / 1e9, "frac_of_37.19": flops * N / ms / 1e9 / 37.19,
                       "eliminated": len(sol.idx_e), "base": len(sol.idx_base),
-                      "describe": {k: v for k, v in eng.describe_plan(fm, cfg_run).items() if k in ("ring_kernel", "why", "nw", "npc", "smem")}}))
+                      "describe": {k: v for k, v in eng.describe_plan(fm, cfg_run).items() if k in ("ring_kernel", "why", "nw", "producer_ctas", "smem")}}))
 
 
 if __name__ == "__main__":
