@@ -725,7 +725,7 @@ extern "C" int fg_state_accumulate_dense(fg_state* s, const double* W, int64_t l
     if (rc) return rc;
     rc = timing_begin(s, st);
     if (rc) return rc;
-    cudaError_t e = wide_launch_dense(W, ldw, tau, rows, s->p1, s->d_parts, grid, st);
+    cudaError_t e = wide_launch_dense(W, ldw, tau, 1, rows, s->p1, s->d_parts, grid, st);
     rc = timing_end(s, st);
     if (rc) return rc;
     if (e != cudaSuccess) return set_err(FG_ERR_CUDA, "wide dense kernel failed: %s", cudaGetErrorString(e));
@@ -1048,11 +1048,23 @@ static int accumulate_samples_dev(fg_state* s, fg_model* m, const fg_regressor_c
       if (rc) return rc;
       rc = timing_begin(s, st);
       if (rc) return rc;
-      cudaError_t ce = wide_launch_samples(pl->P, pl->ptrs, q, v, a, tau, ld_tau, N, s->d_parts, grid, m->max_smem, st);
+      // forward kinematics of a chunk of samples live in a scratch buffer (shared with the ring: never both in use)
+      const int64_t fw_chunk = std::min<int64_t>(N, 1 << 16);
+      const int64_t fw_need = fw_chunk * wide_fw_doubles_per_sample(pl->P);
+      if (fw_need > s->ring_cap) {
+        if (s->d_ring) cudaFree(s->d_ring);
+        s->d_ring = nullptr; s->ring_cap = 0;
+        FG_CUDA(cudaMalloc(&s->d_ring, sizeof(double) * fw_need));
+        s->ring_cap = fw_need;
+      }
+      s->ring_plan = nullptr;  // whatever tile layout the ring held is gone
+      int nl = 0;
+      cudaError_t ce = wide_launch_samples(pl->P, pl->ptrs, q, v, a, tau, ld_tau, N, s->d_parts, grid, m->max_smem,
+                                           s->d_ring, fw_chunk, &nl, st);
       rc = timing_end(s, st);
       if (rc) return rc;
       if (ce != cudaSuccess) return set_err(FG_ERR_CUDA, "wide fused kernel failed: %s", cudaGetErrorString(ce));
-      FG_LAUNCHED();
+      for (int i = 0; i < nl; ++i) FG_LAUNCHED();
       rc = merge_parts_into_state(s, grid, m->max_smem, st);
       if (rc) return rc;
       s->rows += N * ms;
@@ -1274,10 +1286,31 @@ extern "C" int fg_state_colsq(fg_state* s, double* out, void* stream) {
   return FG_OK;
 }
 
-static int run_small_qr(double* A, int mrows, int n, const int* d_ext, cudaStream_t st) {
+// packed upper triangle (n columns) -> dense n x n (ld = n), zeros below the diagonal
+__global__ void tri_to_square_kernel(const double* __restrict__ part, int n, double* __restrict__ A) {
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n * n; idx += gridDim.x * blockDim.x) {
+    const int r = idx / n, c = idx % n;
+    A[idx] = c >= r ? part[tri_off(r, n) + c - r] : 0.0;
+  }
+}
+
+// In-place QR of the (mrows x n, ld = n) matrix A on the device: the upper triangle of its first n rows becomes R.
+// Small matrices: one CTA in shared memory (small_qr_kernel).  Wide ones (n > 128): the rows are folded by the
+// CTA-wide register-tile kernel of fg_wide.cuh (one CTA; the last column rides as the rhs) into `scratch`
+// (part_doubles(n) doubles) and unpacked.  Only the first min(mrows, n) rows of the result are meaningful.
+static int run_small_qr(double* A, int mrows, int n, const int* d_ext, cudaStream_t st, double* scratch = nullptr) {
   int sm_count, max_smem;
   int rc = device_limits(&sm_count, &max_smem);
   if (rc) return rc;
+  if (n > 128 && scratch != nullptr && wide_dense_tile_rows(n) > 0) {
+    cudaError_t e = wide_launch_dense(A, n, A + (n - 1), n, mrows, n, scratch, 1, st);
+    if (e != cudaSuccess) return set_err(FG_ERR_CUDA, "small stage (wide) failed: %s", cudaGetErrorString(e));
+    FG_LAUNCHED();
+    tri_to_square_kernel<<<64, 256, 0, st>>>(scratch, n, A);
+    FG_CUDA(cudaGetLastError());
+    FG_LAUNCHED();
+    return FG_OK;
+  }
   int smem = (mrows * n + n) * 8 + n * 4, use_smem = 1;
   if (smem > max_smem) { smem = n * 8 + n * 4; use_smem = 0; }
   FG_CUDA(cudaFuncSetAttribute(small_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1306,7 +1339,9 @@ extern "C" int fg_state_reduce(fg_state* s, const int32_t* keep, int32_t nk, dou
   gather_cols_kernel<<<64, 256, 0, st>>>(s->d_part, p1, 1, s->d_idx, p1, n, s->d_A);
   FG_CUDA(cudaGetLastError());
   FG_LAUNCHED();
-  int rc = run_small_qr(s->d_A, p1, n, s->d_idx + n, st);
+  int rc = ensure_parts(s, 2);
+  if (rc) return rc;
+  rc = run_small_qr(s->d_A, p1, n, s->d_idx + n, st, s->d_parts);
   if (rc) return rc;
   // keep the leading n x n block as the reduced factor (dense, ld = n)
   FG_CUDA(cudaMemcpyAsync(s->d_Re, s->d_A, sizeof(double) * n * n, cudaMemcpyDeviceToDevice, st));
@@ -1445,7 +1480,9 @@ extern "C" int fg_state_regroup_solve(fg_state* s, const int32_t* base, int32_t 
   gather_cols_kernel<<<64, 256, 0, st>>>(s->d_Re, n, 0, s->d_idx, n, n, s->d_A);
   FG_CUDA(cudaGetLastError());
   FG_LAUNCHED();
-  int rc = run_small_qr(s->d_A, n, n, s->d_idx + n, st);
+  int rc = ensure_parts(s, 2);
+  if (rc) return rc;
+  rc = run_small_qr(s->d_A, n, n, s->d_idx + n, st, s->d_parts);
   if (rc) return rc;
   const int nrhs = ng + 1;
   if (nb <= 32 * US_M) upper_solve_kernel<<<(nrhs + 3) / 4, 128, 0, st>>>(s->d_A, n, nb, nrhs, s->d_X);

@@ -118,7 +118,12 @@ __device__ inline void forward_sample(const Plan& P, const DevJoint* J, const do
   for (int k = 0; k < FW_STRIDE; ++k) fw[k] = 0.0;
   fw[FW_R + 0] = fw[FW_R + 4] = fw[FW_R + 8] = 1.0;
   fw[FW_A + 0] = -P.gravity[0]; fw[FW_A + 1] = -P.gravity[1]; fw[FW_A + 2] = -P.gravity[2];
-  for (int k = 0; k < P.nv; ++k) { vs[k] = valid ? qd[k] : 0.0; as[k] = valid ? qdd[k] : 0.0; }
+  if (vs != nullptr) {
+    for (int k = 0; k < P.nv; ++k) { vs[k] = valid ? qd[k] : 0.0; as[k] = valid ? qdd[k] : 0.0; }
+  } else {  // no shared-memory copy of (dq, ddq): read them where they are
+    vs = const_cast<double*>(qd);
+    as = const_cast<double*>(qdd);
+  }
   for (int i = 1; i < P.nj; ++i) {
     const DevJoint& jt = J[i];
     double Rj[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, pj[3] = {0, 0, 0};
@@ -267,8 +272,8 @@ __device__ __forceinline__ void gen_column(const Plan& P, const DevJoint* J, con
   } else if (cd.kind == COL_EXTRA) {
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-      const double vv = vs[s * P.nv + cd.vidx], aa = as[s * P.nv + cd.vidx];
       const bool valid = sample0 + s < N;
+      const double vv = valid ? vs[s * P.nv + cd.vidx] : 0.0, aa = valid ? as[s * P.nv + cd.vidx] : 0.0;
       double val = cd.k == SRC_QDD ? aa : (cd.k == SRC_QD ? vv : (cd.k == SRC_SIGN_QD ? sgn(vv) : 1.0));
       if (!valid) val = 0.0;
 #pragma unroll
@@ -279,8 +284,9 @@ __device__ __forceinline__ void gen_column(const Plan& P, const DevJoint* J, con
     // add_coupling_TX40 (regressor.py:216-225): row block 4 <- [a5, v5, sign(v4+v5)], row block 5 <- [a4, v4, sign(v4+v5)]
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-      const double v4 = vs[s * P.nv + 4], v5 = vs[s * P.nv + 5], a4 = as[s * P.nv + 4], a5 = as[s * P.nv + 5];
       const bool valid = sample0 + s < N;
+      const int so = valid ? s * P.nv : 0;
+      const double v4 = vs[so + 4], v5 = vs[so + 5], a4 = as[so + 4], a5 = as[so + 5];
       const double sg = sgn(v4 + v5);
 #pragma unroll
       for (int g = 0; g < MSMAX; ++g) {

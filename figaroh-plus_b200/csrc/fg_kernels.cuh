@@ -456,8 +456,8 @@ __global__ void __launch_bounds__(1024) small_qr_kernel(double* __restrict__ Ag,
     for (int i = threadIdx.x; i < m * n; i += blockDim.x) Ag[i] = A[i];
 }
 
-// Back substitution of one right-hand side by one warp (r <= 128), see upper_solve_kernel below.
-constexpr int US_M = 4;
+// Back substitution of one right-hand side by one warp (r <= 32 US_M = 256), see upper_solve_kernel below.
+constexpr int US_M = 8;
 __device__ __forceinline__ void upper_solve_warp(const double* Rg, int ldr, int r, int j, int nrhs, double* X, int lane) {
   double b[US_M], rc[US_M];
 #pragma unroll
@@ -474,8 +474,10 @@ __device__ __forceinline__ void upper_solve_warp(const double* Rg, int ldr, int 
       rn[m] = (i > 0 && k < i) ? Rg[(size_t)k * ldr + (i - 1)] : 0.0;
     }
     const int s = i >> 5;
-    const double bs = s == 0 ? b[0] : (s == 1 ? b[1] : (s == 2 ? b[2] : b[3]));
-    const double rs = s == 0 ? rc[0] : (s == 1 ? rc[1] : (s == 2 ? rc[2] : rc[3]));
+    double bs = b[0], rs = rc[0];
+#pragma unroll
+    for (int m = 1; m < US_M; ++m)
+      if (s == m) { bs = b[m]; rs = rc[m]; }
     const double xi = __shfl_sync(0xffffffffu, bs, i & 31) / __shfl_sync(0xffffffffu, rs, i & 31);
     if (lane == 0) X[(size_t)i * nrhs + j] = xi;
 #pragma unroll

@@ -14,52 +14,12 @@
 #define FG_GQ_DEVICE_ONLY
 #include "fg_groupqr.cuh"
 #include "fg_rq.h"
+#include "fg_async.cuh"
 
 namespace fg {
 
 constexpr unsigned RQ_SPIN_LIMIT = 1u << 22;  // bounded waits: ~1 s, then the error flag is raised
 constexpr int RQ_ERR_CONSUMER = 1, RQ_ERR_PRODUCER = 2, RQ_ERR_MBAR = 3;
-
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers: mbarrier, bulk copy (TMA engine, SASS UBLKCP), acquire / release flags
-__device__ __forceinline__ uint32_t rq_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void rq_mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rq_smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void rq_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rq_smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool rq_mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      " .reg .pred p;\n"
-      " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      " selp.u32 %0, 1, 0, p;\n"
-      "}"
-      : "=r"(ok)
-      : "r"(rq_smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void rq_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   rq_smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(rq_smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void rq_fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
-// shared-memory only: orders this thread's generic-proxy accesses to the tile before a bulk copy into it, without
-// waiting for the thread's outstanding global stores (the R blocks)
-__device__ __forceinline__ void rq_fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ unsigned rq_ld_acquire(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void rq_st_release(unsigned* p, unsigned v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 
 // lane 0 waits until *flag >= want (monotonic counters); false = gave up (error flag raised by the caller)
 __device__ __forceinline__ bool rq_spin_ge(const unsigned* flag, unsigned want, const unsigned* err) {
@@ -114,12 +74,16 @@ __device__ __forceinline__ void rq_emit(double* gslot, int ed, const double* sl,
   val[7] = sa[0] * al[2] + sa[2] * al[0] + h[0] * om[2] + h[2] * om[0];   // Ixz
   val[8] = sa[1] * al[2] + sa[2] * al[1] + h[1] * om[2] + h[2] * om[1];   // Iyz
   val[9] = sa[2] * al[2] + h[2] * om[2];                                   // Izz
+  // column `slot` of the tile starts at slot * 32 doubles ((slot >> 3) * GQ_BLK + (slot & 7) * 32); the row
+  // swizzle tq_sw(c) of column c = slot & 7 takes the values 0, 5, 8, 13, 5, 8, 13, 0
   int slot = ed >> 10;
+  double* dst = gslot + slot * 32;
 #pragma unroll
   for (int k = 0; k < 10; ++k) {
     if ((ed >> k) & 1) {  // uniform
-      gslot[(slot >> 3) * GQ_BLK + tq_idx(slot & 7, lane)] = valid ? val[k] : 0.0;
+      dst[lane ^ tq_sw(slot & 7)] = valid ? val[k] : 0.0;
       ++slot;
+      dst += 32;
     }
   }
 }
@@ -254,7 +218,7 @@ static __device__ __forceinline__ void rq_produce_tile(const RqParams& P, const 
     double* gs = slot + P.goff[g];
     for (int t = 0; t < G.nsimple; ++t) {
       const GqSimple s1 = S.simple[g][t];
-      const int ix = (s1.slot >> 3) * GQ_BLK + tq_idx(s1.slot & 7, lane);
+      const int ix = s1.slot * 32 + (lane ^ tq_sw(s1.slot & 7));
       double val = 0.0;
       if (s1.kind == COL_RHS) {
         if (valid && tau != nullptr) val = __ldg(tau + (int64_t)g * ld_tau + smp);
@@ -309,7 +273,9 @@ struct RqRefill {
 
 // ---------------------------------------------------------------------------------------------
 // ctl: ready[ring] | done[ring] | err
-__global__ void __launch_bounds__(GQ_MAXNW * 32, 1)
+// MAXNW: warps per CTA the kernel is compiled for (16: 128 registers per thread, 20: 96)
+template <int MAXNW>
+__global__ void __launch_bounds__(MAXNW * 32, 1)
 rq_accumulate_kernel(const __grid_constant__ RqParams P, const unsigned char* __restrict__ tab_g,
                      const unsigned short* __restrict__ tab_i, const double* __restrict__ q,
                      const double* __restrict__ qd, const double* __restrict__ qdd, const double* __restrict__ tau,

@@ -231,7 +231,8 @@ RqLaunch rq_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, co
   npcta = std::max(1, std::min(npcta, rl.sm_count - 1));
   if (rl.sm_count < 2) { rq_fail(why, "needs at least two SMs"); return rl; }
   const int ncta = rl.sm_count - npcta;
-  for (int nw = GQ_MAXNW; nw >= 1; --nw) {
+  const int nw_cap = std::max(1, std::min(env_int("FG_RQ_NW", 16), 20));
+  for (int nw = nw_cap; nw >= 1; --nw) {
     if (R.prod_smem_doubles * nw * 8 + gen_doubles * 8 > max_smem) continue;
     const int W = ncta * nw;
     if (W < ms) continue;
@@ -313,7 +314,8 @@ RqLaunch rq_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, co
 cudaError_t rq_launch(const RqLaunch& rl, const RqParams& prm, const double* q, const double* v, const double* a,
                       const double* tau, int64_t ld_tau, int64_t N, double* r_all, double* ring, unsigned* ring_ctl,
                       int first, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(rq_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rl.smem);
+  const void* kern = rl.nw > 16 ? (const void*)rq_accumulate_kernel<20> : (const void*)rq_accumulate_kernel<16>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, rl.smem);
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(ring_ctl, 0, sizeof(unsigned) * (2 * (size_t)prm.ring), st);  // ready / done; the error word stays until it is reported
   if (e != cudaSuccess) return e;
@@ -322,8 +324,7 @@ cudaError_t rq_launch(const RqLaunch& rl, const RqParams& prm, const double* q, 
   void* args[] = {(void*)&prm, (void*)&tg, (void*)&ti, (void*)&q, (void*)&v, (void*)&a, (void*)&tau,
                   (void*)&ld_tau, (void*)&N, (void*)&r_all, (void*)&ring, (void*)&ring_ctl, (void*)&first};
   // every CTA must be resident (producers and consumers wait for each other): cooperative launch
-  return cudaLaunchCooperativeKernel((const void*)rq_accumulate_kernel, dim3(rl.sm_count), dim3(rl.nw * 32), args,
-                                     (size_t)rl.smem, st);
+  return cudaLaunchCooperativeKernel(kern, dim3(rl.sm_count), dim3(rl.nw * 32), args, (size_t)rl.smem, st);
 }
 
 }  // namespace fg

@@ -8,16 +8,16 @@
 namespace fg {
 
 template <int MSMAX, int S, int NSLOT>
-static cudaError_t launch_samples(const Plan& P, const DevPlanPtrs& pp, const double* q, const double* v,
-                                  const double* a, const double* tau, int64_t ld_tau, int64_t N, double* parts,
-                                  int grid, int max_smem, cudaStream_t st) {
+static cudaError_t launch_samples(const Plan& P, const DevPlanPtrs& pp, const double* v, const double* a,
+                                  const double* tau, int64_t ld_tau, int64_t n, const double* fw, double* parts,
+                                  int grid, int max_smem, int first, cudaStream_t st) {
   constexpr int TR = MSMAX * S;
-  const WideLayout L = wide_layout(P.nj, P.ms, P.nv, S, TR);
+  const WideLayout L = wide_layout(P.nj, P.ms, S, TR);
   if (L.total > max_smem) return cudaErrorInvalidConfiguration;
-  auto kern = wide_accumulate_samples_kernel<MSMAX, S, NSLOT, 1>;
+  auto kern = wide_accumulate_samples_kernel<MSMAX, S, NSLOT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
   if (e != cudaSuccess) return e;
-  kern<<<grid, WD_THREADS + 32, L.total, st>>>(pp, q, v, a, tau, ld_tau, N, parts);
+  kern<<<grid, WD_THREADS, L.total, st>>>(pp, v, a, tau, ld_tau, n, fw, parts, first, 0);
   return cudaGetLastError();
 }
 
@@ -29,35 +29,51 @@ int wide_samples_per_tile(int ms, int p1) {
   return ms <= 6 ? 4 : (ms <= 8 ? 3 : (ms <= 24 ? 1 : 0));
 }
 
+int64_t wide_fw_doubles_per_sample(const Plan& P) { return (int64_t)P.nj * FW_STRIDE; }
+
 cudaError_t wide_launch_samples(const Plan& P, const DevPlanPtrs& pp, const double* q, const double* v, const double* a,
                                 const double* tau, int64_t ld_tau, int64_t N, double* parts, int grid, int max_smem,
-                                cudaStream_t st) {
+                                double* fw_buf, int64_t fw_chunk, int* launches, cudaStream_t st) {
   const int nslot = (P.p1 + WD_THREADS - 1) / WD_THREADS, ms = P.ms;
-#define FG_WD(MS_, S_, NS_) return launch_samples<MS_, S_, NS_>(P, pp, q, v, a, tau, ld_tau, N, parts, grid, max_smem, st)
-  if (nslot == 1) {
-    if (ms <= 6) FG_WD(6, 8, 1);
-    if (ms <= 8) FG_WD(8, 6, 1);
-    if (ms <= 24) FG_WD(24, 2, 1);
-    if (ms <= 48) FG_WD(48, 1, 1);
-  } else if (nslot == 2) {
-    if (ms <= 6) FG_WD(6, 6, 2);
-    if (ms <= 8) FG_WD(8, 4, 2);
-    if (ms <= 24) FG_WD(24, 1, 2);
-    if (ms <= 48) FG_WD(48, 1, 2);
-  } else if (nslot == 3) {
-    if (ms <= 6) FG_WD(6, 4, 3);
-    if (ms <= 8) FG_WD(8, 3, 3);
-    if (ms <= 24) FG_WD(24, 1, 3);
-  }
+  const int fw_smem = align16((int)sizeof(Plan)) + P.nj * (int)sizeof(DevJoint);
+  for (int64_t c0 = 0; c0 < N; c0 += fw_chunk) {
+    const int64_t n = std::min(fw_chunk, N - c0);
+    wide_forward_kernel<<<(unsigned)((n + 127) / 128), 128, fw_smem, st>>>(pp, q + c0 * P.nq, v + c0 * P.nv, a + c0 * P.nv, n, fw_buf);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const double* vc = v + c0 * P.nv;
+    const double* ac = a + c0 * P.nv;
+    const double* tc = tau ? tau + c0 : nullptr;
+    const int first = c0 == 0 ? 1 : 0;
+    e = cudaErrorInvalidConfiguration;
+#define FG_WD(MS_, S_, NS_) e = launch_samples<MS_, S_, NS_>(P, pp, vc, ac, tc, ld_tau, n, fw_buf, parts, grid, max_smem, first, st)
+    if (nslot == 1) {
+      if (ms <= 6) FG_WD(6, 8, 1);
+      else if (ms <= 8) FG_WD(8, 6, 1);
+      else if (ms <= 24) FG_WD(24, 2, 1);
+      else if (ms <= 48) FG_WD(48, 1, 1);
+    } else if (nslot == 2) {
+      if (ms <= 6) FG_WD(6, 6, 2);
+      else if (ms <= 8) FG_WD(8, 4, 2);
+      else if (ms <= 24) FG_WD(24, 1, 2);
+      else if (ms <= 48) FG_WD(48, 1, 2);
+    } else if (nslot == 3) {
+      if (ms <= 6) FG_WD(6, 4, 3);
+      else if (ms <= 8) FG_WD(8, 3, 3);
+      else if (ms <= 24) FG_WD(24, 1, 3);
+    }
 #undef FG_WD
-  return cudaErrorInvalidConfiguration;
+    if (e != cudaSuccess) return e;
+    if (launches) *launches += 2;
+  }
+  return cudaSuccess;
 }
 
 template <int TR, int NSLOT>
-static cudaError_t launch_dense_t(const double* W, int64_t ldw, const double* tau, int64_t rows, int p1, double* parts,
-                                  int grid, cudaStream_t st) {
+static cudaError_t launch_dense_t(const double* W, int64_t ldw, const double* tau, int64_t tau_stride, int64_t rows,
+                                  int p1, double* parts, int grid, cudaStream_t st) {
   const int smem = 2 * (((TR + 7) / 8) * 8 + 4) * 8;
-  wide_accumulate_dense_kernel<TR, NSLOT, 1><<<grid, WD_THREADS, smem, st>>>(W, ldw, tau, rows, p1, parts);
+  wide_accumulate_dense_kernel<TR, NSLOT, 1><<<grid, WD_THREADS, smem, st>>>(W, ldw, tau, tau_stride, rows, p1, parts);
   return cudaGetLastError();
 }
 
@@ -66,12 +82,12 @@ int wide_dense_tile_rows(int p1) {
   return nslot == 1 ? 64 : (nslot == 2 ? 40 : (nslot == 3 ? 24 : 0));
 }
 
-cudaError_t wide_launch_dense(const double* W, int64_t ldw, const double* tau, int64_t rows, int p1, double* parts,
-                              int grid, cudaStream_t st) {
+cudaError_t wide_launch_dense(const double* W, int64_t ldw, const double* tau, int64_t tau_stride, int64_t rows, int p1,
+                              double* parts, int grid, cudaStream_t st) {
   const int nslot = (p1 + WD_THREADS - 1) / WD_THREADS;
-  if (nslot == 1) return launch_dense_t<64, 1>(W, ldw, tau, rows, p1, parts, grid, st);
-  if (nslot == 2) return launch_dense_t<40, 2>(W, ldw, tau, rows, p1, parts, grid, st);
-  if (nslot == 3) return launch_dense_t<24, 3>(W, ldw, tau, rows, p1, parts, grid, st);
+  if (nslot == 1) return launch_dense_t<64, 1>(W, ldw, tau, tau_stride, rows, p1, parts, grid, st);
+  if (nslot == 2) return launch_dense_t<40, 2>(W, ldw, tau, tau_stride, rows, p1, parts, grid, st);
+  if (nslot == 3) return launch_dense_t<24, 3>(W, ldw, tau, tau_stride, rows, p1, parts, grid, st);
   return cudaErrorInvalidConfiguration;
 }
 

@@ -12,10 +12,12 @@
 //   * the CTA's triangular factor lives in an L2-resident global scratch (its part slot): row c is read and
 //     written exactly once per tile, requested one step ahead;
 //   * the regressor entries of a tile are generated column by column (gen_column, fg_device.cuh: body column
-//     in the body frame, carried up the tree to the row group's joint) from per-sample forward kinematics that
-//     a ninth warp computes for the NEXT tile while the other eight fold the current one.
+//     in the body frame, carried up the tree to the row group's joint) from per-sample forward kinematics that a
+//     thread-per-sample pre-kernel leaves in a global buffer (a chunk of samples at a time); the states of the
+//     NEXT tile arrive in shared memory by one bulk copy (TMA engine, mbarrier) while the current tile is folded.
 #pragma once
 #include "fg_device.cuh"
+#include "fg_async.cuh"
 
 namespace fg {
 
@@ -139,58 +141,82 @@ __device__ __forceinline__ void wide_fold(double (&B)[TR][NSLOT], double* __rest
   wd_bar();  // the last step's reads of xs are done before the next tile's first owner writes
 }
 
+// ------------------------------------------------------------------ forward kinematics of a chunk of samples
+// One thread per sample: the per-joint forward state [nj][FW_STRIDE] (placement in the parent frame, spatial
+// velocity, spatial and classical acceleration - pinocchio's JointTorqueRegressorForwardStep) goes to a global
+// buffer, sample-major, so the states of the consecutive samples of a tile are ONE contiguous run that the fold
+// kernel pulls into shared memory with a single bulk copy.
+__global__ void __launch_bounds__(128)
+wide_forward_kernel(DevPlanPtrs pp, const double* __restrict__ q, const double* __restrict__ qd,
+                    const double* __restrict__ qdd, int64_t n, double* __restrict__ fw_out) {
+  extern __shared__ __align__(16) unsigned char wd_smem[];
+  const Plan P0 = *pp.plan;
+  Plan* Ps = reinterpret_cast<Plan*>(wd_smem);
+  double* J = reinterpret_cast<double*>(wd_smem + align16((int)sizeof(Plan)));
+  if (threadIdx.x == 0) *Ps = P0;
+  for (int i = threadIdx.x; i < P0.nj * (int)(sizeof(DevJoint) / 8); i += blockDim.x) J[i] = reinterpret_cast<const double*>(pp.joints)[i];
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  forward_sample(*Ps, reinterpret_cast<const DevJoint*>(J), q + i * P0.nq, qd + i * P0.nv, qdd + i * P0.nv,
+                 fw_out + (size_t)i * P0.nj * FW_STRIDE, nullptr, nullptr, true);
+}
+
 // ------------------------------------------------------------------ fused: samples -> factor
-// grid: persistent; CTA b folds tiles b, b + gridDim.x, ... into its own part slot parts[b].
-// blockDim = 288: warps 0..7 own columns, warp 8 runs the forward kinematics of the next tile.
-// shared memory: plan tables | 2 x (fw [S][nj][27] | vs [S][nv] | as [S][nv]) | xs
+// grid: persistent; CTA b folds tiles b, b + gridDim.x, ... of the chunk into its own part slot parts[b] (the
+// factor stays there between the chunks of one call: `first` zeroes it).  256 threads = column owners.
+// shared memory: plan tables | 2 x fw tile [S][nj][27] (bulk-copied, double-buffered) | xs | 2 mbarriers
 struct WideLayout {
-  int off_plan, off_joints, off_rows, off_fw[2], off_vs[2], off_as[2], off_xs, total;
+  int off_plan, off_joints, off_rows, off_fw[2], off_xs, off_bar, total;
 };
-__host__ __device__ inline WideLayout wide_layout(int nj, int ms, int nv, int S, int TR) {
+__host__ __device__ inline WideLayout wide_layout(int nj, int ms, int S, int TR) {
   WideLayout L;
   int o = 0;
   L.off_plan = o;   o = align16(o + (int)sizeof(Plan));
   L.off_joints = o; o = align16(o + nj * (int)sizeof(DevJoint));
   L.off_rows = o;   o = align16(o + ms * (int)sizeof(RowDesc));
-  for (int b = 0; b < 2; ++b) {
-    L.off_fw[b] = o; o = align16(o + S * nj * FW_STRIDE * 8);
-    L.off_vs[b] = o; o = align16(o + S * nv * 8);
-    L.off_as[b] = o; o = align16(o + S * nv * 8);
-  }
+  for (int b = 0; b < 2; ++b) { L.off_fw[b] = o; o = align16(o + S * nj * FW_STRIDE * 8); }
   L.off_xs = o; o = align16(o + 2 * (((TR + 7) / 8) * 8 + 4) * 8);
+  L.off_bar = o; o = align16(o + 16);
   L.total = o;
   return L;
 }
 
-// (__launch_bounds__(288) makes ptxas budget for 384 threads = 168 registers; nine warps fit with 224.)
-template <int MSMAX, int S, int NSLOT, int MINB>
-__global__ void __maxnreg__(224)
-wide_accumulate_samples_kernel(DevPlanPtrs pp, const double* __restrict__ q, const double* __restrict__ qd,
-                               const double* __restrict__ qdd, const double* __restrict__ tau, int64_t ld_tau,
-                               int64_t N, double* __restrict__ parts) {
+template <int MSMAX, int S, int NSLOT>
+__global__ void __launch_bounds__(WD_THREADS, 1)
+wide_accumulate_samples_kernel(DevPlanPtrs pp, const double* __restrict__ qd, const double* __restrict__ qdd,
+                               const double* __restrict__ tau, int64_t ld_tau, int64_t n,
+                               const double* __restrict__ fw_all, double* __restrict__ parts, int first, int last) {
   constexpr int TR = MSMAX * S;
   extern __shared__ __align__(16) unsigned char wd_smem[];
   const Plan P0 = *pp.plan;
-  const WideLayout L = wide_layout(P0.nj, P0.ms, P0.nv, S, TR);
+  const WideLayout L = wide_layout(P0.nj, P0.ms, S, TR);
   const int tid = threadIdx.x;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wd_smem + L.off_bar);
   {
-    if (tid == 0) *reinterpret_cast<Plan*>(wd_smem + L.off_plan) = P0;
+    if (tid == 0) {
+      *reinterpret_cast<Plan*>(wd_smem + L.off_plan) = P0;
+      rq_mbar_init(bars, 1);
+      rq_mbar_init(bars + 1, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      rq_fence_proxy_async();
+    }
     double* J = reinterpret_cast<double*>(wd_smem + L.off_joints);
     for (int i = tid; i < P0.nj * (int)(sizeof(DevJoint) / 8); i += blockDim.x) J[i] = reinterpret_cast<const double*>(pp.joints)[i];
     double* Rw = reinterpret_cast<double*>(wd_smem + L.off_rows);
     for (int i = tid; i < P0.ms * (int)(sizeof(RowDesc) / 8); i += blockDim.x) Rw[i] = reinterpret_cast<const double*>(pp.rows)[i];
   }
+  const int p1 = P0.p1, ntri = p1 * (p1 + 1) / 2;
+  double* Rt = parts + (size_t)blockIdx.x * part_doubles(p1);
+  if (first)
+    for (int i = tid; i < ntri + p1; i += blockDim.x) Rt[i] = 0.0;
   __syncthreads();
   const Plan& P = *reinterpret_cast<const Plan*>(wd_smem + L.off_plan);
   const DevJoint* J = reinterpret_cast<const DevJoint*>(wd_smem + L.off_joints);
   const RowDesc* rows = reinterpret_cast<const RowDesc*>(wd_smem + L.off_rows);
   double* xs = reinterpret_cast<double*>(wd_smem + L.off_xs);
-  const int p1 = P.p1, ntri = p1 * (p1 + 1) / 2;
-  double* Rt = parts + (size_t)blockIdx.x * part_doubles(p1);
-  for (int i = tid; i < ntri; i += blockDim.x) Rt[i] = 0.0;
-  const bool kin = tid >= WD_THREADS;  // warp 8
-  const int lane = tid & 31;
-  const int64_t ntiles = (N + S - 1) / S;
+  const int64_t ntiles = (n + S - 1) / S;
+  const int fw_sample = P.nj * FW_STRIDE;  // doubles per sample
 
   ColDesc cd[NSLOT];
   uint64_t anc[NSLOT];
@@ -201,62 +227,56 @@ wide_accumulate_samples_kernel(DevPlanPtrs pp, const double* __restrict__ q, con
     cd[s].kind = COL_ZERO; cd[s].body = 0; cd[s].k = 0; cd[s].vidx = 0; cd[s].grp = -2;
     anc[s] = 0;
     csq[s] = 0.0;
-    if (!kin && col < p1) {
+    if (col < p1) {
       cd[s] = pp.cols[col];
       anc[s] = col_ancmask(cd[s]);
     }
   }
-  auto forward_tile = [&](int64_t tile, int buf) {
-    if (lane < S) {
-      const int64_t smp = tile * S + lane;
-      const bool valid = smp < N;
-      const int64_t scl = valid ? smp : 0;
-      forward_sample(P, J, q + scl * P.nq, qd + scl * P.nv, qdd + scl * P.nv,
-                     reinterpret_cast<double*>(wd_smem + L.off_fw[buf]) + (size_t)lane * P.nj * FW_STRIDE,
-                     reinterpret_cast<double*>(wd_smem + L.off_vs[buf]) + lane * P.nv,
-                     reinterpret_cast<double*>(wd_smem + L.off_as[buf]) + lane * P.nv, valid);
-    }
+  auto request = [&](int64_t tile, int buf) {  // thread 0: forward states of the tile's samples -> shared memory
+    const int64_t s0 = tile * S;
+    const int ns = (int)((n - s0) < S ? (n - s0) : S);
+    const uint32_t bytes = (uint32_t)ns * fw_sample * 8;
+    rq_mbar_expect_tx(bars + buf, bytes);
+    rq_bulk_g2s(wd_smem + L.off_fw[buf], fw_all + (size_t)s0 * fw_sample, bytes, bars + buf);
   };
   int64_t tile = blockIdx.x;
-  if (kin && tile < ntiles) forward_tile(tile, 0);
-  __syncthreads();
+  if (tid == 0 && tile < ntiles) request(tile, 0);
   int buf = 0;
+  uint32_t par[2] = {0u, 0u};
   for (; tile < ntiles; tile += gridDim.x, buf ^= 1) {
-    if (kin) {
-      if (tile + gridDim.x < ntiles) forward_tile(tile + gridDim.x, buf ^ 1);
-    } else {
-      const double* fw = reinterpret_cast<const double*>(wd_smem + L.off_fw[buf]);
-      const double* vs = reinterpret_cast<const double*>(wd_smem + L.off_vs[buf]);
-      const double* as = reinterpret_cast<const double*>(wd_smem + L.off_as[buf]);
-      double B[TR][NSLOT];
-#pragma unroll
-      for (int s = 0; s < NSLOT; ++s) {
-        double out[TR];
-        gen_column<MSMAX, S>(P, J, rows, cd[s], anc[s], fw, vs, as, tau, ld_tau, tile * S, N, out);
-#pragma unroll
-        for (int r = 0; r < TR; ++r) {
-          B[r][s] = out[r];
-          csq[s] = fma(out[r], out[r], csq[s]);
-        }
-      }
-      wide_fold<TR, NSLOT>(B, Rt, p1, 0, xs, tid);
-    }
-    __syncthreads();
-  }
-  if (!kin) {
+    // every thread finished reading the other buffer (generation of the previous tile) before the last barrier of
+    // its fold: it can be refilled now
+    if (tid == 0 && tile + gridDim.x < ntiles) request(tile + gridDim.x, buf ^ 1);
+    while (!rq_mbar_try_wait(bars + buf, par[buf])) {}
+    par[buf] ^= 1u;
+    const double* fw = reinterpret_cast<const double*>(wd_smem + L.off_fw[buf]);
+    const int64_t s0 = tile * S;
+    double B[TR][NSLOT];
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) {
-      const int col = tid + WD_THREADS * s;
-      if (col < p1) Rt[ntri + col] = csq[s];
+      double out[TR];
+      gen_column<MSMAX, S>(P, J, rows, cd[s], anc[s], fw, qd + s0 * P.nv, qdd + s0 * P.nv, tau, ld_tau, s0, n, out);
+#pragma unroll
+      for (int r = 0; r < TR; ++r) {
+        B[r][s] = out[r];
+        csq[s] = fma(out[r], out[r], csq[s]);
+      }
     }
+    wide_fold<TR, NSLOT>(B, Rt, p1, 0, xs, tid);
   }
+#pragma unroll
+  for (int s = 0; s < NSLOT; ++s) {
+    const int col = tid + WD_THREADS * s;
+    if (col < p1) Rt[ntri + col] += csq[s];
+  }
+  (void)last;
 }
 
 // ------------------------------------------------------------------ dense: rows x p matrix in HBM -> factor
 template <int TR, int NSLOT, int MINB>
 __global__ void __launch_bounds__(WD_THREADS, MINB)
-wide_accumulate_dense_kernel(const double* __restrict__ W, int64_t ldw, const double* __restrict__ tau, int64_t nrows,
-                             int p1, double* __restrict__ parts) {
+wide_accumulate_dense_kernel(const double* __restrict__ W, int64_t ldw, const double* __restrict__ tau,
+                             int64_t tau_stride, int64_t nrows, int p1, double* __restrict__ parts) {
   extern __shared__ __align__(16) unsigned char wd_smem[];
   double* xs = reinterpret_cast<double*>(wd_smem);
   const int tid = threadIdx.x;
@@ -280,7 +300,7 @@ wide_accumulate_dense_kernel(const double* __restrict__ W, int64_t ldw, const do
         double val = 0.0;
         if (row < nrows) {
           if (col < p) val = __ldcs(W + row * ldw + col);
-          else if (col == p && tau != nullptr) val = __ldcs(tau + row);
+          else if (col == p && tau != nullptr) val = __ldcs(tau + row * tau_stride);
         }
         B[r][s] = val;
         csq[s] = fma(val, val, csq[s]);
