@@ -25,18 +25,40 @@ for p in (ROOT, os.path.join(ROOT, "figaroh-plus_b200")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-MODEL_JSON = os.path.join(ROOT, "tests", "golden", "models", "ur10.json")
-PARAM = dict(is_joint_torques=True, is_external_wrench=False, force_torque=None,
-             has_friction=True, has_actuator_inertia=True, has_joint_offset=True,
-             # UR10's yaml has None here; SURVEY 8(d): take the TX40 values
-             fv=[8.05e0, 5.53e0, 1.97e0, 1.11e0, 1.86e0, 6.5e-1], fs=[7.14e0, 8.26e0, 6.34e0, 2.48e0, 3.03e0, 2.82e-1],
+MODELS = os.path.join(ROOT, "tests", "golden", "models")
+METRIC = "samples/sec for regressor build+TSQR+OLS solve"
+_TX40 = dict(fv=[8.05e0, 5.53e0, 1.97e0, 1.11e0, 1.86e0, 6.5e-1], fs=[7.14e0, 8.26e0, 6.34e0, 2.48e0, 3.03e0, 2.82e-1],
              Ia=[3.62e-1, 3.62e-1, 9.88e-2, 3.13e-2, 4.68e-2, 1.05e-2],
              off=[3.92e-1, 1.37, 3.26e-1, -1.02e-1, -2.88e-2, 1.27e-1])
-METRIC = "samples/sec for regressor build+TSQR+OLS solve"
-# algorithmic flops per sample: F_reg + 2*m_s*(p_e+1)^2, UR10 flags on: p_e = 73
-F_REG = 170 * 6 + 120 * 6 + 420 * 21
-F_QR = 2 * 6 * (73 + 1) ** 2
-FLOPS_PER_SAMPLE = F_REG + F_QR
+
+
+def _cyc(vals, n):
+    return [vals[i % len(vals)] for i in range(n)]
+
+
+# The three robots of BASELINE.json configs[1..3].  `ranges`: (q, dq, ddq) half-widths of the uniform draws.
+WORKLOADS = {
+    "ur10": dict(
+        model="ur10", baseline_config="configs[1]",
+        title="UR10 6-DoF, friction+actuator inertia+joint offsets",
+        param=dict(is_joint_torques=True, is_external_wrench=False, force_torque=None, has_friction=True,
+                   has_actuator_inertia=True, has_joint_offset=True, **_TX40),  # UR10's yaml has None: SURVEY 8(d) takes TX40's
+        active=None, ranges=(6.0, 6.0, 6.0), tol_e=1e-6, default_samples=1_000_000, cpu_samples=100_000),
+    "tiago": dict(
+        model="tiago", baseline_config="configs[2]",
+        title="TIAGo torso+arm, 8 active joints of the 24-DoF tree (rows of the active joints only, "
+              "examples/tiago/identification.py:157-166), friction+actuator inertia+joint offsets",
+        param=dict(is_joint_torques=True, is_external_wrench=False, force_torque=None, has_friction=True,
+                   has_actuator_inertia=True, has_joint_offset=True, fv=_cyc(_TX40["fv"], 24), fs=_cyc(_TX40["fs"], 24),
+                   Ia=_cyc(_TX40["Ia"], 24), off=_cyc(_TX40["off"], 24)),
+        active=list(range(13, 21)), ranges=(1.5, 2.0, 4.0), tol_e=1e-3, default_samples=1_000_000, cpu_samples=4_000),
+    "talos": dict(
+        model="talos_ff", baseline_config="configs[3]",
+        title="Talos humanoid with free-flyer, external-wrench rows (force_torque=All, regressor.py:89-192)",
+        param=dict(is_joint_torques=False, is_external_wrench=True, force_torque=["All"], has_friction=False,
+                   has_actuator_inertia=False, has_joint_offset=False, fv=None, fs=None, Ia=None, off=None),
+        active=None, ranges=(1.0, 1.0, 2.0), tol_e=1e-6, default_samples=1_000_000, cpu_samples=4_000),
+}
 
 
 def fp64_peak_tflops():
@@ -51,28 +73,106 @@ def fp64_peak_tflops():
 _REAL_STDOUT = sys.stdout
 
 
-def ncu_traffic(n):
+def ncu_traffic(workload, n):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed ncu
-    capture of this command at the same sample count (profiles/ncu_traffic_r01.json); None if there is none."""
+    capture of this command at the same workload and sample count (profiles/ncu_traffic_r02.json); None if none."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")))
-        return d["dram_bytes_per_launch"] if int(d["samples"]) == int(n) else None
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r02.json")))
+        e = d.get(workload)
+        return e["dram_bytes_per_launch"] if e and int(e["samples"]) == int(n) else None
     except Exception:  # noqa: BLE001
         return None
 
 
-def standard_phi(fm):
-    """phi_std in FIGAROH column order from the flattened model (no oracle involved)."""
+def standard_phi(fm, param):
+    """phi_std in FIGAROH column order from the flattened model (robot.py:76-155 semantics; no oracle involved)."""
     pin2fig = [9, 6, 7, 8, 0, 1, 3, 2, 4, 5]
     dyn = fm.dynamic_parameters()
     phi, names = [], []
     inertial = ("Ixx", "Ixy", "Ixz", "Iyy", "Iyz", "Izz", "mx", "my", "mz", "m")
+
+    def pick(flag, key, i):
+        if not param[flag] or param.get(key) is None:
+            return 0.0
+        try:
+            return float(param[key][i - 1])
+        except Exception:  # noqa: BLE001
+            return 0.0
     for i in range(1, fm.njoints):
         blk = np.empty(10)
         blk[pin2fig] = dyn[i - 1]
-        phi += list(blk) + [PARAM["Ia"][i - 1], PARAM["fv"][i - 1], PARAM["fs"][i - 1], PARAM["off"][i - 1]]
+        phi += list(blk) + [pick("has_actuator_inertia", "Ia", i), pick("has_friction", "fv", i),
+                            pick("has_friction", "fs", i), pick("has_joint_offset", "off", i)]
         names += [n + str(i) for n in inertial] + [f"Ia{i}", f"fv{i}", f"fs{i}", f"off{i}"]
     return np.array(phi), names
+
+
+def active_rows(fm, wl):
+    return None if wl["active"] is None else [int(fm.idx_v[i]) for i in wl["active"]]
+
+
+def host_inputs(fm, wl, n, seed):
+    """Seeded synthetic (q, dq, ddq) on the host with the workload's structure (used for the CPU arm and the
+    parity subsample; the GPU arm draws on the device with the same structure)."""
+    rng = np.random.default_rng(seed)
+    rq, rv, ra = wl["ranges"]
+    q = rng.uniform(-rq, rq, (n, fm.nq))
+    v = rng.uniform(-rv, rv, (n, fm.nv))
+    a = rng.uniform(-ra, ra, (n, fm.nv))
+    act = None if wl["active"] is None else set(wl["active"])
+    for i in range(1, fm.njoints):
+        iq, iv, jt = int(fm.idx_q[i]), int(fm.idx_v[i]), int(fm.jtype[i])
+        if act is not None and i not in act:  # resting joint: fixed configuration, no motion
+            if jt == 2:
+                q[:, iq], q[:, iq + 1] = 1.0, 0.0
+            else:
+                q[:, iq] = 0.1
+            v[:, iv] = 0.0
+            a[:, iv] = 0.0
+        elif jt == 2:
+            th = rng.uniform(-np.pi, np.pi, n)
+            q[:, iq], q[:, iq + 1] = np.cos(th), np.sin(th)
+        elif jt == 4:
+            quat = rng.normal(size=(n, 4))
+            q[:, iq + 3:iq + 7] = quat / np.linalg.norm(quat, axis=1, keepdims=True)
+    return q, v, a
+
+
+def device_inputs(torch, fm, wl, n, seed, dev):
+    """Same structure, drawn on the device."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    rq, rv, ra = wl["ranges"]
+
+    def uni(cols, r):
+        return torch.rand((n, cols), generator=g, device=dev, dtype=torch.float64) * (2 * r) - r
+    q, v, a = uni(fm.nq, rq), uni(fm.nv, rv), uni(fm.nv, ra)
+    act = None if wl["active"] is None else set(wl["active"])
+    for i in range(1, fm.njoints):
+        iq, iv, jt = int(fm.idx_q[i]), int(fm.idx_v[i]), int(fm.jtype[i])
+        if act is not None and i not in act:
+            if jt == 2:
+                q[:, iq], q[:, iq + 1] = 1.0, 0.0
+            else:
+                q[:, iq] = 0.1
+            v[:, iv] = 0.0
+            a[:, iv] = 0.0
+        elif jt == 2:
+            th = (torch.rand(n, generator=g, device=dev, dtype=torch.float64) * 2 - 1) * np.pi
+            q[:, iq], q[:, iq + 1] = torch.cos(th), torch.sin(th)
+        elif jt == 4:
+            quat = torch.randn((n, 4), generator=g, device=dev, dtype=torch.float64)
+            q[:, iq + 3:iq + 7] = quat / quat.norm(dim=1, keepdim=True)
+    return q, v, a
+
+
+def flops_per_sample(plan, rps, n_keep):
+    """F = F_reg + 2 m_s (p_e + 1)^2 (Householder QR of an m_s-row slab against the p_e kept columns
+    + the rhs), F_reg = 170 walked joints + 120 bodies + 420 (row group, body) hops."""
+    nproc = len(plan["walk"]) if plan.get("ring_kernel") else plan.get("nbodies", 0)
+    hops = sum(len(g["emit"]) for g in plan["groups"]) if plan.get("ring_kernel") else plan.get("hops", 0)
+    f_reg = 170 * nproc + 120 * nproc + 420 * hops
+    return f_reg + 2 * rps * (n_keep + 1) ** 2, f_reg
 
 
 class ClockSampler:
@@ -163,39 +263,67 @@ class ClockSampler:
         return out
 
 
+def oracle_path(om, wl, fm, q, v, a, per_sample):
+    """The reference's script sequence on the CPU oracle (regressor.py:20-293, qrdecomposition.py:89-187)."""
+    from oracle import ref_path
+    param = wl["param"]
+    n = len(q)
+    std = ref_path.standard_parameters(om, param)
+    W = ref_path.build_regressor_basic(om, q, v, a, param, per_sample=per_sample)
+    rows = active_rows(fm, wl)
+    if rows is not None:  # examples/tiago/identification.py:157-166
+        W = np.concatenate([W[r * n:(r + 1) * n] for r in rows])
+    phi = np.array(list(std.values()), dtype=float)
+    rng = np.random.default_rng(1)
+    tau = W @ phi
+    tau = tau + 0.01 * np.sqrt(np.mean(tau ** 2)) * rng.normal(size=tau.shape)
+    idx_e, params_r = ref_path.get_index_eliminate(W, std, wl["tol_e"])
+    W_e = ref_path.build_regressor_reduced(W, idx_e)
+    out = ref_path.double_QR(tau, W_e, params_r, std)
+    return dict(std=std, tau=tau, idx_e=idx_e, params_r=params_r, W_e=W_e, out=out)
+
+
+def cpu_arm(wl, n):
+    """One timed pass of the CPU port on n samples of the workload; returns (seconds, description)."""
+    from oracle import kernels
+    mpath = os.path.join(MODELS, wl["model"] + ".json")
+    om = kernels.OracleModel(mpath)
+    from figaroh_b200.model import FlatModel
+    fm = FlatModel.from_json(open(mpath).read())
+    q, v, a = host_inputs(fm, wl, n, 0)
+    t0 = time.perf_counter()
+    oracle_path(om, wl, fm, q, v, a, per_sample=True)
+    return time.perf_counter() - t0
+
+
+def workload_string(wl, n, per_gpu=True):
+    cnt = "1M" if n == 1_000_000 else ("10M" if n == 10_000_000 else str(n))
+    return "%s, %s synthetic samples%s (BASELINE.json %s)" % (wl["title"], cnt, " per GPU" if per_gpu else " in total", wl["baseline_config"])
+
+
 def run_reference(args):
-    """The reference's CPU path (oracle port: per-sample regressor loop + two tall np.linalg.qr)
+    """The reference's CPU path (oracle port: per-sample regressor loop + get_index_eliminate + two tall LAPACK QRs)
     on the host cores, same workload and metric; each step is a bounded sample of it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import kernels, ref_path
-    om = kernels.OracleModel(MODEL_JSON)
-    std = ref_path.standard_parameters(om, PARAM)
-    n = args.ref_samples
-    rng = np.random.default_rng(0)
-    q, v, a = (rng.uniform(-6, 6, (n, 6)) for _ in range(3))
-    phi = np.array(list(std.values()), dtype=float)
-
-    def step():
-        W = ref_path.build_regressor_basic(om, q, v, a, PARAM, per_sample=True)
-        tau = W @ phi
-        idx_e, params_r = ref_path.get_index_eliminate(W, std, 1e-6)
-        W_e = ref_path.build_regressor_reduced(W, idx_e)
-        return ref_path.double_QR(tau, W_e, params_r, std)
-
+    try:  # torchrun exports OMP_NUM_THREADS=1: give LAPACK the host cores back
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:  # noqa: BLE001
+        pass
+    wl = WORKLOADS[args.config]
+    n = args.ref_samples or wl["cpu_samples"]
     for _ in range(min(args.warmup, 1)):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt = (time.perf_counter() - t0) / args.steps
+        cpu_arm(wl, n)
+    dts = [cpu_arm(wl, n) for _ in range(args.steps)]
+    dt = sum(dts) / len(dts)
     val = n / dt
     cores = os.cpu_count()
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "UR10 6-DoF, friction+actuator inertia+joint offsets, 1M synthetic samples per GPU",
+            "config": {"workload": workload_string(wl, args.samples or wl["default_samples"]),
                        "note": "CPU port of the reference path; each step processes a bounded sample"},
             "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
                              "sample": f"{n} samples per step (per-sample regressor loop through the C oracle standing in "
@@ -204,23 +332,39 @@ def run_reference(args):
     print(json.dumps(line), file=_REAL_STDOUT, flush=True)
 
 
-def cpu_baseline(n):
-    from oracle import kernels, ref_path
-    om = kernels.OracleModel(MODEL_JSON)
-    std = ref_path.standard_parameters(om, PARAM)
-    rng = np.random.default_rng(0)
-    q, v, a = (rng.uniform(-6, 6, (n, 6)) for _ in range(3))
-    phi = np.array(list(std.values()), dtype=float)
-    t0 = time.perf_counter()
-    W = ref_path.build_regressor_basic(om, q, v, a, PARAM, per_sample=True)
-    tau = W @ phi
-    idx_e, params_r = ref_path.get_index_eliminate(W, std, 1e-6)
-    W_e = ref_path.build_regressor_reduced(W, idx_e)
-    ref_path.double_QR(tau, W_e, params_r, std)
-    dt = time.perf_counter() - t0
+def cpu_baseline(wl, n):
+    dt = cpu_arm(wl, n)
     return {"value": n / dt, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
             "sample": f"{n} of the workload's samples, once: per-sample regressor loop (C oracle standing in for "
                       f"pinocchio) + get_index_eliminate + double_QR (two LAPACK QRs), {dt:.1f} s"}
+
+
+def parity_check(eng, torch, dm, fm, wl, cfg, sel, names, cols, n=4096):
+    """Rank 0: the fused path and the CPU oracle on the SAME 4096-sample subsample: index sets, expression strings,
+    base parameters in the norm in which they are well posed (the predicted torques), cond(R1) beside it."""
+    from oracle import kernels
+    om = kernels.OracleModel(os.path.join(MODELS, wl["model"] + ".json"))
+    q, v, a = host_inputs(fm, wl, n, 12345)
+    o = oracle_path(om, wl, fm, q, v, a, per_sample=False)
+    rps = cfg_rows(dm, cfg)
+    st = eng.TsqrState(len(sel))
+    st.accumulate_samples(dm, cfg.with_columns(sel), q, v, a, o["tau"].reshape(rps, n))
+    sol = eng.solve_state(st, names, tol_e=wl["tol_e"], col_map=sel, p_full=cols, params_std=o["std"])
+    Wb = o["W_e"][:, sol.idx_base] if len(sol.keep) == o["W_e"].shape[1] else None
+    out = {"subsample": n, "idx_e_equal": sol.idx_e == o["idx_e"],
+           "idx_base_equal": [sol.params_r[i] for i in sol.idx_base] == [b.split(" ")[0] for b in o["out"][2]],
+           "expressions_equal": sol.params_base == o["out"][2]}
+    if Wb is not None and out["idx_base_equal"]:
+        Q1, R1 = np.linalg.qr(Wb)
+        phi_ref = np.linalg.solve(R1, Q1.T @ o["tau"])
+        out["torque_norm_err"] = float(np.linalg.norm(R1 @ (sol.phi_b_raw - phi_ref)) / np.linalg.norm(o["tau"]))
+        out["phi_b_max_rel_err"] = float(np.abs(sol.phi_b_raw - phi_ref).max() / np.abs(phi_ref).max())
+        out["cond_R1_subsample"] = float(np.linalg.cond(R1))
+    return out
+
+
+def cfg_rows(dm, cfg):
+    return dm.shape(cfg)[0]
 
 
 def main():
@@ -228,11 +372,16 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--samples", type=int, default=1_000_000, help="samples per GPU")
+    ap.add_argument("--config", default="ur10", choices=sorted(WORKLOADS))
+    ap.add_argument("--samples", type=int, default=0, help="samples per GPU (weak scaling; default: the workload's)")
+    ap.add_argument("--total-samples", type=int, default=0, help="strong scaling: this many samples sharded over the GPUs")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--ref-samples", type=int, default=100_000)
-    ap.add_argument("--cpu-baseline-samples", type=int, default=100_000)
+    ap.add_argument("--ref-samples", type=int, default=0)
+    ap.add_argument("--cpu-baseline-samples", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--pageable", action="store_true", help="e2e from ordinary (pageable) host arrays instead of pinned ones")
     args = ap.parse_args()
     # Libraries (NCCL prints its version banner) write to fd 1: keep stdout for the ONE JSON line.
     global _REAL_STDOUT
@@ -257,27 +406,35 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
-    fm = FlatModel.from_json(open(MODEL_JSON).read())
+    wl = WORKLOADS[args.config]
+    fm = FlatModel.from_json(open(os.path.join(MODELS, wl["model"] + ".json")).read())
     dm = eng.DeviceModel(fm)
-    cfg = eng.RegressorConfig.from_param(PARAM)
+    rows = active_rows(fm, wl)
+    cfg = eng.RegressorConfig.from_param(wl["param"], row_sel=rows)
     rps, cols = dm.shape(cfg)
-    phi_std, names = standard_phi(fm)
-    N = args.samples
+    phi_std, names = standard_phi(fm, wl["param"])
+    strong = args.total_samples > 0
+    if strong:
+        lo, hi = fdist.shard_range(args.total_samples, rank, world)
+        N = hi - lo
+    else:
+        N = args.samples or wl["default_samples"]
 
     # ---- synthetic inputs, generated on the device (seeded per rank); tau = W phi_std + 1% noise
-    g = torch.Generator(device=dev)
-    g.manual_seed(1234 + rank)
-    q = (torch.rand((N, fm.nq), generator=g, device=dev, dtype=torch.float64) * 12 - 6)
-    v = (torch.rand((N, fm.nv), generator=g, device=dev, dtype=torch.float64) * 12 - 6)
-    a = (torch.rand((N, fm.nv), generator=g, device=dev, dtype=torch.float64) * 12 - 6)
+    q, v, a = device_inputs(torch, fm, wl, N, 1234 + rank, dev)
     tau = torch.empty((rps, N), device=dev, dtype=torch.float64)
     phi_d = torch.from_numpy(phi_std).to(dev)
-    chunk = 1 << 17
+    full_rps = dm.shape(eng.RegressorConfig(cfg.mode, cfg.flags, cfg.ft_mask))[0]
+    chunk = max(1024, min(1 << 17, (1 << 31) // (8 * full_rps * cols)))
+    rsel = None if rows is None else torch.as_tensor(rows, device=dev)
     for i0 in range(0, N, chunk):
         n = min(chunk, N - i0)
         Wc = dm.materialize(cfg, q[i0:i0 + n], v[i0:i0 + n], a[i0:i0 + n])
-        tau[:, i0:i0 + n] = (Wc @ phi_d).view(rps, n)
+        t = (Wc @ phi_d).view(full_rps, n)
+        tau[:, i0:i0 + n] = t if rsel is None else t[rsel]
         del Wc
+    g = torch.Generator(device=dev)
+    g.manual_seed(99 + rank)
     tau += 0.01 * tau.pow(2).mean().sqrt() * torch.randn(tau.shape, generator=g, device=dev, dtype=torch.float64)
     torch.cuda.synchronize()
 
@@ -287,21 +444,13 @@ def main():
     local = eng.TsqrState(len(sel))
     merged = eng.TsqrState(len(sel)) if world > 1 else None
     local.set_timing(True)
+    tol_e = wl["tol_e"]
 
     def step_device():
         local.reset()
         local.accumulate_samples(dm, cfg_run, q, v, a, tau)
         st = fdist.allgather_merge(local, merged)
-        return eng.solve_state(st, names, tol_e=1e-6, col_map=sel, p_full=cols)
-
-    # pinned host copies for the end-to-end path
-    qh, vh, ah, th = (x.cpu().pin_memory() for x in (q, v, a, tau))
-
-    def step_e2e():
-        local.reset()
-        local.accumulate_samples_host(dm, cfg_run, qh, vh, ah, th)
-        st = fdist.allgather_merge(local, merged)
-        return eng.solve_state(st, names, tol_e=1e-6, col_map=sel, p_full=cols)
+        return eng.solve_state(st, names, tol_e=tol_e, col_map=sel, p_full=cols)
 
     def barrier():
         torch.cuda.synchronize()
@@ -337,38 +486,81 @@ def main():
     kern_ms, kern_n = local.get_timing()
     kern_ms_avg = kern_ms / max(kern_n, 1)
 
-    for _ in range(2):
-        step_e2e()
-    ms_e2e, sol_e = timed(step_e2e, max(3, args.steps // 2))
+    e2e = None
+    if not args.no_e2e:
+        # host copies for the end-to-end path: pinned (the caller's staging buffers) unless --pageable
+        if args.pageable:
+            qh, vh, ah, th = (x.cpu().numpy() for x in (q, v, a, tau))
+        else:
+            qh, vh, ah, th = (x.cpu().pin_memory() for x in (q, v, a, tau))
+
+        def step_e2e():
+            local.reset()
+            local.accumulate_samples_host(dm, cfg_run, qh, vh, ah, th)
+            st = fdist.allgather_merge(local, merged)
+            return eng.solve_state(st, names, tol_e=tol_e, col_map=sel, p_full=cols)
+
+        for _ in range(2):
+            step_e2e()
+        ms_e2e, sol_e = timed(step_e2e, max(3, args.steps // 2))
+        h2d = int(N * (fm.nq + 2 * fm.nv + rps) * 8)
+        e2e = {"value": (args.total_samples if strong else N * world) / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e,
+               "h2d_bytes_per_step": h2d, "h2d_gbs_per_rank": h2d / (ms_e2e * 1e-3) / 1e9,
+               "host_buffers": "pageable" if args.pageable else "pinned",
+               "d2h_bytes_per_step": int(8 * (2 * (cols + 1) + len(sol.idx_base) * (len(sol.idx_regroup) + 1 + len(sol.idx_base))
+                                              + (len(sol.keep) + 1) ** 2))}
 
     if rank == 0:
-        total = N * world
+        total = args.total_samples if strong else N * world
         peak, peak_src = fp64_peak_tflops()
-        achieved = FLOPS_PER_SAMPLE * N / (kern_ms_avg * 1e-3) / 1e12
+        plan = eng.describe_plan(fm, cfg_run)
+        if not plan.get("ring_kernel"):  # wide kernel: count bodies / hops from the model
+            depth = [0] * fm.njoints
+            for i in range(1, fm.njoints):
+                depth[i] = depth[int(fm.parent[i])] + 1
+            plan["nbodies"] = fm.njoints - 1
+            plan["hops"] = int(sum(depth))
+        fps, f_reg = flops_per_sample(plan, rps, len(sol.keep))
+        achieved = fps * N / (kern_ms_avg * 1e-3) / 1e12
+        kernel = ("rq_accumulate_kernel (producer SMs walk the kinematic tree once per 32-sample tile and write every row group's "
+                  "tile into an L2-resident ring; consumer SMs: one Householder TSQR stream per (warp, row group), cp.async.bulk "
+                  "tile refill, 8-column panels, DMMA trailing updates)") if plan.get("ring_kernel") else \
+                 ("wide_accumulate_samples_kernel (CTA-wide register tile, one column per thread and slot, Householder column "
+                  "steps through one named barrier, factor row streamed from L2; forward kinematics by a thread-per-sample "
+                  "pre-kernel, staged per tile by cp.async.bulk)")
+        diag = np.asarray(sol.diag[:len(sol.keep)])
+        base_diag = diag[diag > 1e-8]
         line = {
             "metric": METRIC, "value": total / (ms_step * 1e-3), "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "UR10 6-DoF, friction+actuator inertia+joint offsets, %s synthetic samples per GPU "
-                                   "(BASELINE.json configs[1]%s)" % ("1M" if N == 1_000_000 else str(N),
-                                                                    "" if N == 1_000_000 else "; sample count overridden: configs[4] sweep"),
-                       "samples_per_gpu": N, "rows_per_sample": rps, "columns": cols, "columns_folded": int(len(sel)), "parallelism": f"dp{world}",
-                       "l2": "inputs (192 B/sample x N = %.0f MB per step) exceed the 126 MB L2" % (N * 192 / 1e6),
-                       "eliminated": len(sol.idx_e), "base_parameters": len(sol.idx_base)},
-            "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": int(N * (fm.nq + 2 * fm.nv + rps) * 8),
-                    "d2h_bytes_per_step": int(8 * (2 * (cols + 1) + len(sol.idx_base) * (len(sol.idx_regroup) + 1 + len(sol.idx_base))
-                                                   + (len(sol.keep) + 1) ** 2))},
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_string(wl, total if strong else N, per_gpu=not strong),
+                       "samples_per_gpu": N, "rows_per_sample": rps, "columns": cols, "columns_folded": int(len(sel)),
+                       "parallelism": f"dp{world}",
+                       "l2": "inputs (%d B/sample x N = %.0f MB per step) exceed the 126 MB L2" % (
+                           (fm.nq + 2 * fm.nv + rps) * 8, N * (fm.nq + 2 * fm.nv + rps) * 8 / 1e6),
+                       "eliminated": len(sol.idx_e), "kept": len(sol.keep), "base_parameters": len(sol.idx_base),
+                       "cond_R1": float(np.linalg.cond(sol.R1)),
+                       "min_base_diag_over_tol_qr": float(base_diag.min() / 1e-8) if len(base_diag) else None,
+                       "max_dependent_diag_over_tol_qr": float(diag[diag <= 1e-8].max() / 1e-8) if (diag <= 1e-8).any() else None},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "pipe": "fp64 (DFMA panels + DMMA m8n8k4 trailing updates; tcgen05 has no fp64 mode)",
-                         "kernel": "gq_accumulate_kernel (one Householder TSQR stream per (warp, row group): sample-per-lane regressor rows into a 32 x w_g shared-memory tile, 8-column panels, DMMA trailing updates)",
-                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(N), "kernel_ms": kern_ms_avg, "kernel_share_of_step": kern_ms_avg / ms_step,
-                         "flops_per_sample": FLOPS_PER_SAMPLE, "peak_source": peak_src},
+            "roofline": {"bound": "tensor", "pipe": "fp64 (DFMA + DMMA m8n8k4; tcgen05 has no fp64 mode)",
+                         "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic(args.config, N), "kernel_ms": kern_ms_avg,
+                         "kernel_share_of_step": kern_ms_avg / ms_step, "flops_per_sample": fps,
+                         "flops_note": "SURVEY 8(d) dense formula F_reg + 2 m_s (p_e+1)^2 with p_e = kept columns; the row-group "
+                                       "streams do fewer real flops (block sparsity), see DESIGN.md", "peak_source": peak_src},
         }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if not args.no_parity_check:
+            try:
+                line["parity_check"] = parity_check(eng, torch, dm, fm, wl, cfg, sel, names, cols)
+            except Exception as ex:  # noqa: BLE001
+                line["parity_check"] = {"error": repr(ex)[:300]}
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(args.cpu_baseline_samples)
+            line["cpu_baseline"] = cpu_baseline(wl, args.cpu_baseline_samples or wl["cpu_samples"])
         print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     if world > 1:
         dist.destroy_process_group()

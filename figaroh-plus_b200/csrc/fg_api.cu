@@ -1043,7 +1043,7 @@ static int accumulate_samples_dev(fg_state* s, fg_model* m, const fg_regressor_c
     const int spt = wide_samples_per_tile(ms, pl->P.p1);
     if (use_wide && spt > 0 && s->perm.empty()) {
       const int64_t ntiles = (N + spt - 1) / spt;
-      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, m->sm_count));
+      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)m->sm_count * wide_ctas_per_sm(ms, pl->P.p1)));
       rc = ensure_parts(s, grid + 1);
       if (rc) return rc;
       rc = timing_begin(s, st);

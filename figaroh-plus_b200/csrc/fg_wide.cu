@@ -1,29 +1,39 @@
 // fg_wide.cu - launchers of the CTA-wide register-tile kernels (fg_wide.cuh): fused samples -> factor for any
 // tree / row-group count / up to 767 columns, dense matrix -> factor, and the pairwise merge of wide parts.
 #include <algorithm>
+#include <cstdlib>
 
 #include "fg_wide.cuh"
 #include "fg_wide.h"
 
 namespace fg {
 
-template <int MSMAX, int S, int NSLOT>
+template <int MSMAX, int S, int NSLOT, int MINB = 1>
 static cudaError_t launch_samples(const Plan& P, const DevPlanPtrs& pp, const double* v, const double* a,
                                   const double* tau, int64_t ld_tau, int64_t n, const double* fw, double* parts,
                                   int grid, int max_smem, int first, cudaStream_t st) {
   constexpr int TR = MSMAX * S;
   const WideLayout L = wide_layout(P.nj, P.ms, S, TR);
   if (L.total > max_smem) return cudaErrorInvalidConfiguration;
-  auto kern = wide_accumulate_samples_kernel<MSMAX, S, NSLOT>;
+  auto kern = wide_accumulate_samples_kernel<MSMAX, S, NSLOT, MINB>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
   if (e != cudaSuccess) return e;
   kern<<<grid, WD_THREADS, L.total, st>>>(pp, v, a, tau, ld_tau, n, fw, parts, first, 0);
   return cudaGetLastError();
 }
 
+// two CTAs per SM with half-height tiles (128 registers per thread): FG_WIDE_OCC2=1, six row groups, <= 511 columns
+static bool wide_occ2(int ms, int nslot) {
+  const char* e = getenv("FG_WIDE_OCC2");
+  return e && e[0] == '1' && ms <= 6 && nslot == 2;
+}
+
+int wide_ctas_per_sm(int ms, int p1) { return wide_occ2(ms, (p1 + WD_THREADS - 1) / WD_THREADS) ? 2 : 1; }
+
 int wide_samples_per_tile(int ms, int p1) {
   const int nslot = (p1 + WD_THREADS - 1) / WD_THREADS;
   if (nslot > 3 || ms > 48) return 0;
+  if (wide_occ2(ms, nslot)) return 3;
   if (nslot == 1) return ms <= 6 ? 8 : (ms <= 8 ? 6 : (ms <= 24 ? 2 : 1));
   if (nslot == 2) return ms <= 6 ? 6 : (ms <= 8 ? 4 : 1);
   return ms <= 6 ? 4 : (ms <= 8 ? 3 : (ms <= 24 ? 1 : 0));
@@ -53,7 +63,8 @@ cudaError_t wide_launch_samples(const Plan& P, const DevPlanPtrs& pp, const doub
       else if (ms <= 24) FG_WD(24, 2, 1);
       else if (ms <= 48) FG_WD(48, 1, 1);
     } else if (nslot == 2) {
-      if (ms <= 6) FG_WD(6, 6, 2);
+      if (wide_occ2(ms, nslot)) e = launch_samples<6, 3, 2, 2>(P, pp, vc, ac, tc, ld_tau, n, fw_buf, parts, grid, max_smem, first, st);
+      else if (ms <= 6) FG_WD(6, 6, 2);
       else if (ms <= 8) FG_WD(8, 4, 2);
       else if (ms <= 24) FG_WD(24, 1, 2);
       else if (ms <= 48) FG_WD(48, 1, 2);

@@ -26,119 +26,166 @@ constexpr int WD_BAR = 1;         // named barrier of the 256 column owners
 
 __device__ __forceinline__ void wd_bar() { asm volatile("bar.sync %0, %1;" ::"n"(WD_BAR), "n"(WD_THREADS) : "memory"); }
 
+// sqrt(x), 1/sqrt(x) and 1/x from a MUFU seed and two Newton steps (full double accuracy for normal x; the
+// sequences sqrt() / division expand to are three times as long and sit on the critical path of every column)
+__device__ __forceinline__ void wd_sqrt_rsqrt(double x, double& sq, double& rs) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double g = x * y, h = 0.5 * y;
+  double r = fma(-g, h, 0.5);
+  g = fma(g, r, g);
+  h = fma(h, r, h);
+  r = fma(-g, h, 0.5);
+  sq = fma(g, r, g);
+  rs = 2.0 * fma(h, r, h);
+}
+__device__ __forceinline__ double wd_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+
+// Householder reflector of [alpha; x] (LAPACK dlarfg convention: beta = -sign(alpha) norm, v = x / (alpha - beta),
+// tau = (beta - alpha) / beta), published for the other threads: xb[0..TR) = x (not normalised), xb[TRP] = 1 / (alpha
+// - beta), xb[TRP + 1] = tau (0: H = I).  Returns beta (the new diagonal entry of R) or alpha when H = I.
+template <int TR, int NSLOT>
+__device__ __forceinline__ void wide_publish(const double (&B)[TR][NSLOT], int sc, double alpha, double* xb,
+                                             double* Rdiag) {
+  constexpr int TRP = ((TR + 7) / 8) * 8;
+  double sg[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int s = 0; s < NSLOT; ++s)
+    if (s == sc) {
+#pragma unroll
+      for (int r = 0; r < TR; ++r) {
+        const double x = B[r][s];
+        xb[r] = x;
+        sg[r & 3] = fma(x, x, sg[r & 3]);
+      }
+    }
+  const double sigma = (sg[0] + sg[1]) + (sg[2] + sg[3]);
+  double inv = 0.0, tauh = 0.0;
+  const double mu = fma(alpha, alpha, sigma);
+  if (sigma != 0.0 && mu > 1e-280) {  // else H = I (dlarfg with xnorm == 0)
+    double nrm, rs;
+    wd_sqrt_rsqrt(mu, nrm, rs);
+    const double beta = alpha >= 0.0 ? -nrm : nrm;
+    const double den = alpha - beta;
+    inv = wd_rcp(den);
+    tauh = fabs(den) * rs;  // (beta - alpha) / beta
+    __stcg(Rdiag, beta);
+  }
+  xb[TRP] = inv;
+  xb[TRP + 1] = tauh;
+}
+
+// Apply the published reflector to the thread's column of slot s (col > c): dot product, new R entry, rank-1 update.
+template <int TR, int NSLOT, int S_>
+__device__ __forceinline__ void wide_apply_slot(double (&B)[TR][NSLOT], const double* xb, double inv, double tauh,
+                                                double rho, double* Rdst, bool active) {
+  double d[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int r0 = 0; r0 < TR; r0 += 4) {
+    const double2 t0 = *reinterpret_cast<const double2*>(xb + r0);
+    const double2 t1 = *reinterpret_cast<const double2*>(xb + r0 + 2);
+    if (r0 < TR) d[0] = fma(t0.x, B[r0 < TR ? r0 : 0][S_], d[0]);
+    if (r0 + 1 < TR) d[1] = fma(t0.y, B[r0 + 1 < TR ? r0 + 1 : 0][S_], d[1]);
+    if (r0 + 2 < TR) d[2] = fma(t1.x, B[r0 + 2 < TR ? r0 + 2 : 0][S_], d[2]);
+    if (r0 + 3 < TR) d[3] = fma(t1.y, B[r0 + 3 < TR ? r0 + 3 : 0][S_], d[3]);
+  }
+  const double dd = (d[0] + d[1]) + (d[2] + d[3]);
+  const double sdot = fma(dd, inv, rho);  // w^T [rho; b],  w = [1; x * inv]
+  double gco = 0.0;
+  if (active) {
+    __stcg(Rdst, fma(-tauh, sdot, rho));
+    gco = tauh * sdot * inv;
+  }
+#pragma unroll
+  for (int r0 = 0; r0 < TR; r0 += 4) {
+    const double2 t0 = *reinterpret_cast<const double2*>(xb + r0);
+    const double2 t1 = *reinterpret_cast<const double2*>(xb + r0 + 2);
+    if (r0 < TR) B[r0 < TR ? r0 : 0][S_] = fma(-gco, t0.x, B[r0 < TR ? r0 : 0][S_]);
+    if (r0 + 1 < TR) B[r0 + 1 < TR ? r0 + 1 : 0][S_] = fma(-gco, t0.y, B[r0 + 1 < TR ? r0 + 1 : 0][S_]);
+    if (r0 + 2 < TR) B[r0 + 2 < TR ? r0 + 2 : 0][S_] = fma(-gco, t1.x, B[r0 + 2 < TR ? r0 + 2 : 0][S_]);
+    if (r0 + 3 < TR) B[r0 + 3 < TR ? r0 + 3 : 0][S_] = fma(-gco, t1.y, B[r0 + 3 < TR ? r0 + 3 : 0][S_]);
+  }
+}
+
+template <int TR, int NSLOT, int S_>
+__device__ __forceinline__ void wide_apply_slots(double (&B)[TR][NSLOT], const double* xb, double inv, double tauh,
+                                                 const double (&rho)[NSLOT], double* Rrow, int c, int p1, int tid,
+                                                 int only, int skip) {
+  if constexpr (S_ < NSLOT) {
+    const int col = tid + WD_THREADS * S_;
+    // warp-uniform: a slot whose 32 columns of this warp are all <= c has retired
+    const bool warp_live = (col | 31) > c;
+    if (warp_live && (only < 0 || only == S_) && skip != S_)
+      wide_apply_slot<TR, NSLOT, S_>(B, xb, inv, tauh, rho[S_], Rrow + col - c, col > c && col < p1);
+    wide_apply_slots<TR, NSLOT, S_ + 1>(B, xb, inv, tauh, rho, Rrow, c, p1, tid, only, skip);
+  }
+}
+
 // Fold the register tile B (TR rows; thread `tid` owns columns tid + 256 s) into the packed upper-triangular
 // factor Rt (p1 columns, global memory, private to this CTA).  Columns < c_begin of the tile are zero.
 // xs: 2 * (ceil8(TR) + 4) doubles of shared memory.
+// Step c applies reflector c (published in xs[c & 1]) to every live column.  LOOK-AHEAD: the owner of column c + 1
+// updates that column first, takes its reflector and publishes it into the other buffer before finishing its
+// own step, so the one barrier per step never waits for the square root.
 template <int TR, int NSLOT>
 __device__ __forceinline__ void wide_fold(double (&B)[TR][NSLOT], double* __restrict__ Rt, int p1, int c_begin,
                                           double* xs, int tid) {
-  constexpr int XS = ((TR + 7) / 8) * 8 + 4;  // reflector (padded to whole 8-row chunks) + scalars
+  constexpr int TRP = ((TR + 7) / 8) * 8;
+  constexpr int XS = TRP + 4;
   double rho[NSLOT];
+  {
+    const int roff = tri_off(c_begin, p1);
 #pragma unroll
-  for (int s = 0; s < NSLOT; ++s) {
-    const int col = tid + WD_THREADS * s;
-    rho[s] = (col >= c_begin && col < p1) ? __ldcg(Rt + tri_off(c_begin, p1) + col - c_begin) : 0.0;
+    for (int s = 0; s < NSLOT; ++s) {
+      const int col = tid + WD_THREADS * s;
+      rho[s] = (col >= c_begin && col < p1) ? __ldcg(Rt + roff + col - c_begin) : 0.0;
+    }
+    if (tid == (c_begin & (WD_THREADS - 1))) {
+      const int sc = c_begin / WD_THREADS;
+      double alpha = 0.0;
+#pragma unroll
+      for (int s = 0; s < NSLOT; ++s)
+        if (s == sc) alpha = rho[s];
+      wide_publish<TR, NSLOT>(B, sc, alpha, xs + (c_begin & 1) * XS, Rt + roff);
+    }
   }
+  wd_bar();
   for (int c = c_begin; c < p1; ++c) {
     double rho_n[NSLOT];
     const int roff = tri_off(c, p1);
-    {
-      const int rn = roff + (p1 - c);  // tri_off(c + 1, p1)
+    const int rn = roff + (p1 - c);  // tri_off(c + 1, p1)
 #pragma unroll
-      for (int s = 0; s < NSLOT; ++s) {
-        const int col = tid + WD_THREADS * s;
-        rho_n[s] = (c + 1 < p1 && col > c && col < p1) ? __ldcg(Rt + rn + col - c - 1) : 0.0;
-      }
+    for (int s = 0; s < NSLOT; ++s) {
+      const int col = tid + WD_THREADS * s;
+      rho_n[s] = (c + 1 < p1 && col > c && col < p1) ? __ldcg(Rt + rn + col - c - 1) : 0.0;
     }
-    const int tc = c & (WD_THREADS - 1), sc = c / WD_THREADS;
-    double* xb = xs + (c & 1) * XS;
-    if (tid == tc) {
+    const double* xb = xs + (c & 1) * XS;
+    const double inv = xb[TRP], tauh = xb[TRP + 1];
+    const int cn = c + 1;
+    const bool next_owner = cn < p1 && tid == (cn & (WD_THREADS - 1));
+    const int sn = cn / WD_THREADS;
+    if (next_owner) {  // my column c + 1 first, then its reflector, then the rest of my columns
+      if (tauh != 0.0) wide_apply_slots<TR, NSLOT, 0>(B, xb, inv, tauh, rho, Rt + roff, c, p1, tid, sn, -1);
       double alpha = 0.0;
-      double sg[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
       for (int s = 0; s < NSLOT; ++s)
-        if (s == sc) {
-          alpha = rho[s];
-#pragma unroll
-          for (int r = 0; r < TR; ++r) {
-            const double x = B[r][s];
-            xb[r] = x;
-            sg[r & 3] = fma(x, x, sg[r & 3]);
-          }
-        }
-      const double sigma = (sg[0] + sg[1]) + (sg[2] + sg[3]);
-      double inv = 0.0, tauh = 0.0;
-      if (sigma != 0.0) {  // else H = I (dlarfg with xnorm == 0)
-        const double mu = fma(alpha, alpha, sigma);
-        const double nrm = sqrt(mu);
-        const double beta = alpha >= 0.0 ? -nrm : nrm;
-        const double den = alpha - beta;
-        inv = 1.0 / den;
-        tauh = (beta - alpha) / beta;
-        __stcg(Rt + roff, beta);
-      }
-      xb[TR] = inv;
-      xb[TR + 1] = tauh;
-    }
-    wd_bar();
-    const double inv = xb[TR], tauh = xb[TR + 1];
-    if (tauh != 0.0) {  // uniform
-      // v is streamed from shared memory in chunks of 8 rows (broadcast reads), once for the dot products of all
-      // the thread's columns and once for their updates: the tile owns the registers, not the reflector
-      double dd[NSLOT];
-#pragma unroll
-      for (int s = 0; s < NSLOT; ++s) dd[s] = 0.0;
-#pragma unroll
-      for (int r0 = 0; r0 < TR; r0 += 8) {
-        double v[8];
-#pragma unroll
-        for (int r = 0; r < 8; r += 2) {
-          const double2 t2 = *reinterpret_cast<const double2*>(xb + r0 + r);
-          v[r] = t2.x;
-          v[r + 1] = t2.y;
-        }
-#pragma unroll
-        for (int s = 0; s < NSLOT; ++s) {
-          double d0 = 0.0, d1 = 0.0;
-#pragma unroll
-          for (int r = 0; r < 8; r += 2) {
-            if (r0 + r < TR) d0 = fma(v[r], B[r0 + r][s], d0);
-            if (r0 + r + 1 < TR) d1 = fma(v[r + 1], B[r0 + r + 1][s], d1);
-          }
-          dd[s] += d0 + d1;
-        }
-      }
-      double gco[NSLOT];
-#pragma unroll
-      for (int s = 0; s < NSLOT; ++s) {
-        const int col = tid + WD_THREADS * s;
-        gco[s] = 0.0;
-        if (col > c && col < p1) {
-          const double sdot = fma(dd[s], inv, rho[s]);  // w^T [rho; b],  w = [1; x * inv]
-          __stcg(Rt + roff + col - c, fma(-tauh, sdot, rho[s]));
-          gco[s] = tauh * sdot * inv;
-        }
-      }
-#pragma unroll
-      for (int r0 = 0; r0 < TR; r0 += 8) {
-        double v[8];
-#pragma unroll
-        for (int r = 0; r < 8; r += 2) {
-          const double2 t2 = *reinterpret_cast<const double2*>(xb + r0 + r);
-          v[r] = t2.x;
-          v[r + 1] = t2.y;
-        }
-#pragma unroll
-        for (int s = 0; s < NSLOT; ++s)
-#pragma unroll
-          for (int r = 0; r < 8; ++r)
-            if (r0 + r < TR) B[r0 + r][s] = fma(-gco[s], v[r], B[r0 + r][s]);
-      }
+        if (s == sn) alpha = rho_n[s];
+      wide_publish<TR, NSLOT>(B, sn, alpha, xs + (cn & 1) * XS, Rt + rn);
+      if (tauh != 0.0) wide_apply_slots<TR, NSLOT, 0>(B, xb, inv, tauh, rho, Rt + roff, c, p1, tid, -1, sn);
+    } else if (tauh != 0.0) {
+      wide_apply_slots<TR, NSLOT, 0>(B, xb, inv, tauh, rho, Rt + roff, c, p1, tid, -1, -1);
     }
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) rho[s] = rho_n[s];
+    wd_bar();
   }
-  wd_bar();  // the last step's reads of xs are done before the next tile's first owner writes
 }
 
 // ------------------------------------------------------------------ forward kinematics of a chunk of samples
@@ -182,8 +229,8 @@ __host__ __device__ inline WideLayout wide_layout(int nj, int ms, int S, int TR)
   return L;
 }
 
-template <int MSMAX, int S, int NSLOT>
-__global__ void __launch_bounds__(WD_THREADS, 1)
+template <int MSMAX, int S, int NSLOT, int MINB>
+__global__ void __launch_bounds__(WD_THREADS, MINB)
 wide_accumulate_samples_kernel(DevPlanPtrs pp, const double* __restrict__ qd, const double* __restrict__ qdd,
                                const double* __restrict__ tau, int64_t ld_tau, int64_t n,
                                const double* __restrict__ fw_all, double* __restrict__ parts, int first, int last) {

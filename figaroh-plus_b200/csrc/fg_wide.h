@@ -11,6 +11,8 @@ constexpr int WD_MAX_P1 = 768;  // three columns per thread
 
 // samples per tile the fused kernel uses for (row groups, columns incl. rhs); 0 = shape not supported
 int wide_samples_per_tile(int ms, int p1);
+// resident CTAs per SM of the fused kernel for that shape (grid = SMs x this)
+int wide_ctas_per_sm(int ms, int p1);
 // rows per tile of the dense kernel; 0 = too wide
 int wide_dense_tile_rows(int p1);
 
