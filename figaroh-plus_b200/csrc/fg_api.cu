@@ -12,8 +12,7 @@
 
 #include "../../include/figaroh_b200.h"
 #include "fg_kernels.cuh"
-#include "fg_bq.h"
-#include "fg_tq.h"
+#include "fg_tile.cuh"
 #include "fg_gq.h"
 #include "fg_rq.h"
 #include "fg_wide.h"
@@ -49,21 +48,12 @@ struct DevPlan {
   std::vector<int> nact, fullcol;
   void* d_blob = nullptr;  // one allocation holding everything
   DevPlanPtrs ptrs{};
-  // third-generation kernel (fg_tileqr.cuh): launch parameters, built on first use
-  bool tq_tried = false;
-  TqLaunch tql;
-  std::unique_ptr<TqParams> tq;
-  // fourth-generation kernel (fg_groupqr.cuh)
-  bool gq_tried = false;
-  GqLaunch gql;
-  std::unique_ptr<GqParams> gq;
-  void* d_gq_tab = nullptr;  // warp -> (row group, instance) tables of the full launch
   // fifth-generation kernel (fg_ringqr.cuh)
   bool rq_tried = false;
   RqLaunch rql;
   std::unique_ptr<RqParams> rq;
   void* d_rq_tab = nullptr;
-  ~DevPlan() { if (d_blob) cudaFree(d_blob); if (d_gq_tab) cudaFree(d_gq_tab); if (d_rq_tab) cudaFree(d_rq_tab); }
+  ~DevPlan() { if (d_blob) cudaFree(d_blob); if (d_rq_tab) cudaFree(d_rq_tab); }
 };
 
 struct fg_model {
@@ -80,6 +70,8 @@ struct fg_model {
 struct fg_state {
   int p = 0, p1 = 0;
   int64_t rows = 0;
+  double* d_rows_pending = nullptr;  // rows that arrived inside packed factors, summed on the device
+  bool rows_pending = false;
   bool empty = true;
   double* d_part = nullptr;     // merged factor: packed triangle + norms   [part_doubles(p1)]
   double* d_parts = nullptr;    // scratch partial factors
@@ -497,7 +489,18 @@ extern "C" int fg_regressor_materialize(const fg_model* mc, const fg_regressor_c
 // ------------------------------------------------------------------------------------ state
 extern "C" int64_t fg_state_packed_doubles(int32_t p) { return (int64_t)(p + 1) * (p + 1) + 2 * (p + 1); }
 extern "C" int fg_state_p(const fg_state* s) { return s ? s->p : -1; }
-extern "C" int64_t fg_state_rows(const fg_state* s) { return s ? s->rows : -1; }
+extern "C" int64_t fg_state_rows(const fg_state* sc) {
+  if (!sc) return -1;
+  fg_state* s = const_cast<fg_state*>(sc);
+  if (s->rows_pending) {  // row counts of merged packed factors: one small synchronous copy, on demand
+    double r = 0.0;
+    if (cudaMemcpy(&r, s->d_rows_pending, sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    cudaMemset(s->d_rows_pending, 0, sizeof(double));
+    s->rows += (int64_t)r;
+    s->rows_pending = false;
+  }
+  return s->rows;
+}
 
 extern "C" int fg_state_create(int32_t p, fg_state** out) {
   if (p < 1 || p + 1 > WD_MAX_P1 || !out) return set_err(FG_ERR_INVALID, "fg_state_create: p=%d outside [1,%d]", p, WD_MAX_P1 - 1);
@@ -516,6 +519,7 @@ extern "C" int fg_state_create(int32_t p, fg_state** out) {
 
 extern "C" void fg_state_destroy(fg_state* s) {
   if (!s) return;
+  cudaFree(s->d_rows_pending);
   cudaFree(s->d_part); cudaFree(s->d_parts); cudaFree(s->d_gR); cudaFree(s->d_A); cudaFree(s->d_Re);
   cudaFree(s->d_X); cudaFree(s->d_idx); cudaFree(s->d_stage); cudaFree(s->d_solve); cudaFree(s->d_ring);
   if (s->h_rq_err) cudaFreeHost(s->h_rq_err);
@@ -555,6 +559,10 @@ extern "C" int fg_state_get_timing(fg_state* s, double* total_ms, long long* lau
 extern "C" int fg_state_reset(fg_state* s, void* stream) {
   if (!s) return set_err(FG_ERR_INVALID, "null state");
   FG_CUDA(cudaMemsetAsync(s->d_part, 0, sizeof(double) * part_doubles(s->p1), (cudaStream_t)stream));
+  if (s->rows_pending) {
+    FG_CUDA(cudaMemsetAsync(s->d_rows_pending, 0, sizeof(double), (cudaStream_t)stream));
+    s->rows_pending = false;
+  }
   s->rows = 0; s->empty = true; s->nk = -1;
   s->perm.clear();
   return FG_OK;
@@ -744,149 +752,6 @@ extern "C" int fg_state_accumulate_dense(fg_state* s, const double* W, int64_t l
   return launch_dense<15, 8>(s, W, ldw, tau, rows, st);
 }
 
-// ---- fused accumulate
-template <int NSLOT, int MS, int S>
-static int launch_fused(fg_state* s, fg_model* m, DevPlan* pl, const double* q, const double* v, const double* a,
-                        const double* tau, int64_t ld_tau, int64_t N, cudaStream_t st) {
-  constexpr int TR = MS * S;
-  constexpr int TRM = TR >= 8 ? TR : 8;
-  static_assert(TRM == TR || true, "");
-  const int p1 = s->p1, ntri = p1 * (p1 + 1) / 2;
-  const int static_smem = 8 * 32 * NSLOT * 8 + 64;
-  int nwarps = 8;
-  bool in_smem = true;
-  while (nwarps > 1 &&
-         make_layout(pl->P.nj, pl->P.ms, p1, pl->P.nv, S, TRM, nwarps, true, true).total + static_smem > m->max_smem)
-    --nwarps;
-  if (make_layout(pl->P.nj, pl->P.ms, p1, pl->P.nv, S, TRM, nwarps, true, true).total + static_smem > m->max_smem ||
-      nwarps < 4) {
-    in_smem = false;
-    nwarps = 8;
-  }
-  const SmemLayout L = make_layout(pl->P.nj, pl->P.ms, p1, pl->P.nv, S, TRM, nwarps, in_smem, true);
-  if (L.total + static_smem > m->max_smem) return set_err(FG_ERR_UNSUPPORTED, "fused kernel needs %d bytes of shared memory", L.total);
-  const int64_t ntiles = (N + S - 1) / S;
-  int grid = (int)std::min<int64_t>((ntiles + nwarps - 1) / nwarps, m->sm_count);
-  if (grid < 1) grid = 1;
-  int rc;
-  if (!in_smem) {
-    const int64_t cap = std::max<int64_t>(1, (64ll << 20) / ((int64_t)ntri * 8 * nwarps));
-    grid = (int)std::min<int64_t>(grid, cap);
-    rc = ensure_gR(s, (int64_t)grid * nwarps * ntri);
-    if (rc) return rc;
-  }
-  rc = ensure_parts(s, grid + 1);
-  if (rc) return rc;
-  auto kern = accumulate_samples_kernel<NSLOT, MS, S>;
-  FG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-  rc = timing_begin(s, st);
-  if (rc) return rc;
-  kern<<<grid, nwarps * 32, L.total, st>>>(pl->ptrs, q, v, a, tau, ld_tau, N, s->d_parts,
-                                           in_smem ? nullptr : s->d_gR, 1);
-  rc = timing_end(s, st);
-  if (rc) return rc;
-  FG_CUDA(cudaGetLastError());
-  FG_LAUNCHED();
-  rc = merge_parts_into_state(s, grid, m->max_smem, st);
-  if (rc) return rc;
-  s->rows += N * pl->P.ms;
-  return FG_OK;
-}
-
-// second-generation fused kernel (fg_blockqr.cuh): register tile in DMMA fragment layout
-static int launch_bq(fg_state* s, fg_model* m, DevPlan* pl, const double* q, const double* v, const double* a,
-                     const double* tau, int64_t ld_tau, int64_t N, cudaStream_t st) {
-  const BqLaunch bl = bq_plan_launch(pl->P, N, m->sm_count, m->max_smem);
-  if (!bl.ok) return set_err(FG_ERR_UNSUPPORTED, "block-QR kernel needs %d bytes of shared memory", bl.smem);
-  int rc = ensure_parts(s, bl.nparts + 1);
-  if (rc) return rc;
-  rc = timing_begin(s, st);
-  if (rc) return rc;
-  cudaError_t e = bq_launch(bl, pl->ptrs, q, v, a, tau, ld_tau, N, s->d_parts, st);
-  rc = timing_end(s, st);
-  if (rc) return rc;
-  if (e != cudaSuccess) return set_err(FG_ERR_CUDA, "bq_launch failed: %s", cudaGetErrorString(e));
-  FG_LAUNCHED();
-  rc = merge_parts_into_state(s, bl.nparts, m->max_smem, st);
-  if (rc) return rc;
-  s->rows += N * pl->P.ms;
-  return FG_OK;
-}
-
-// third-generation fused kernel (fg_tileqr.cuh): shared-memory tiles of 32 samples, rows grouped by joint.
-// `phase`: TQ_PHASE_FIRST starts the per-CTA factors from zero, TQ_PHASE_LAST writes them out and merges
-// them into the state; a chunked caller (the host-buffer path) sets FIRST on its first chunk and LAST on its
-// last one, so the factors stay in the L2-resident scratch between launches and are merged once.
-static int launch_tq(fg_state* s, fg_model* m, DevPlan* pl, const double* q, const double* v, const double* a,
-                     const double* tau, int64_t ld_tau, int64_t N, int phase, cudaStream_t st) {
-  const TqLaunch& tl = pl->tql;
-  const int64_t ntiles = (N + TQ_S - 1) / TQ_S;
-  const bool whole = phase == (TQ_PHASE_FIRST | TQ_PHASE_LAST);
-  const int grid = whole ? (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, tl.grid)) : tl.grid;
-  int rc = ensure_parts(s, grid + 1);
-  if (rc) return rc;
-  if (phase & TQ_PHASE_FIRST) {
-    rc = ensure_gR(s, (int64_t)grid * tl.r_doubles);
-    if (rc) return rc;
-  } else if (s->gR_cap < (int64_t)grid * tl.r_doubles) {
-    return set_err(FG_ERR_INVALID, "internal: continued launch without a first one");
-  }
-  rc = timing_begin(s, st);
-  if (rc) return rc;
-  cudaError_t e = tq_launch(tl, *pl->tq, q, v, a, tau, ld_tau, N, s->d_gR, s->d_parts, grid, phase, st);
-  rc = timing_end(s, st);
-  if (rc) return rc;
-  if (e != cudaSuccess) return set_err(FG_ERR_CUDA, "tq_launch failed: %s", cudaGetErrorString(e));
-  FG_LAUNCHED();
-  s->rows += N * pl->P.ms;
-  if (!(phase & TQ_PHASE_LAST)) return FG_OK;
-  return merge_parts_into_state(s, grid, m->max_smem, st);
-}
-
-// fourth-generation fused kernel (fg_groupqr.cuh): one independent TSQR stream per (warp, row group); the
-// per-leaf factors stay in the L2-resident scratch between the launches of a chunked caller and are merged
-// (tree per row group, then the roots into the full factor) by gq_merge on the last chunk.
-static int launch_gq(fg_state* s, fg_model* m, DevPlan* pl, const double* q, const double* v, const double* a,
-                     const double* tau, int64_t ld_tau, int64_t N, int phase, cudaStream_t st) {
-  GqLaunch& gl = pl->gql;
-  if (!pl->d_gq_tab) {
-    const size_t nb_i = gl.tab_i.size() * sizeof(unsigned short), nb_g = (gl.tab_g.size() + 15) / 16 * 16;
-    FG_CUDA(cudaMalloc(&pl->d_gq_tab, nb_g + nb_i));
-    FG_CUDA(cudaMemcpy(pl->d_gq_tab, gl.tab_g.data(), gl.tab_g.size(), cudaMemcpyHostToDevice));
-    FG_CUDA(cudaMemcpy(static_cast<char*>(pl->d_gq_tab) + nb_g, gl.tab_i.data(), nb_i, cudaMemcpyHostToDevice));
-    gl.d_tab_g = static_cast<const unsigned char*>(pl->d_gq_tab);
-    gl.d_tab_i = reinterpret_cast<const unsigned short*>(static_cast<char*>(pl->d_gq_tab) + nb_g);
-  }
-  const bool whole = phase == (TQ_PHASE_FIRST | TQ_PHASE_LAST);
-  const int64_t cnt_doubles = ((int64_t)GQ_MAXG * pl->gq->maxinst + 3) / 2 + 1;
-  const int64_t need = gl.r_doubles + gl.rfull_doubles + cnt_doubles;
-  int rc;
-  if (phase & TQ_PHASE_FIRST) {
-    rc = ensure_gR(s, need);
-    if (rc) return rc;
-  } else if (s->gR_cap < need) {
-    return set_err(FG_ERR_INVALID, "internal: continued launch without a first one");
-  }
-  rc = ensure_parts(s, 2);
-  if (rc) return rc;
-  rc = timing_begin(s, st);
-  if (rc) return rc;
-  cudaError_t e = gq_launch(gl, *pl->gq, q, v, a, tau, ld_tau, N, s->d_gR, (phase & TQ_PHASE_FIRST) ? 1 : 0, st);
-  rc = timing_end(s, st);
-  if (rc) return rc;
-  if (e != cudaSuccess) return set_err(FG_ERR_CUDA, "gq_launch failed: %s", cudaGetErrorString(e));
-  FG_LAUNCHED();
-  s->rows += N * pl->P.ms;
-  if (!(phase & TQ_PHASE_LAST)) return FG_OK;
-  double* rfull = s->d_gR + gl.r_doubles;
-  unsigned* counters = reinterpret_cast<unsigned*>(rfull + gl.rfull_doubles);
-  // a single launch over few tiles leaves the higher instances at zero: they are not merged
-  e = gq_merge(gl, *pl->gq, s->d_gR, whole ? (N + GQ_S - 1) / GQ_S : 0, counters, rfull, s->d_parts, st);
-  if (e != cudaSuccess) return set_err(FG_ERR_CUDA, "gq_merge failed: %s", cudaGetErrorString(e));
-  FG_LAUNCHED();
-  return merge_parts_into_state(s, 1, m->max_smem, st);
-}
-
 // fifth-generation fused kernel (fg_ringqr.cuh): producer warps write every row group's tile into an L2-resident
 // ring, consumer warps (one TSQR stream per (warp, row group)) pull their blocks with bulk copies.  Factors and
 // merge exactly as generation 4.
@@ -912,11 +777,11 @@ static int launch_rq(fg_state* s, fg_model* m, DevPlan* pl, const double* q, con
     rl.d_tab_g = static_cast<const unsigned char*>(pl->d_rq_tab);
     rl.d_tab_i = reinterpret_cast<const unsigned short*>(static_cast<char*>(pl->d_rq_tab) + nb_g);
   }
-  const bool whole = phase == (TQ_PHASE_FIRST | TQ_PHASE_LAST);
+  const bool whole = phase == (FG_PHASE_FIRST | FG_PHASE_LAST);
   const int64_t cnt_doubles = ((int64_t)GQ_MAXG * prm.gq.maxinst + 3) / 2 + 1;
   const int64_t need = rl.r_doubles + rl.rfull_doubles + cnt_doubles;
   int rc;
-  if (phase & TQ_PHASE_FIRST) {
+  if (phase & FG_PHASE_FIRST) {
     rc = ensure_gR(s, need);
     if (rc) return rc;
   } else if (s->gR_cap < need) {
@@ -943,7 +808,7 @@ static int launch_rq(fg_state* s, fg_model* m, DevPlan* pl, const double* q, con
   unsigned* ctl = reinterpret_cast<unsigned*>(s->d_ring + rl.ring_doubles);
   rc = timing_begin(s, st);
   if (rc) return rc;
-  cudaError_t e = rq_launch(rl, prm, q, v, a, tau, ld_tau, N, s->d_gR, s->d_ring, ctl, (phase & TQ_PHASE_FIRST) ? 1 : 0, st);
+  cudaError_t e = rq_launch(rl, prm, q, v, a, tau, ld_tau, N, s->d_gR, s->d_ring, ctl, (phase & FG_PHASE_FIRST) ? 1 : 0, st);
   rc = timing_end(s, st);
   if (rc) return rc;
   if (e != cudaSuccess) return set_err(FG_ERR_CUDA, "rq_launch failed: %s", cudaGetErrorString(e));
@@ -951,12 +816,10 @@ static int launch_rq(fg_state* s, fg_model* m, DevPlan* pl, const double* q, con
   s->rows += N * pl->P.ms;
   // the flag of every launch is OR-ed into the pinned word by the copy of the last one; a timeout aborts all warps
   FG_CUDA(cudaMemcpyAsync(s->h_rq_err, ctl + 2 * (size_t)prm.ring, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-  if (!(phase & TQ_PHASE_LAST)) return FG_OK;
+  if (!(phase & FG_PHASE_LAST)) return FG_OK;
   double* rfull = s->d_gR + rl.r_doubles;
   unsigned* counters = reinterpret_cast<unsigned*>(rfull + rl.rfull_doubles);
-  GqLaunch gl;
-  gl.smem_merge = rl.smem_merge;
-  e = gq_merge(gl, prm.gq, s->d_gR, whole ? (N + GQ_S - 1) / GQ_S : 0, counters, rfull, s->d_parts, st);
+  e = gq_merge(rl.smem_merge, prm.gq, s->d_gR, whole ? (N + GQ_S - 1) / GQ_S : 0, counters, rfull, s->d_parts, st);
   if (e != cudaSuccess) return set_err(FG_ERR_CUDA, "gq_merge failed: %s", cudaGetErrorString(e));
   FG_LAUNCHED();
   return merge_parts_into_state(s, 1, m->max_smem, st);
@@ -964,7 +827,7 @@ static int launch_rq(fg_state* s, fg_model* m, DevPlan* pl, const double* q, con
 
 static int accumulate_samples_dev(fg_state* s, fg_model* m, const fg_regressor_cfg* cfg, const double* q,
                                   const double* v, const double* a, const double* tau, int64_t ld_tau, int64_t N,
-                                  cudaStream_t st, int phase = TQ_PHASE_FIRST | TQ_PHASE_LAST, bool* chunkable = nullptr) {
+                                  cudaStream_t st, int phase = FG_PHASE_FIRST | FG_PHASE_LAST, bool* chunkable = nullptr) {
   DevPlan* pl = nullptr;
   int rc = get_plan(m, cfg, cfg->col_sel, cfg->n_col_sel, &pl);
   if (rc) return rc;
@@ -988,54 +851,6 @@ static int accumulate_samples_dev(fg_state* s, fg_model* m, const fg_regressor_c
       if (chunkable) *chunkable = true;
       return launch_rq(s, m, pl, q, v, a, tau, ld_tau, N, phase, st);
     }
-  }
-  {
-    const char* e = getenv("FG_USE_GQ");
-    const bool use_gq = !(e && e[0] == '0');
-    if (use_gq && !pl->gq_tried) {
-      pl->gq_tried = true;
-      pl->gq.reset(new GqParams);
-      const char* why = "";
-      pl->gql = gq_build(pl->P, m->joints.data(), pl->rows.data(), pl->cols.data(), m->sm_count, m->max_smem,
-                         pl->gq.get(), &why);
-      if (!pl->gql.ok) pl->gq.reset();
-    }
-    if (use_gq && pl->gql.ok && s->perm.empty()) {
-      if (chunkable) *chunkable = true;
-      return launch_gq(s, m, pl, q, v, a, tau, ld_tau, N, phase, st);
-    }
-  }
-  {
-    const char* e = getenv("FG_USE_TQ");
-    const bool use_tq = !(e && e[0] == '0');
-    if (use_tq && !pl->tq_tried) {
-      pl->tq_tried = true;
-      pl->tq.reset(new TqParams);
-      const char* why = "";
-      pl->tql = tq_build(pl->P, m->joints.data(), pl->rows.data(), pl->cols.data(), m->sm_count, m->max_smem,
-                         pl->tq.get(), &why);
-      if (!pl->tql.ok) pl->tq.reset();
-      else {
-        bool ident = true;
-        for (size_t i = 0; i < pl->tql.perm.size(); ++i) ident = ident && pl->tql.perm[i] == (int)i;
-        if (ident) pl->tql.perm.clear();
-      }
-    }
-    if (use_tq && pl->tql.ok) {
-      if (s->empty) s->perm = pl->tql.perm;
-      if (s->perm == pl->tql.perm) {
-        if (chunkable) *chunkable = true;
-        return launch_tq(s, m, pl, q, v, a, tau, ld_tau, N, phase, st);
-      }
-      // the state already holds a factor in another column order: stay on the path that produced it
-    }
-    if (!s->perm.empty())
-      return set_err(FG_ERR_INVALID, "the state holds a factor in a column order this configuration cannot extend");
-  }
-  {
-    const char* e = getenv("FG_USE_BQ");
-    const bool use_bq = !(e && e[0] == '0');
-    if (use_bq && bq_supported(pl->P)) return launch_bq(s, m, pl, q, v, a, tau, ld_tau, N, st);
   }
   {
     const char* e = getenv("FG_USE_WIDE");
@@ -1071,11 +886,6 @@ static int accumulate_samples_dev(fg_state* s, fg_model* m, const fg_regressor_c
       return FG_OK;
     }
   }
-  if (ms == 6 && nslot <= 3) return launch_fused<3, 6, 4>(s, m, pl, q, v, a, tau, ld_tau, N, st);
-  if (ms == 6 && nslot <= 11) return launch_fused<11, 6, 1>(s, m, pl, q, v, a, tau, ld_tau, N, st);
-  if (ms == 6 && nslot <= 15) return launch_fused<15, 6, 1>(s, m, pl, q, v, a, tau, ld_tau, N, st);
-  if (ms == 8 && nslot <= 5) return launch_fused<5, 8, 2>(s, m, pl, q, v, a, tau, ld_tau, N, st);
-  if (ms == 8 && nslot <= 11) return launch_fused<11, 8, 1>(s, m, pl, q, v, a, tau, ld_tau, N, st);
   return set_err(FG_ERR_UNSUPPORTED,
                  "no fused kernel for %d row blocks x %d columns; materialise W and use fg_state_accumulate_dense",
                  ms, pl->P.ncols);
@@ -1121,9 +931,9 @@ extern "C" int fg_state_accumulate_samples_host(fg_state* s, const fg_model* mc,
   for (int64_t i0 = 0, n = 0; i0 < N; i0 += n, b ^= 1) {
     n = std::min(ramp, N - i0);
     ramp = std::min(chunk, 2 * ramp);
-    int phase = TQ_PHASE_FIRST | TQ_PHASE_LAST;
-    if (i0 == 0) phase = N > n ? TQ_PHASE_FIRST : phase;
-    else if (chunkable) phase = i0 + n >= N ? TQ_PHASE_LAST : 0;
+    int phase = FG_PHASE_FIRST | FG_PHASE_LAST;
+    if (i0 == 0) phase = N > n ? FG_PHASE_FIRST : phase;
+    else if (chunkable) phase = i0 + n >= N ? FG_PHASE_LAST : 0;
     double* base = s->d_stage + (int64_t)b * chunk * per_sample;
     double* dq = base;
     double* dv = dq + chunk * m->nq;
@@ -1222,17 +1032,15 @@ extern "C" int fg_differentiate(const double* q, int64_t N, int32_t nq, int64_t 
 extern "C" int fg_state_export(const fg_state* s, double* packed, void* stream) {
   if (!s || !packed) return set_err(FG_ERR_INVALID, "fg_state_export: null argument");
   cudaStream_t st = (cudaStream_t)stream;
+  // [R dense p1 x p1 | squared column norms p1 | rows | column order p] - everything written by the kernel
   tri_to_dense_kernel<<<64, 256, 0, st>>>(s->d_part, s->p1, packed, (double)s->rows);
   FG_CUDA(cudaGetLastError());
   FG_LAUNCHED();
-  // the column order travels with the factor: p doubles after [R | norms | rows]
-  std::vector<double> pd(s->p);
-  for (int i = 0; i < s->p; ++i) pd[i] = s->perm.empty() ? (double)i : (double)s->perm[i];
-  FG_CUDA(cudaMemcpyAsync(packed + (int64_t)s->p1 * s->p1 + s->p1 + 1, pd.data(), sizeof(double) * s->p,
-                          cudaMemcpyHostToDevice, st));  // pageable source: staged before the call returns
   return FG_OK;
 }
 
+// Merge n packed factors (fg_state_export layout, e.g. the output of an all-gather) into the state.  No host
+// round trip: the row counts are summed on the device and fetched only when somebody asks (fg_state_rows).
 extern "C" int fg_state_merge_packed(fg_state* s, const double* packed, int32_t n, void* stream) {
   if (!s || !packed || n < 1) return set_err(FG_ERR_INVALID, "fg_state_merge_packed: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1241,35 +1049,15 @@ extern "C" int fg_state_merge_packed(fg_state* s, const double* packed, int32_t 
   if (rc) return rc;
   rc = ensure_parts(s, n + 1);
   if (rc) return rc;
-  // row counts and column orders travel behind the factor
-  const int64_t pk = fg_state_packed_doubles(s->p);
-  const int64_t tail0 = (int64_t)s->p1 * s->p1 + s->p1, ntail = 1 + s->p;
-  std::vector<double> tail((size_t)n * ntail);
-  FG_CUDA(cudaMemcpy2DAsync(tail.data(), sizeof(double) * ntail, packed + tail0, sizeof(double) * pk,
-                            sizeof(double) * ntail, n, cudaMemcpyDeviceToHost, st));
-  FG_CUDA(cudaStreamSynchronize(st));
-  std::vector<int> perm(s->p);
-  bool ident = true;
-  for (int i = 0; i < s->p; ++i) {
-    const double v = tail[1 + i];
-    if (!(v >= 0 && v < s->p) || v != (double)(int)v) return set_err(FG_ERR_INVALID, "fg_state_merge_packed: corrupt column order");
-    perm[i] = (int)v;
-    ident = ident && perm[i] == i;
-    for (int k = 1; k < n; ++k)
-      if (tail[(size_t)k * ntail + 1 + i] != v)
-        return set_err(FG_ERR_INVALID, "fg_state_merge_packed: the packed factors use different column orders");
+  if (!s->d_rows_pending) {
+    FG_CUDA(cudaMalloc(&s->d_rows_pending, sizeof(double)));
+    FG_CUDA(cudaMemsetAsync(s->d_rows_pending, 0, sizeof(double), st));
   }
-  if (ident) perm.clear();
-  if (s->empty) s->perm = perm;
-  else if (s->perm != perm)
-    return set_err(FG_ERR_INVALID, "fg_state_merge_packed: the state and the packed factors use different column orders");
-  dense_to_tri_kernel<<<dim3(16, n), 256, 0, st>>>(packed, n, s->p1, s->d_parts);
+  dense_to_tri_kernel<<<dim3(16, n), 256, 0, st>>>(packed, n, s->p1, s->d_parts, s->d_rows_pending);
   FG_CUDA(cudaGetLastError());
   FG_LAUNCHED();
-  rc = merge_parts_into_state(s, n, max_smem, st);
-  if (rc) return rc;
-  for (int k = 0; k < n; ++k) s->rows += (int64_t)tail[(size_t)k * ntail];
-  return FG_OK;
+  s->rows_pending = true;
+  return merge_parts_into_state(s, n, max_smem, st);
 }
 
 // ------------------------------------------------------------------------------------ small stage

@@ -1,5 +1,5 @@
-// fg_gq.h - host interface and launch parameters of the fourth-generation fused kernel
-// (fg_groupqr.cuh): one independent Householder TSQR stream per (warp, row group).
+// fg_gq.h - tables of the row-group TSQR streams (fg_groupqr.cuh: one independent Householder TSQR stream per
+// (warp, row group)) and the host interface of the merge of the per-stream factors.
 //
 // The regressor of row group g (the rows S_g^T B of joint g, regressor.py:49-70 of the reference) is
 // non-zero only in the columns of the bodies that joint supports plus the joint's own Ia/fv/fs/off
@@ -74,33 +74,11 @@ struct GqParams {
   unsigned char gcol[GQ_MAXG][GQ_MAXW]; // local column -> state column
 };
 
-// Which row group a warp works on.  The number of warps per row group is proportional to the group's cost
-// (forward pass + panels + trailing updates), so that all streams finish together; warp gw = blockIdx.x * nw +
-// warp of a full launch reads its row group and its instance index from two small device tables.
-struct GqLaunch {
-  bool ok = false;
-  int nw = 0;             // warps per CTA
-  int sm_count = 0;       // CTAs of a launch
-  int smem = 0;           // accumulate kernel, dynamic shared memory of a CTA (largest row-group mix)
-  int smem_merge = 0;     // merge kernel, per warp
-  int64_t r_doubles = 0;  // scratch doubles of all factors
-  int64_t rfull_doubles = 0;
-  std::vector<unsigned char> tab_g;    // [sm_count * nw] row group of warp gw
-  std::vector<unsigned short> tab_i;   // [sm_count * nw] instance index of warp gw inside its row group
-  const unsigned char* d_tab_g = nullptr;   // device copies (owned by the caller)
-  const unsigned short* d_tab_i = nullptr;
-};
-
-GqLaunch gq_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, const ColDesc* cols, int sm_count,
-                  int max_smem, GqParams* out, const char** why);
-
-// accumulate N samples into the per-instance factors (scratch r_all)
-cudaError_t gq_launch(const GqLaunch& gl, const GqParams& prm, const double* q, const double* v, const double* a,
-                      const double* tau, int64_t ld_tau, int64_t N, double* r_all, int first, cudaStream_t st);
 // tree-merge the per-instance factors of every row group (instances that received no tile are skipped when
 // ntiles_hint > 0), fold the roots into one full factor and write it as a packed part (upper triangle +
-// squared column norms) to part_out.  counters: GQ_MAXG * maxinst + 2 unsigneds.
-cudaError_t gq_merge(const GqLaunch& gl, const GqParams& prm, double* r_all, int64_t ntiles_hint, unsigned* counters,
+// squared column norms) to part_out.  counters: GQ_MAXG * maxinst + 2 unsigneds; smem_merge: dynamic shared memory
+// of a merge warp ((2 max(maxnb, nbf) GQ_BLK + GQ_SCRATCH) doubles).
+cudaError_t gq_merge(int smem_merge, const GqParams& prm, double* r_all, int64_t ntiles_hint, unsigned* counters,
                      double* rfull, double* part_out, cudaStream_t st);
 
 }  // namespace fg

@@ -1,25 +1,18 @@
-// fg_groupqr.cuh - kernel (1)+(2), fourth generation: row-group streams.
+// fg_groupqr.cuh - the row-group TSQR stream: Householder panel, compact-WY factor, DMMA trailing update and
+// the fold of a 32-row (or 64-row) tile into a block-triangular factor, plus the merge of the per-stream factors.
 //
-// What the generation-3 profile showed (profiles/ncu_tq_r01_v3.md): 2 165 warp instructions per
-// sample at an issue rate of 24 %, the largest stall reason by far being the CTA barriers between
-// the one panel warp and its three workers - the panel chain of a tile that mixes all row groups is
-// serial, and every trailing update pays for the fill-in between row groups.
-//
-// This kernel removes both.  Rows of different row groups are different rows of W, hence
-// R = qr([R_0; ...; R_{ms-1}]) with R_g the factor of row group g's own non-zero columns (fg_gq.h).
-// A warp works on ONE row group for the whole launch (the number of warps per row group is proportional to
-// the group's cost, fg_gq.h) and, per tile of 32 samples:
-//   1. runs the forward pass with one sample per lane and writes that row group's entries
-//      s_g^T B_b (pinocchio::computeJointTorqueRegressor, reference call sites regressor.py:49,93)
-//      into its private 32 x w_g shared-memory tile,
-//   2. folds the tile into its private block-triangular R_g (L2-resident scratch) by a blocked
-//      Householder QR: 8-column panels with one row per lane, compact-WY T, DMMA trailing updates
-//      whose reflector fragments stay in registers for the whole panel.
-// No warp ever waits for another one: a CTA is a single warp, there is no barrier in the kernel.
-// The per-warp factors are merged by gq_merge_kernel (pairwise tree per row group driven by arrival
-// counters, then the ms roots are folded into the full factor in state column order).
+// Rows of different row groups are different rows of W, hence R = qr([R_0; ...; R_{ms-1}]) with R_g the factor of
+// row group g's own non-zero columns (fg_gq.h).  A warp works on ONE row group for the whole launch and folds
+// 32-sample tiles of that group's entries (pinocchio::computeJointTorqueRegressor rows, reference call sites
+// regressor.py:49,93) into its private block-triangular R_g (L2-resident scratch) by a blocked Householder QR:
+// 8-column panels with one row per lane, compact-WY T, DMMA trailing updates whose reflector fragments stay in
+// registers for the whole panel.  No warp ever waits for another one.  The tiles come from the producers of
+// fg_ringqr.cuh (generation 5); generation 4 generated them inside the stream (one forward pass per row group
+// and tile - 39 % of the kernel, profiles/ncu_gq_r01_v4i.md).
+// The per-warp factors are merged by gq_merge_kernel (pairwise tree per row group driven by arrival counters,
+// then the ms roots are folded into the full factor in state column order).
 #pragma once
-#include "fg_tileqr.cuh"
+#include "fg_tile.cuh"
 #include "fg_gq.h"
 
 namespace fg {
@@ -322,222 +315,7 @@ __device__ __forceinline__ void gq_fold(double* tile, int nb, double* Rg, int k0
   gq_fold_h<CG, RPL, GqNoHook>(tile, nb, Rg, k0, scr, o, lane, nh);
 }
 
-// ---------------------------------------------------------------------------------------------
-// regressor entries of (row group g, body): value[k] = s^T B[:, k] with s = [sl; sa] the motion axis of the
-// row group expressed in the body's frame (see tq_emit).
-// ed = (first local slot << 10) | mask of the generated pinocchio parameters: the generated entries of one
-// body occupy consecutive local columns in parameter order.
-__device__ __forceinline__ void gq_emit(double* tile, int ed, const double* sl, const double* sa, const double* om,
-                                        const double* al, const double* ap, bool valid, int lane) {
-  double val[10];
-  val[0] = sl[0] * ap[0] + sl[1] * ap[1] + sl[2] * ap[2];
-  const double ww = om[0] * om[0] + om[1] * om[1] + om[2] * om[2];
-  const double so = sl[0] * om[0] + sl[1] * om[1] + sl[2] * om[2];
-  double x1[3], x2[3], h[3];
-  cross3(sl, al, x1);
-  cross3(ap, sa, x2);
-  for (int j = 0; j < 3; ++j) val[1 + j] = x1[j] + so * om[j] - ww * sl[j] + x2[j];
-  cross3(sa, om, h);
-  val[4] = sa[0] * al[0] + h[0] * om[0];                                   // Ixx
-  val[5] = sa[0] * al[1] + sa[1] * al[0] + h[0] * om[1] + h[1] * om[0];   // Ixy
-  val[6] = sa[1] * al[1] + h[1] * om[1];                                   // Iyy
-  val[7] = sa[0] * al[2] + sa[2] * al[0] + h[0] * om[2] + h[2] * om[0];   // Ixz
-  val[8] = sa[1] * al[2] + sa[2] * al[1] + h[1] * om[2] + h[2] * om[1];   // Iyz
-  val[9] = sa[2] * al[2] + h[2] * om[2];                                   // Izz
-  int slot = ed >> 10;
-#pragma unroll
-  for (int k = 0; k < 10; ++k) {
-    if ((ed >> k) & 1) {  // uniform
-      if (valid) tile[(slot >> 3) * GQ_BLK + tq_idx(slot & 7, lane)] = val[k];
-      ++slot;
-    }
-  }
-}
-
-// Forward pass of one sample per lane, emitting the entries of row group g.  S: the generator tables in
-// shared memory.  The (q, dq, ddq) entries of a joint are requested two joints ahead.
-static __device__ __forceinline__ void gq_generate(const GqParams& P, const GqGen& S, int g, double* tile,
-                                                   const double* __restrict__ q, const double* __restrict__ qd,
-                                                   const double* __restrict__ qdd, const double* __restrict__ tau,
-                                                   int64_t ld_tau, int64_t s0, int64_t N, int lane) {
-  const int64_t smp = s0 + lane;
-  const bool valid = smp < N;
-  const int64_t sc = valid ? smp : N - 1;
-  const double* qs = q + sc * P.nq;
-  const double* vs = qd + sc * P.nv;
-  const double* as = qdd + sc * P.nv;
-  const GqGroup& G = S.grp[g];
-  const int nproc = P.nproc;
-  double sx[6] = {0, 0, 0, 0, 0, 0};  // motion axis of the row group in the frame of the joint being walked
-  double v[6] = {0, 0, 0, 0, 0, 0}, a[6] = {0, 0, 0, 0, 0, 0};
-  // one-joint-ahead input queue (a deeper queue rotated by register moves adds no cover: the move is the first
-  // touch of the load, measured)
-  double nq0 = __ldg(qs + S.pj[0].idx_q), nv0 = __ldg(vs + S.pj[0].idx_v), na0 = __ldg(as + S.pj[0].idx_v);
-  // rhs entry and the row group's own (dq, ddq): requested while the LAST joint is walked, consumed after the walk
-  double taug = 0.0, vg = 0.0, ag = 0.0;
-  const int vidx_g = S.pj[G.tjoint].idx_v;
-  for (int t = 0; t < nproc; ++t) {
-    const DevJoint& jt = S.pj[t];
-    const double cq0 = nq0, cv0 = nv0, ca0 = na0;
-    if (t + 1 < nproc) {
-      const DevJoint& jn = S.pj[t + 1];
-      nq0 = __ldg(qs + jn.idx_q); nv0 = __ldg(vs + jn.idx_v); na0 = __ldg(as + jn.idx_v);
-    }
-    if (jt.parent == 0) {  // restart from the universe (the host only admits chains hanging off it)
-      for (int k = 0; k < 6; ++k) v[k] = 0.0;
-      a[0] = -P.gravity[0]; a[1] = -P.gravity[1]; a[2] = -P.gravity[2];
-      a[3] = a[4] = a[5] = 0.0;
-    }
-    double Rj[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, pj[3] = {0, 0, 0};
-    double vj[6] = {0, 0, 0, 0, 0, 0}, aj[6] = {0, 0, 0, 0, 0, 0};
-    const int iq = jt.idx_q, iv = jt.idx_v;
-    const double ax[3] = {jt.axis[0], jt.axis[1], jt.axis[2]};
-    if (jt.jtype == 1) {
-      double s, c;
-      sincos(cq0, &s, &c);
-      axis_rot(ax, c, s, Rj);
-      for (int k = 0; k < 3; ++k) { vj[3 + k] = ax[k] * cv0; aj[3 + k] = ax[k] * ca0; }
-    } else if (jt.jtype == 2) {
-      axis_rot(ax, cq0, __ldg(qs + iq + 1), Rj);
-      for (int k = 0; k < 3; ++k) { vj[3 + k] = ax[k] * cv0; aj[3 + k] = ax[k] * ca0; }
-    } else if (jt.jtype == 3) {
-      for (int k = 0; k < 3; ++k) { pj[k] = ax[k] * cq0; vj[k] = ax[k] * cv0; aj[k] = ax[k] * ca0; }
-    } else {  // free-flyer
-      quat_rot(__ldg(qs + iq + 3), __ldg(qs + iq + 4), __ldg(qs + iq + 5), __ldg(qs + iq + 6), Rj);
-      for (int k = 0; k < 3; ++k) pj[k] = __ldg(qs + iq + k);
-      for (int k = 0; k < 6; ++k) { vj[k] = __ldg(vs + iv + k); aj[k] = __ldg(as + iv + k); }
-    }
-    // liMi = placement * Mj
-    double R[9], p[3];
-    for (int r = 0; r < 3; ++r) {
-      const double m0 = jt.plcR[3 * r], m1 = jt.plcR[3 * r + 1], m2 = jt.plcR[3 * r + 2];
-      for (int c = 0; c < 3; ++c) R[3 * r + c] = m0 * Rj[c] + m1 * Rj[3 + c] + m2 * Rj[6 + c];
-      p[r] = m0 * pj[0] + m1 * pj[1] + m2 * pj[2] + jt.plcp[r];
-    }
-    // v = vJ + liMi.actInv(v_parent);  a = v x vJ + S qdd + liMi.actInv(a_parent)
-    double vn[6], an[6], tt[3];
-    cross3(p, v + 3, tt);
-    for (int k = 0; k < 3; ++k) tt[k] = v[k] - tt[k];
-    for (int k = 0; k < 3; ++k) {
-      vn[k] = vj[k] + R[k] * tt[0] + R[3 + k] * tt[1] + R[6 + k] * tt[2];
-      vn[3 + k] = vj[3 + k] + R[k] * v[3] + R[3 + k] * v[4] + R[6 + k] * v[5];
-    }
-    double l1[3], l2[3], l3[3];
-    cross3(vn + 3, vj, l1);
-    cross3(vn, vj + 3, l2);
-    cross3(vn + 3, vj + 3, l3);
-    cross3(p, a + 3, tt);
-    for (int k = 0; k < 3; ++k) tt[k] = a[k] - tt[k];
-    for (int k = 0; k < 3; ++k) {
-      an[k] = l1[k] + l2[k] + aj[k] + R[k] * tt[0] + R[3 + k] * tt[1] + R[6 + k] * tt[2];
-      an[3 + k] = l3[k] + aj[3 + k] + R[k] * a[3] + R[3 + k] * a[4] + R[6 + k] * a[5];
-    }
-    for (int k = 0; k < 6; ++k) { v[k] = vn[k]; a[k] = an[k]; }
-    // the row group's motion axis: its own joint's axis at that joint, transported down the chain afterwards
-    // (liMi.actInv: the same transform the velocity takes) - the product of these transports is oM_body^-1 oM_joint
-    if (t == nproc - 1) {
-      if (valid && tau != nullptr) taug = __ldg(tau + (int64_t)g * ld_tau + smp);
-      vg = __ldg(vs + vidx_g);
-      ag = __ldg(as + vidx_g);
-    }
-    if (t == G.tjoint) {
-      for (int k = 0; k < 6; ++k) sx[k] = G.S[k];
-    } else if (t > G.tjoint) {
-      cross3(p, sx + 3, tt);
-      for (int k = 0; k < 3; ++k) tt[k] = sx[k] - tt[k];
-      double sn[6];
-      for (int k = 0; k < 3; ++k) {
-        sn[k] = R[k] * tt[0] + R[3 + k] * tt[1] + R[6 + k] * tt[2];
-        sn[3 + k] = R[k] * sx[3] + R[3 + k] * sx[4] + R[6 + k] * sx[5];
-      }
-      for (int k = 0; k < 6; ++k) sx[k] = sn[k];
-    }
-    const int ed = S.emit[g][t];
-    if (ed) {
-      double ap[3];
-      cross3(v + 3, v, ap);  // classical acceleration a' = a_lin + w x v_lin
-      for (int k = 0; k < 3; ++k) ap[k] += a[k];
-      gq_emit(tile, ed, sx, sx + 3, v + 3, a + 3, ap, valid, lane);
-    }
-  }
-  // columns read straight off the inputs
-  for (int t = 0; t < G.nsimple; ++t) {
-    const GqSimple s1 = S.simple[g][t];
-    const int ix = (s1.slot >> 3) * GQ_BLK + tq_idx(s1.slot & 7, lane);
-    double val = 0.0;
-    if (s1.kind == COL_RHS) {
-      val = taug;
-    } else if (s1.kind == COL_EXTRA) {
-      const bool own = s1.vidx == vidx_g;  // uniform
-      const double vv = own ? vg : __ldg(vs + s1.vidx), aa = own ? ag : __ldg(as + s1.vidx);
-      val = s1.src == SRC_QDD ? aa : (s1.src == SRC_QD ? vv : (s1.src == SRC_SIGN_QD ? sgn(vv) : 1.0));
-    } else {
-      // add_coupling_TX40 (regressor.py:216-225): row block 4 <- [a5, v5, sign(v4+v5)], 5 <- [a4, v4, sign(v4+v5)]
-      const double v4 = __ldg(vs + 4), v5 = __ldg(vs + 5), a4 = __ldg(as + 4), a5 = __ldg(as + 5);
-      const double sg = sgn(v4 + v5);
-      val = G.rowblock == 4 ? (s1.src == 0 ? a5 : (s1.src == 1 ? v5 : sg)) : (s1.src == 0 ? a4 : (s1.src == 1 ? v4 : sg));
-    }
-    tile[ix] = valid ? val : 0.0;
-  }
-}
-
-#ifndef FG_GQ_DEVICE_ONLY  // fg_rq.cu reuses the device functions above, not the generation-4 kernels
-// ---------------------------------------------------------------------------------------------
-// One CTA per SM, blockDim.x / 32 independent warps; the only CTA-wide synchronisation is the one after the
-// generator tables have been copied to shared memory.  Warp gw = blockIdx.x * nw + warp works on row group
-// tab_g[gw] as its instance tab_i[gw]: it folds the tiles inst, inst + ninst, ... into its own factor.  The
-// shared-memory tile of a warp has exactly the width of its row group.
-__global__ void __launch_bounds__(GQ_MAXNW * 32, 1)
-gq_accumulate_kernel(const __grid_constant__ GqParams P, const unsigned char* __restrict__ tab_g,
-                     const unsigned short* __restrict__ tab_i, const double* __restrict__ q,
-                     const double* __restrict__ qd, const double* __restrict__ qdd, const double* __restrict__ tau,
-                     int64_t ld_tau, int64_t N, double* __restrict__ r_all, int first) {
-  extern __shared__ __align__(16) double gq_smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  GqGen* Sg = reinterpret_cast<GqGen*>(gq_smem);
-  {
-    const int* src = reinterpret_cast<const int*>(&P.gen);
-    int* dst = reinterpret_cast<int*>(Sg);
-    for (int i = threadIdx.x; i < (int)(sizeof(GqGen) / 4); i += blockDim.x) dst[i] = src[i];
-  }
-  __syncthreads();
-  const GqGen& S = *Sg;
-  const int gw = blockIdx.x * nw + warp;
-  const int g = tab_g[gw], inst = tab_i[gw];
-  int boff = 0;
-  for (int w = 0; w < warp; ++w) boff += S.grp[tab_g[blockIdx.x * nw + w]].nb;
-  double* tile = gq_smem + GQ_GEN_DOUBLES + (size_t)boff * GQ_BLK + (size_t)warp * GQ_SCRATCH;
-  const GqGroup& G = S.grp[g];
-  const int nb = G.nb, ninst = G.ninst;
-  double* scr = tile + nb * GQ_BLK;
-  double* Rg = r_all + (size_t)G.r_off + (size_t)inst * G.r_size;
-  if (first) {
-    for (int i = lane; i < G.r_size; i += 32) Rg[i] = 0.0;
-    __syncwarp();
-  }
-  GqOffs offs;
-  gq_make_offs(offs, lane);
-  const int64_t ntiles = (N + GQ_S - 1) / GQ_S;
-  for (int64_t tl = inst; tl < ntiles; tl += ninst) {
-    if (tl + ninst < ntiles) {  // pull the next tile's inputs into L2 while this one is folded
-      const int64_t sn = (tl + ninst) * GQ_S + lane;
-      if (sn < N) {
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(q + sn * P.nq));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(qd + sn * P.nv));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(qdd + sn * P.nv));
-      }
-    }
-    {
-      double2* t2 = reinterpret_cast<double2*>(tile);
-      for (int i = lane; i < nb * (GQ_BLK / 2); i += 32) t2[i] = make_double2(0.0, 0.0);
-    }
-    __syncwarp();
-    gq_generate(P, S, g, tile, q, qd, qdd, tau, ld_tau, tl * GQ_S, N, lane);
-    __syncwarp();
-    gq_fold<false, 1>(tile, nb, Rg, 0, scr, offs, lane);
-  }
-}
-
+#ifndef FG_GQ_DEVICE_ONLY  // fg_rq.cu reuses the device functions above, not the merge kernel
 // ---------------------------------------------------------------------------------------------
 // Merge of the per-warp factors.  One warp per (row group g, pair of instances).  A warp folds instance
 // i + stride into instance i, then climbs: at every internal node the first of the two children to arrive

@@ -1,7 +1,6 @@
 // fg_kernels.cuh - the __global__ kernels of the identification path (sm_100a, fp64).
 //
 //   regressor_materialize_kernel : kernel (1) alone, W written to HBM in the reference layout
-//   accumulate_samples_kernel    : kernel (1) fused into the TSQR fold (W never leaves registers)
 //   accumulate_dense_kernel      : TSQR fold of a dense matrix already in HBM
 //   merge_pairs_kernel           : pairwise merge of partial R factors (tree reduction step)
 //   small_qr_kernel / solve      : kernel (3), the N-independent stage on the (p+1)^2 factor
@@ -176,96 +175,6 @@ __device__ inline double* warpR_fn(int w, void* ctx) {
   return reinterpret_cast<double*>(c->base + (size_t)w * c->stride);
 }
 
-// ------------------------------------------------------------------ kernel (1)+(2) fused
-// Persistent grid, one warp = one TSQR stream.  Per tile of S samples:
-//   lanes 0..S-1: forward kinematics into shared memory;
-//   all lanes:    generate the entries of their own columns straight into registers
-//                 (B[row][slot]), accumulate exact column norms, Householder-fold into the
-//                 stream's packed R (shared memory when it fits, else an HBM scratch slot).
-// At the end the CTA's streams are merged and written to parts[blockIdx.x].
-template <int NSLOT, int MS, int S>
-__global__ void __launch_bounds__(256, 1)
-accumulate_samples_kernel(DevPlanPtrs pp, const double* __restrict__ q, const double* __restrict__ qd,
-                          const double* __restrict__ qdd, const double* __restrict__ tau, int64_t ld_tau, int64_t N,
-                          double* __restrict__ parts, double* __restrict__ gR /* global R slots or null */,
-                          int use_structure) {
-  constexpr int TR = MS * S;
-  constexpr int TRM = TR >= 8 ? TR : 8;  // tile height used by the factor merges
-  extern __shared__ __align__(16) unsigned char smem[];
-  const Plan P0 = *pp.plan;
-  const int nwarps = blockDim.x / 32;
-  const bool R_in_smem = gR == nullptr;
-  const SmemLayout L = make_layout(P0.nj, P0.ms, P0.p1, P0.nv, S, TRM, nwarps, R_in_smem, true);
-  load_plan_to_smem(smem, L, pp);
-  const Plan& P = *reinterpret_cast<const Plan*>(smem + L.off_plan);
-  const DevJoint* J = reinterpret_cast<const DevJoint*>(smem + L.off_joints);
-  const RowDesc* rows = reinterpret_cast<const RowDesc*>(smem + L.off_rows);
-  const int* nact = use_structure ? reinterpret_cast<const int*>(smem + L.off_nact) : nullptr;
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  unsigned char* wb = smem + L.off_warp0 + (size_t)warp * L.warp_stride;
-  double* fw = reinterpret_cast<double*>(wb + L.w_fw);
-  double* vs = reinterpret_cast<double*>(wb + L.w_vs);
-  double* as = reinterpret_cast<double*>(wb + L.w_as);
-  double* xs = reinterpret_cast<double*>(wb + L.w_xs);
-  const int p1 = P.p1;
-  const int ntri = p1 * (p1 + 1) / 2;
-  const size_t gstride = (size_t)ntri * 8;
-  double* Rt = R_in_smem ? reinterpret_cast<double*>(wb + L.w_R)
-                         : gR + ((size_t)blockIdx.x * nwarps + warp) * ntri;
-  for (int i = lane; i < ntri; i += 32) Rt[i] = 0.0;
-
-  ColDesc cd[NSLOT];
-  uint64_t anc[NSLOT];
-  double csq[NSLOT];
-#pragma unroll
-  for (int t = 0; t < NSLOT; ++t) {
-    const int col = lane + 32 * t;
-    cd[t].kind = COL_ZERO; cd[t].body = 0; cd[t].k = 0; cd[t].vidx = 0; cd[t].grp = -2;
-    anc[t] = 0;
-    csq[t] = 0.0;
-    if (col < p1) {
-      cd[t] = pp.cols[col];
-      anc[t] = col_ancmask(cd[t]);
-    }
-  }
-  __syncwarp();
-
-  const int64_t ntiles = (N + S - 1) / S;
-  for (int64_t tile = (int64_t)blockIdx.x * nwarps + warp; tile < ntiles; tile += (int64_t)gridDim.x * nwarps) {
-    const int64_t s0 = tile * S;
-    if (lane < S) {
-      const int64_t smp = s0 + lane;
-      const bool valid = smp < N;
-      const int64_t sc = valid ? smp : 0;
-      forward_sample(P, J, q + sc * P.nq, qd + sc * P.nv, qdd + sc * P.nv, fw + (size_t)lane * P.nj * FW_STRIDE,
-                     vs + lane * P.nv, as + lane * P.nv, valid);
-    }
-    __syncwarp();
-    double B[TR][NSLOT];
-#pragma unroll
-    for (int t = 0; t < NSLOT; ++t) {
-      double out[TR];
-      gen_column<MS, S>(P, J, rows, cd[t], anc[t], fw, vs, as, tau, ld_tau, s0, N, out);
-#pragma unroll
-      for (int r = 0; r < TR; ++r) {
-        B[r][t] = out[r];
-        csq[t] = fma(out[r], out[r], csq[t]);
-      }
-    }
-    __syncwarp();
-    fold_tile<NSLOT, TR, S>(B, Rt, p1, xs, nact, 0, lane);
-    __syncwarp();
-  }
-
-  // ---- CTA-level merge of the warp streams
-  __shared__ double csq_buf[8 * 32 * NSLOT];
-  WarpRCtx ctx;
-  if (R_in_smem) { ctx.base = smem + L.off_warp0 + L.w_R; ctx.stride = (size_t)L.warp_stride; }
-  else { ctx.base = reinterpret_cast<unsigned char*>(gR + (size_t)blockIdx.x * nwarps * ntri); ctx.stride = gstride; }
-  __threadfence_block();
-  cta_merge_and_store<NSLOT, TRM>(Rt, warpR_fn, &ctx, csq, csq_buf, p1, xs, parts, lane, warp, nwarps);
-}
-
 // ------------------------------------------------------------------ dense TSQR fold
 // W is rows x p (ld = ldw) in HBM, tau optional.  Each warp streams tiles of TR rows:
 // B[r][t] = W[row0 + r][lane + 32 t] (coalesced), last column = tau.
@@ -358,11 +267,15 @@ __global__ void tri_to_dense_kernel(const double* __restrict__ part, int p1, dou
   if (blockIdx.x == 0) {
     for (int i = threadIdx.x; i < p1; i += blockDim.x) dense[(size_t)p1 * p1 + i] = part[ntri + i];
     if (threadIdx.x == 0) dense[(size_t)p1 * p1 + p1] = nrows_as_double;
+    // column order of the factor (always the caller's order since generation 5; kept in the exchange format)
+    for (int i = threadIdx.x; i < p1 - 1; i += blockDim.x) dense[(size_t)p1 * p1 + p1 + 1 + i] = (double)i;
   }
 }
 
-// packed exchange buffers (dense square + norms + rows) -> parts (packed triangles)
-__global__ void dense_to_tri_kernel(const double* __restrict__ packed, int n, int p1, double* __restrict__ parts) {
+// packed exchange buffers (dense square + norms + rows + column order) -> parts (packed triangles); the row
+// counts of the n buffers are added to *rows_acc
+__global__ void dense_to_tri_kernel(const double* __restrict__ packed, int n, int p1, double* __restrict__ parts,
+                                    double* __restrict__ rows_acc) {
   const int ntri = p1 * (p1 + 1) / 2;
   const int64_t pk = (int64_t)p1 * p1 + 2 * (int64_t)p1;  // fg_state_packed_doubles(p1 - 1)
   for (int k = blockIdx.y; k < n; k += gridDim.y) {
@@ -374,6 +287,11 @@ __global__ void dense_to_tri_kernel(const double* __restrict__ packed, int n, in
     }
     if (blockIdx.x == 0)
       for (int i = threadIdx.x; i < p1; i += blockDim.x) dst[ntri + i] = src[(size_t)p1 * p1 + i];
+  }
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    double acc = 0.0;
+    for (int k = 0; k < n; ++k) acc += packed[(size_t)k * pk + (size_t)p1 * p1 + p1];
+    *rows_acc += acc;
   }
 }
 

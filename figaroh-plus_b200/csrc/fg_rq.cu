@@ -219,7 +219,7 @@ RqLaunch rq_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, co
     cost[g] = 250.0 + 1070.0 * G.nb + 100.0 * G.nb * (G.nb - 1) / 2;
     csum += cost[g];
   }
-  const double pcost = 400.0 + 420.0 * nproc + 45.0 * n_transports + 190.0 * n_emits + 25.0 * n_simple + 60.0 * (nops - nproc);
+  const double pcost = 1.07 * (400.0 + 420.0 * nproc + 45.0 * n_transports + 190.0 * n_emits + 25.0 * n_simple + 60.0 * (nops - nproc));  // 1.07: A/B on UR10 (26 producer SMs of 148)
   rl.sm_count = std::max(1, sm_count);
   const int gen_doubles = GQ_GEN_DOUBLES + (int)(sizeof(RqOp) * RQ_MAXOPS / 8);
   // Roles are assigned per CTA (= per SM): a producer SM runs only the generator, a consumer SM only the fold, so

@@ -48,12 +48,14 @@ __device__ __forceinline__ double wd_rcp(double x) {
   return fma(y, e, y);
 }
 
-// Householder reflector of [alpha; x] (LAPACK dlarfg convention: beta = -sign(alpha) norm, v = x / (alpha - beta),
-// tau = (beta - alpha) / beta), published for the other threads: xb[0..TR) = x (not normalised), xb[TRP] = 1 / (alpha
-// - beta), xb[TRP + 1] = tau (0: H = I).  Returns beta (the new diagonal entry of R) or alpha when H = I.
+// What the owner of a column publishes for the other threads: xb[0..TR) = x (the column below R's diagonal, not
+// normalised), xb[TRP] = alpha (the diagonal entry of R), xb[TRP + 1] = sigma = |x|^2.  EVERY thread derives the
+// reflector scalars from (alpha, sigma) itself (LAPACK dlarfg convention: beta = -sign(alpha) sqrt(alpha^2 + sigma),
+// v = x / (alpha - beta), tau = (beta - alpha) / beta) while its dot products are in flight, so the square root and
+// the reciprocal are not on the owner's serial path (profiles/ncu_wide_r02_v2.md: 48 % of the samples waited at the
+// barrier for the owner when it computed them).
 template <int TR, int NSLOT>
-__device__ __forceinline__ void wide_publish(const double (&B)[TR][NSLOT], int sc, double alpha, double* xb,
-                                             double* Rdiag) {
+__device__ __forceinline__ void wide_publish(const double (&B)[TR][NSLOT], int sc, double alpha, double* xb) {
   constexpr int TRP = ((TR + 7) / 8) * 8;
   double sg[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
@@ -66,74 +68,85 @@ __device__ __forceinline__ void wide_publish(const double (&B)[TR][NSLOT], int s
         sg[r & 3] = fma(x, x, sg[r & 3]);
       }
     }
-  const double sigma = (sg[0] + sg[1]) + (sg[2] + sg[3]);
-  double inv = 0.0, tauh = 0.0;
-  const double mu = fma(alpha, alpha, sigma);
-  if (sigma != 0.0 && mu > 1e-280) {  // else H = I (dlarfg with xnorm == 0)
-    double nrm, rs;
-    wd_sqrt_rsqrt(mu, nrm, rs);
-    const double beta = alpha >= 0.0 ? -nrm : nrm;
-    const double den = alpha - beta;
-    inv = wd_rcp(den);
-    tauh = fabs(den) * rs;  // (beta - alpha) / beta
-    __stcg(Rdiag, beta);
-  }
-  xb[TRP] = inv;
-  xb[TRP + 1] = tauh;
+  xb[TRP] = alpha;
+  xb[TRP + 1] = (sg[0] + sg[1]) + (sg[2] + sg[3]);
 }
 
-// Apply the published reflector to the thread's column of slot s (col > c): dot product, new R entry, rank-1 update.
-template <int TR, int NSLOT, int S_>
+// Apply the published reflector to the thread's column of slot S_ (col > c): dot product, new R entry, rank-1
+// update.  PUB: this is the owner's pass over the NEXT column - the updated column and its squared norm go to xn.
+template <int TR, int NSLOT, int S_, bool PUB>
 __device__ __forceinline__ void wide_apply_slot(double (&B)[TR][NSLOT], const double* xb, double inv, double tauh,
-                                                double rho, double* Rdst, bool active) {
-  double d[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-  for (int r0 = 0; r0 < TR; r0 += 4) {
-    const double2 t0 = *reinterpret_cast<const double2*>(xb + r0);
-    const double2 t1 = *reinterpret_cast<const double2*>(xb + r0 + 2);
-    if (r0 < TR) d[0] = fma(t0.x, B[r0 < TR ? r0 : 0][S_], d[0]);
-    if (r0 + 1 < TR) d[1] = fma(t0.y, B[r0 + 1 < TR ? r0 + 1 : 0][S_], d[1]);
-    if (r0 + 2 < TR) d[2] = fma(t1.x, B[r0 + 2 < TR ? r0 + 2 : 0][S_], d[2]);
-    if (r0 + 3 < TR) d[3] = fma(t1.y, B[r0 + 3 < TR ? r0 + 3 : 0][S_], d[3]);
-  }
-  const double dd = (d[0] + d[1]) + (d[2] + d[3]);
-  const double sdot = fma(dd, inv, rho);  // w^T [rho; b],  w = [1; x * inv]
+                                                double rho, double* Rdst, bool active, double* xn, double alpha_n) {
+  constexpr int TRP = ((TR + 7) / 8) * 8;
   double gco = 0.0;
-  if (active) {
-    __stcg(Rdst, fma(-tauh, sdot, rho));
-    gco = tauh * sdot * inv;
-  }
+  if (tauh != 0.0) {  // uniform
+    double d[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-  for (int r0 = 0; r0 < TR; r0 += 4) {
-    const double2 t0 = *reinterpret_cast<const double2*>(xb + r0);
-    const double2 t1 = *reinterpret_cast<const double2*>(xb + r0 + 2);
-    if (r0 < TR) B[r0 < TR ? r0 : 0][S_] = fma(-gco, t0.x, B[r0 < TR ? r0 : 0][S_]);
-    if (r0 + 1 < TR) B[r0 + 1 < TR ? r0 + 1 : 0][S_] = fma(-gco, t0.y, B[r0 + 1 < TR ? r0 + 1 : 0][S_]);
-    if (r0 + 2 < TR) B[r0 + 2 < TR ? r0 + 2 : 0][S_] = fma(-gco, t1.x, B[r0 + 2 < TR ? r0 + 2 : 0][S_]);
-    if (r0 + 3 < TR) B[r0 + 3 < TR ? r0 + 3 : 0][S_] = fma(-gco, t1.y, B[r0 + 3 < TR ? r0 + 3 : 0][S_]);
+    for (int r0 = 0; r0 < TR; r0 += 4) {
+      const double2 t0 = *reinterpret_cast<const double2*>(xb + r0);
+      const double2 t1 = *reinterpret_cast<const double2*>(xb + r0 + 2);
+      if (r0 < TR) d[0] = fma(t0.x, B[r0 < TR ? r0 : 0][S_], d[0]);
+      if (r0 + 1 < TR) d[1] = fma(t0.y, B[r0 + 1 < TR ? r0 + 1 : 0][S_], d[1]);
+      if (r0 + 2 < TR) d[2] = fma(t1.x, B[r0 + 2 < TR ? r0 + 2 : 0][S_], d[2]);
+      if (r0 + 3 < TR) d[3] = fma(t1.y, B[r0 + 3 < TR ? r0 + 3 : 0][S_], d[3]);
+    }
+    const double dd = (d[0] + d[1]) + (d[2] + d[3]);
+    const double sdot = fma(dd, inv, rho);  // w^T [rho; b],  w = [1; x * inv]
+    if (active) {
+      __stcg(Rdst, fma(-tauh, sdot, rho));
+      gco = tauh * sdot * inv;
+    }
+  }
+  double sg[4] = {0.0, 0.0, 0.0, 0.0};
+  if (tauh != 0.0 || PUB) {
+#pragma unroll
+    for (int r0 = 0; r0 < TR; r0 += 4) {
+      const double2 t0 = *reinterpret_cast<const double2*>(xb + r0);
+      const double2 t1 = *reinterpret_cast<const double2*>(xb + r0 + 2);
+      const double tv[4] = {t0.x, t0.y, t1.x, t1.y};
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (r0 + k < TR) {
+          const double nb = fma(-gco, tv[k], B[r0 + k < TR ? r0 + k : 0][S_]);
+          B[r0 + k < TR ? r0 + k : 0][S_] = nb;
+          if (PUB) {
+            xn[r0 + k] = nb;
+            sg[k] = fma(nb, nb, sg[k]);
+          }
+        }
+    }
+  }
+  if (PUB) {
+    xn[TRP] = alpha_n;
+    xn[TRP + 1] = (sg[0] + sg[1]) + (sg[2] + sg[3]);
   }
 }
 
+// all live slots of the thread; `pub_slot`: the slot of column c + 1 if this thread owns it (else -1)
 template <int TR, int NSLOT, int S_>
 __device__ __forceinline__ void wide_apply_slots(double (&B)[TR][NSLOT], const double* xb, double inv, double tauh,
-                                                 const double (&rho)[NSLOT], double* Rrow, int c, int p1, int tid,
-                                                 int only, int skip) {
+                                                 const double (&rho)[NSLOT], const double (&rho_n)[NSLOT], double* Rrow,
+                                                 int c, int p1, int tid, int pub_slot, double* xn) {
   if constexpr (S_ < NSLOT) {
     const int col = tid + WD_THREADS * S_;
     // warp-uniform: a slot whose 32 columns of this warp are all <= c has retired
     const bool warp_live = (col | 31) > c;
-    if (warp_live && (only < 0 || only == S_) && skip != S_)
-      wide_apply_slot<TR, NSLOT, S_>(B, xb, inv, tauh, rho[S_], Rrow + col - c, col > c && col < p1);
-    wide_apply_slots<TR, NSLOT, S_ + 1>(B, xb, inv, tauh, rho, Rrow, c, p1, tid, only, skip);
+    if (warp_live) {
+      if (pub_slot == S_)
+        wide_apply_slot<TR, NSLOT, S_, true>(B, xb, inv, tauh, rho[S_], Rrow + col - c, col > c && col < p1, xn, rho_n[S_]);
+      else
+        wide_apply_slot<TR, NSLOT, S_, false>(B, xb, inv, tauh, rho[S_], Rrow + col - c, col > c && col < p1, nullptr, 0.0);
+    }
+    wide_apply_slots<TR, NSLOT, S_ + 1>(B, xb, inv, tauh, rho, rho_n, Rrow, c, p1, tid, pub_slot, xn);
   }
 }
 
 // Fold the register tile B (TR rows; thread `tid` owns columns tid + 256 s) into the packed upper-triangular
 // factor Rt (p1 columns, global memory, private to this CTA).  Columns < c_begin of the tile are zero.
 // xs: 2 * (ceil8(TR) + 4) doubles of shared memory.
-// Step c applies reflector c (published in xs[c & 1]) to every live column.  LOOK-AHEAD: the owner of column c + 1
-// updates that column first, takes its reflector and publishes it into the other buffer before finishing its
-// own step, so the one barrier per step never waits for the square root.
+// Step c applies reflector c (published in xs[c & 1]) to every live column.  LOOK-AHEAD: while it updates its
+// column c + 1, the owner of that column writes the updated values and their squared norm into the other buffer,
+// so the one barrier per step waits for nothing but the updates themselves.
 template <int TR, int NSLOT>
 __device__ __forceinline__ void wide_fold(double (&B)[TR][NSLOT], double* __restrict__ Rt, int p1, int c_begin,
                                           double* xs, int tid) {
@@ -153,7 +166,7 @@ __device__ __forceinline__ void wide_fold(double (&B)[TR][NSLOT], double* __rest
 #pragma unroll
       for (int s = 0; s < NSLOT; ++s)
         if (s == sc) alpha = rho[s];
-      wide_publish<TR, NSLOT>(B, sc, alpha, xs + (c_begin & 1) * XS, Rt + roff);
+      wide_publish<TR, NSLOT>(B, sc, alpha, xs + (c_begin & 1) * XS);
     }
   }
   wd_bar();
@@ -167,21 +180,21 @@ __device__ __forceinline__ void wide_fold(double (&B)[TR][NSLOT], double* __rest
       rho_n[s] = (c + 1 < p1 && col > c && col < p1) ? __ldcg(Rt + rn + col - c - 1) : 0.0;
     }
     const double* xb = xs + (c & 1) * XS;
-    const double inv = xb[TRP], tauh = xb[TRP + 1];
-    const int cn = c + 1;
-    const bool next_owner = cn < p1 && tid == (cn & (WD_THREADS - 1));
-    const int sn = cn / WD_THREADS;
-    if (next_owner) {  // my column c + 1 first, then its reflector, then the rest of my columns
-      if (tauh != 0.0) wide_apply_slots<TR, NSLOT, 0>(B, xb, inv, tauh, rho, Rt + roff, c, p1, tid, sn, -1);
-      double alpha = 0.0;
-#pragma unroll
-      for (int s = 0; s < NSLOT; ++s)
-        if (s == sn) alpha = rho_n[s];
-      wide_publish<TR, NSLOT>(B, sn, alpha, xs + (cn & 1) * XS, Rt + rn);
-      if (tauh != 0.0) wide_apply_slots<TR, NSLOT, 0>(B, xb, inv, tauh, rho, Rt + roff, c, p1, tid, -1, sn);
-    } else if (tauh != 0.0) {
-      wide_apply_slots<TR, NSLOT, 0>(B, xb, inv, tauh, rho, Rt + roff, c, p1, tid, -1, -1);
+    const double alpha = xb[TRP], sigma = xb[TRP + 1];
+    double inv = 0.0, tauh = 0.0;
+    const double mu = fma(alpha, alpha, sigma);
+    if (sigma != 0.0 && mu > 1e-280) {  // uniform; else H = I (dlarfg with xnorm == 0)
+      double nrm, rs;
+      wd_sqrt_rsqrt(mu, nrm, rs);
+      const double beta = alpha >= 0.0 ? -nrm : nrm;
+      const double den = alpha - beta;
+      inv = wd_rcp(den);
+      tauh = fabs(den) * rs;  // (beta - alpha) / beta
+      if (tid == (c & (WD_THREADS - 1))) __stcg(Rt + roff, beta);
     }
+    const int cn = c + 1;
+    const int pub_slot = (cn < p1 && tid == (cn & (WD_THREADS - 1))) ? cn / WD_THREADS : -1;
+    wide_apply_slots<TR, NSLOT, 0>(B, xb, inv, tauh, rho, rho_n, Rt + roff, c, p1, tid, pub_slot, xs + (cn & 1) * XS);
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) rho[s] = rho_n[s];
     wd_bar();

@@ -392,7 +392,18 @@ class BaseSolution:
         self.resid2 = None       # |tau - W_b phi_b|^2
         self.params_base = []    # expression strings
         self.phi_std = None
-        self.rows = 0
+        self._rows = None        # rows of the regressor (fetched lazily: after a multi-GPU merge it lives on the device)
+        self._state = None
+
+    @property
+    def rows(self):
+        if self._rows is None and self._state is not None:
+            self._rows = self._state.rows
+        return self._rows or 0
+
+    @rows.setter
+    def rows(self, value):
+        self._rows = value
 
 
 def structural_columns(dm: DeviceModel, cfg: RegressorConfig, nprobe=64, seed=20241017) -> np.ndarray:
@@ -443,7 +454,7 @@ def solve_state(state: TsqrState, names, tol_e=None, idx_e=None, tol_qr=TOL_QR, 
     """
     sol = BaseSolution()
     p = state.p
-    sol.rows = state.rows
+    sol._state = state
     if col_map is None:
         col_map = np.arange(p)
         p_full = p

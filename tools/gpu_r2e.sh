@@ -1,0 +1,14 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python __graft_entry__.py > gpurun_out/build.log 2>&1
+echo "== pytest gpu full"
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
+tail -5 gpurun_out/pytest_gpu.log
+timeout 300 python tools/probe_models.py talos 60000 2>&1 | tail -1
+FG_WIDE_OCC2=1 timeout 300 python tools/probe_models.py talos 60000 2>&1 | tail -1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:wide_accumulate_samples -s 1 -c 1 -f -o gpurun_out/prof_wide2 \
+    python tools/probe_models.py talos 30000 > gpurun_out/prof_wide2.log 2>&1; echo "ncu wide rc=$?"
+FG_WIDE_OCC2=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:wide_accumulate_samples -s 1 -c 1 -f -o gpurun_out/prof_wide2_occ2 \
+    python tools/probe_models.py talos 30000 > gpurun_out/prof_wide2_occ2.log 2>&1; echo "ncu wide occ2 rc=$?"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_talos.csv \
+    python tools/probe_models.py talos 60000 > gpurun_out/launches_talos.log 2>&1; echo "ncu list rc=$?"
