@@ -480,7 +480,7 @@ extern "C" int fg_regressor_materialize(const fg_model* mc, const fg_regressor_c
   if (ldw < pl->P.ncols) return set_err(FG_ERR_INVALID, "ldw=%lld smaller than %d columns", (long long)ldw, pl->P.ncols);
   cudaStream_t st = (cudaStream_t)stream;
   const int ms = pl->P.ms;
-  if (ms <= 8) return launch_materialize<8, 4>(m, pl, q, v, a, N, W, ldw, st);
+  if (ms <= 8) return launch_materialize<8, 8>(m, pl, q, v, a, N, W, ldw, st);
   if (ms <= 24) return launch_materialize<24, 1>(m, pl, q, v, a, N, W, ldw, st);
   if (ms <= 48) return launch_materialize<48, 1>(m, pl, q, v, a, N, W, ldw, st);
   return set_err(FG_ERR_UNSUPPORTED, "materialise: %d row blocks per sample not supported", ms);

@@ -21,10 +21,12 @@
 
 namespace fg {
 
-constexpr int WD_THREADS = 256;   // consumer threads (column owners)
-constexpr int WD_BAR = 1;         // named barrier of the 256 column owners
+constexpr int WD_BAR = 1;         // named barrier of the column owners
 
-__device__ __forceinline__ void wd_bar() { asm volatile("bar.sync %0, %1;" ::"n"(WD_BAR), "n"(WD_THREADS) : "memory"); }
+// NT: column-owner threads of the CTA (256 with up to three columns each, or 512 with one or two: twice the
+// warps for the same tile, which is what a latency-bound column step wants)
+template <int NT>
+__device__ __forceinline__ void wd_bar() { asm volatile("bar.sync %0, %1;" ::"n"(WD_BAR), "n"(NT) : "memory"); }
 
 // sqrt(x), 1/sqrt(x) and 1/x from a MUFU seed and two Newton steps (full double accuracy for normal x; the
 // sequences sqrt() / division expand to are three times as long and sit on the critical path of every column)
@@ -123,12 +125,12 @@ __device__ __forceinline__ void wide_apply_slot(double (&B)[TR][NSLOT], const do
 }
 
 // all live slots of the thread; `pub_slot`: the slot of column c + 1 if this thread owns it (else -1)
-template <int TR, int NSLOT, int S_>
+template <int NT, int TR, int NSLOT, int S_>
 __device__ __forceinline__ void wide_apply_slots(double (&B)[TR][NSLOT], const double* xb, double inv, double tauh,
                                                  const double (&rho)[NSLOT], const double (&rho_n)[NSLOT], double* Rrow,
                                                  int c, int p1, int tid, int pub_slot, double* xn) {
   if constexpr (S_ < NSLOT) {
-    const int col = tid + WD_THREADS * S_;
+    const int col = tid + NT * S_;
     // warp-uniform: a slot whose 32 columns of this warp are all <= c has retired
     const bool warp_live = (col | 31) > c;
     if (warp_live) {
@@ -137,7 +139,7 @@ __device__ __forceinline__ void wide_apply_slots(double (&B)[TR][NSLOT], const d
       else
         wide_apply_slot<TR, NSLOT, S_, false>(B, xb, inv, tauh, rho[S_], Rrow + col - c, col > c && col < p1, nullptr, 0.0);
     }
-    wide_apply_slots<TR, NSLOT, S_ + 1>(B, xb, inv, tauh, rho, rho_n, Rrow, c, p1, tid, pub_slot, xn);
+    wide_apply_slots<NT, TR, NSLOT, S_ + 1>(B, xb, inv, tauh, rho, rho_n, Rrow, c, p1, tid, pub_slot, xn);
   }
 }
 
@@ -147,7 +149,7 @@ __device__ __forceinline__ void wide_apply_slots(double (&B)[TR][NSLOT], const d
 // Step c applies reflector c (published in xs[c & 1]) to every live column.  LOOK-AHEAD: while it updates its
 // column c + 1, the owner of that column writes the updated values and their squared norm into the other buffer,
 // so the one barrier per step waits for nothing but the updates themselves.
-template <int TR, int NSLOT>
+template <int NT, int TR, int NSLOT>
 __device__ __forceinline__ void wide_fold(double (&B)[TR][NSLOT], double* __restrict__ Rt, int p1, int c_begin,
                                           double* xs, int tid) {
   constexpr int TRP = ((TR + 7) / 8) * 8;
@@ -157,11 +159,11 @@ __device__ __forceinline__ void wide_fold(double (&B)[TR][NSLOT], double* __rest
     const int roff = tri_off(c_begin, p1);
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) {
-      const int col = tid + WD_THREADS * s;
+      const int col = tid + NT * s;
       rho[s] = (col >= c_begin && col < p1) ? __ldcg(Rt + roff + col - c_begin) : 0.0;
     }
-    if (tid == (c_begin & (WD_THREADS - 1))) {
-      const int sc = c_begin / WD_THREADS;
+    if (tid == (c_begin & (NT - 1))) {
+      const int sc = c_begin / NT;
       double alpha = 0.0;
 #pragma unroll
       for (int s = 0; s < NSLOT; ++s)
@@ -169,14 +171,14 @@ __device__ __forceinline__ void wide_fold(double (&B)[TR][NSLOT], double* __rest
       wide_publish<TR, NSLOT>(B, sc, alpha, xs + (c_begin & 1) * XS);
     }
   }
-  wd_bar();
+  wd_bar<NT>();
   for (int c = c_begin; c < p1; ++c) {
     double rho_n[NSLOT];
     const int roff = tri_off(c, p1);
     const int rn = roff + (p1 - c);  // tri_off(c + 1, p1)
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) {
-      const int col = tid + WD_THREADS * s;
+      const int col = tid + NT * s;
       rho_n[s] = (c + 1 < p1 && col > c && col < p1) ? __ldcg(Rt + rn + col - c - 1) : 0.0;
     }
     const double* xb = xs + (c & 1) * XS;
@@ -190,14 +192,14 @@ __device__ __forceinline__ void wide_fold(double (&B)[TR][NSLOT], double* __rest
       const double den = alpha - beta;
       inv = wd_rcp(den);
       tauh = fabs(den) * rs;  // (beta - alpha) / beta
-      if (tid == (c & (WD_THREADS - 1))) __stcg(Rt + roff, beta);
+      if (tid == (c & (NT - 1))) __stcg(Rt + roff, beta);
     }
     const int cn = c + 1;
-    const int pub_slot = (cn < p1 && tid == (cn & (WD_THREADS - 1))) ? cn / WD_THREADS : -1;
-    wide_apply_slots<TR, NSLOT, 0>(B, xb, inv, tauh, rho, rho_n, Rt + roff, c, p1, tid, pub_slot, xs + (cn & 1) * XS);
+    const int pub_slot = (cn < p1 && tid == (cn & (NT - 1))) ? cn / NT : -1;
+    wide_apply_slots<NT, TR, NSLOT, 0>(B, xb, inv, tauh, rho, rho_n, Rt + roff, c, p1, tid, pub_slot, xs + (cn & 1) * XS);
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) rho[s] = rho_n[s];
-    wd_bar();
+    wd_bar<NT>();
   }
 }
 
@@ -242,8 +244,8 @@ __host__ __device__ inline WideLayout wide_layout(int nj, int ms, int S, int TR)
   return L;
 }
 
-template <int MSMAX, int S, int NSLOT, int MINB>
-__global__ void __launch_bounds__(WD_THREADS, MINB)
+template <int NT, int MSMAX, int S, int NSLOT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 wide_accumulate_samples_kernel(DevPlanPtrs pp, const double* __restrict__ qd, const double* __restrict__ qdd,
                                const double* __restrict__ tau, int64_t ld_tau, int64_t n,
                                const double* __restrict__ fw_all, double* __restrict__ parts, int first, int last) {
@@ -283,7 +285,7 @@ wide_accumulate_samples_kernel(DevPlanPtrs pp, const double* __restrict__ qd, co
   double csq[NSLOT];
 #pragma unroll
   for (int s = 0; s < NSLOT; ++s) {
-    const int col = tid + WD_THREADS * s;
+    const int col = tid + NT * s;
     cd[s].kind = COL_ZERO; cd[s].body = 0; cd[s].k = 0; cd[s].vidx = 0; cd[s].grp = -2;
     anc[s] = 0;
     csq[s] = 0.0;
@@ -322,19 +324,19 @@ wide_accumulate_samples_kernel(DevPlanPtrs pp, const double* __restrict__ qd, co
         csq[s] = fma(out[r], out[r], csq[s]);
       }
     }
-    wide_fold<TR, NSLOT>(B, Rt, p1, 0, xs, tid);
+    wide_fold<NT, TR, NSLOT>(B, Rt, p1, 0, xs, tid);
   }
 #pragma unroll
   for (int s = 0; s < NSLOT; ++s) {
-    const int col = tid + WD_THREADS * s;
+    const int col = tid + NT * s;
     if (col < p1) Rt[ntri + col] += csq[s];
   }
   (void)last;
 }
 
 // ------------------------------------------------------------------ dense: rows x p matrix in HBM -> factor
-template <int TR, int NSLOT, int MINB>
-__global__ void __launch_bounds__(WD_THREADS, MINB)
+template <int NT, int TR, int NSLOT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 wide_accumulate_dense_kernel(const double* __restrict__ W, int64_t ldw, const double* __restrict__ tau,
                              int64_t tau_stride, int64_t nrows, int p1, double* __restrict__ parts) {
   extern __shared__ __align__(16) unsigned char wd_smem[];
@@ -356,7 +358,7 @@ wide_accumulate_dense_kernel(const double* __restrict__ W, int64_t ldw, const do
       const int64_t row = r0 + r;
 #pragma unroll
       for (int s = 0; s < NSLOT; ++s) {
-        const int col = tid + WD_THREADS * s;
+        const int col = tid + NT * s;
         double val = 0.0;
         if (row < nrows) {
           if (col < p) val = __ldcs(W + row * ldw + col);
@@ -366,19 +368,19 @@ wide_accumulate_dense_kernel(const double* __restrict__ W, int64_t ldw, const do
         csq[s] = fma(val, val, csq[s]);
       }
     }
-    wide_fold<TR, NSLOT>(B, Rt, p1, 0, xs, tid);
+    wide_fold<NT, TR, NSLOT>(B, Rt, p1, 0, xs, tid);
   }
 #pragma unroll
   for (int s = 0; s < NSLOT; ++s) {
-    const int col = tid + WD_THREADS * s;
+    const int col = tid + NT * s;
     if (col < p1) Rt[ntri + col] = csq[s];
   }
 }
 
 // ------------------------------------------------------------------ pairwise merge of parts (one tree level)
 // CTA b folds part (2b + 1) * stride into part 2b * stride (packed triangles + norms), if it exists.
-template <int TR, int NSLOT>
-__global__ void __launch_bounds__(WD_THREADS, 1)
+template <int NT, int TR, int NSLOT>
+__global__ void __launch_bounds__(NT, 1)
 wide_merge_pairs_kernel(double* __restrict__ parts, int nparts, int stride, int p1) {
   extern __shared__ __align__(16) unsigned char wd_smem[];
   double* xs = reinterpret_cast<double*>(wd_smem);
@@ -395,11 +397,11 @@ wide_merge_pairs_kernel(double* __restrict__ parts, int nparts, int stride, int 
       const int row = r0 + r;
 #pragma unroll
       for (int s = 0; s < NSLOT; ++s) {
-        const int col = tid + WD_THREADS * s;
+        const int col = tid + NT * s;
         B[r][s] = (row < p1 && col >= row && col < p1) ? __ldcg(pb + tri_off(row, p1) + col - row) : 0.0;
       }
     }
-    wide_fold<TR, NSLOT>(B, pa, p1, r0, xs, tid);
+    wide_fold<NT, TR, NSLOT>(B, pa, p1, r0, xs, tid);
   }
   for (int i = tid; i < p1; i += blockDim.x) pa[ntri + i] += pb[ntri + i];
 }
