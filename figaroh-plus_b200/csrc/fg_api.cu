@@ -480,7 +480,7 @@ extern "C" int fg_regressor_materialize(const fg_model* mc, const fg_regressor_c
   if (ldw < pl->P.ncols) return set_err(FG_ERR_INVALID, "ldw=%lld smaller than %d columns", (long long)ldw, pl->P.ncols);
   cudaStream_t st = (cudaStream_t)stream;
   const int ms = pl->P.ms;
-  if (ms <= 8) return launch_materialize<8, 8>(m, pl, q, v, a, N, W, ldw, st);
+  if (ms <= 8) return launch_materialize<8, 4>(m, pl, q, v, a, N, W, ldw, st);
   if (ms <= 24) return launch_materialize<24, 1>(m, pl, q, v, a, N, W, ldw, st);
   if (ms <= 48) return launch_materialize<48, 1>(m, pl, q, v, a, N, W, ldw, st);
   return set_err(FG_ERR_UNSUPPORTED, "materialise: %d row blocks per sample not supported", ms);
@@ -959,10 +959,11 @@ extern "C" int fg_state_accumulate_samples_host(fg_state* s, const fg_model* mc,
 // scipy.signal.filtfilt(b, a, x, axis=0, padtype="odd", padlen) followed by dropping `trim` rows at both ends
 // (low_pass_filter_data, identification_tools.py:390-424).  b, a, zi are HOST arrays (a[0] != 0; zi =
 // scipy.signal.lfilter_zi(b, a), order entries); x and y are device matrices.
-extern "C" int fg_filtfilt(const double* x, int64_t N, int32_t ncols, int64_t ldx, const double* b, int32_t nb,
-                           const double* a, int32_t na, const double* zi, int32_t padlen, int64_t trim, double* y,
-                           int64_t ldy, void* stream) {
-  if (!x || !y || !b || !a || !zi || N < 1 || ncols < 1 || ldx < ncols || ldy < ncols || nb < 1 || na < 1 || a[0] == 0.0)
+static int filtfilt_impl(const double* x, int64_t N, int32_t ncols, int64_t ldx, const double* b, int32_t nb,
+                         const double* a, int32_t na, const double* zi, int32_t padlen, int64_t trim, int64_t step,
+                         double* y, int64_t ldy, void* stream) {
+  if (!x || !y || !b || !a || !zi || N < 1 || ncols < 1 || ldx < ncols || ldy < ncols || nb < 1 || na < 1 || a[0] == 0.0 ||
+      step < 1)
     return set_err(FG_ERR_INVALID, "fg_filtfilt: bad argument");
   const int n = std::max(nb, na) - 1;
   if (n < 1 || n > IIR_MAXN) return set_err(FG_ERR_UNSUPPORTED, "fg_filtfilt: filter order %d outside [1,%d]", n, IIR_MAXN);
@@ -998,7 +999,7 @@ extern "C" int fg_filtfilt(const double* x, int64_t N, int32_t ncols, int64_t ld
   const int blocks = (int)((nchunks * ncols + threads - 1) / threads);
   for (int pass = 0; pass < 2; ++pass) {
     IirIo io;
-    io.N = N; io.M = M; io.padlen = padlen; io.ncols = ncols; io.backward = pass; io.trim = trim;
+    io.N = N; io.M = M; io.padlen = padlen; io.ncols = ncols; io.backward = pass; io.trim = trim; io.step = step;
     if (pass == 0) { io.x = x; io.ldx = ldx; io.y = y1; io.ldy = ncols; }
     else { io.x = y1; io.ldx = ncols; io.y = y; io.ldy = ldy; }
     iir_chunk_kernel<false><<<blocks, threads, 0, st>>>(F, io, S, nullptr);
@@ -1010,6 +1011,42 @@ extern "C" int fg_filtfilt(const double* x, int64_t N, int32_t ncols, int64_t ld
   FG_CUDA(cudaFreeAsync(y1, st));
   FG_CUDA(cudaFreeAsync(S, st));
   FG_CUDA(cudaFreeAsync(Z0, st));
+  return FG_OK;
+}
+
+extern "C" int fg_filtfilt(const double* x, int64_t N, int32_t ncols, int64_t ldx, const double* b, int32_t nb,
+                           const double* a, int32_t na, const double* zi, int32_t padlen, int64_t trim, double* y,
+                           int64_t ldy, void* stream) {
+  return filtfilt_impl(x, N, ncols, ldx, b, nb, a, na, zi, padlen, trim, 1, y, ldy, stream);
+}
+
+// scipy.signal.decimate(x, q, zero_phase=True) for every column: filtfilt with the caller's (Chebyshev) design,
+// then every q-th row - only those rows are written (ceil(N / q) of them).
+extern "C" int fg_filtfilt_decimate(const double* x, int64_t N, int32_t ncols, int64_t ldx, const double* b, int32_t nb,
+                                    const double* a, int32_t na, const double* zi, int32_t padlen, int32_t q, double* y,
+                                    int64_t ldy, void* stream) {
+  if (q < 1) return set_err(FG_ERR_INVALID, "fg_filtfilt_decimate: q must be >= 1");
+  return filtfilt_impl(x, N, ncols, ldx, b, nb, a, na, zi, padlen, 0, q, y, ldy, stream);
+}
+
+extern "C" int fg_medfilt(const double* x, int64_t N, int32_t ncols, int64_t ldx, int32_t k, double* y, int64_t ldy,
+                          void* stream) {
+  if (!x || !y || N < 1 || ncols < 1 || ldx < ncols || ldy < ncols || k < 1 || k > MEDFILT_MAXK || (k & 1) == 0)
+    return set_err(FG_ERR_INVALID, "fg_medfilt: bad argument (odd kernel size up to %d)", MEDFILT_MAXK);
+  const int blocks = (int)std::min<int64_t>((N * ncols + 255) / 256, 148 * 16);
+  medfilt_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, N, ncols, ldx, k, y, ldy);
+  FG_CUDA(cudaGetLastError());
+  FG_LAUNCHED();
+  return FG_OK;
+}
+
+extern "C" int fg_gradient(const double* x, int64_t N, int32_t ncols, int64_t ldx, const double* t_dev, double* y,
+                           int64_t ldy, void* stream) {
+  if (!x || !y || N < 2 || ncols < 1 || ldx < ncols || ldy < ncols) return set_err(FG_ERR_INVALID, "fg_gradient: bad argument (needs N >= 2)");
+  const int blocks = (int)std::min<int64_t>((N * ncols + 255) / 256, 148 * 16);
+  gradient_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, N, ncols, ldx, t_dev, y, ldy);
+  FG_CUDA(cudaGetLastError());
+  FG_LAUNCHED();
   return FG_OK;
 }
 

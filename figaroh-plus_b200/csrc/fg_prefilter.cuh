@@ -48,6 +48,7 @@ struct IirIo {
   double* y;           // forward: y1 (ld = ncols); backward: out
   int64_t ldy;
   int64_t trim;        // backward only: rows dropped at both ends of the N-row result
+  int64_t step;        // backward only: keep every step-th row of the (trimmed) result (scipy.signal.decimate's y[::q])
 };
 
 __device__ __forceinline__ double iir_input(const IirIo& io, int64_t e, int c) {
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(128) iir_chunk_kernel(const __grid_constant__ 
       } else {
         // backward index e is row M - 1 - e of the extended signal = row M - 1 - e - padlen of the result
         const int64_t r = io.M - 1 - e - io.padlen - io.trim;
-        if (r >= 0 && r < io.N - 2 * io.trim) io.y[r * io.ldy + c] = y;
+        if (r >= 0 && r < io.N - 2 * io.trim && r % io.step == 0) io.y[(r / io.step) * io.ldy + c] = y;
       }
     }
   }
@@ -146,6 +147,47 @@ __global__ void differentiate_kernel(const double* __restrict__ q, int64_t N, in
       g /= dtv ? dtv[i] : dt;
     }
     ddq[i * ldo + j] = g;
+  }
+}
+
+// scipy.signal.medfilt(x[:, c], k) for every column c: median of the k-sample window centred on the row, zeros
+// beyond both ends (examples/tiago/identification.py:70,80 of the reference: medfilt(., 5) ahead of filtfilt).
+constexpr int MEDFILT_MAXK = 15;
+__global__ void medfilt_kernel(const double* __restrict__ x, int64_t N, int ncols, int64_t ldx, int k,
+                               double* __restrict__ y, int64_t ldy) {
+  const int h = k / 2;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < N * ncols;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = idx / ncols;
+    const int c = (int)(idx % ncols);
+    double w[MEDFILT_MAXK];
+    for (int t = 0; t < k; ++t) {
+      const int64_t r = i - h + t;
+      w[t] = (r >= 0 && r < N) ? x[r * ldx + c] : 0.0;
+    }
+    for (int a = 1; a < k; ++a) {  // insertion sort of a handful of values
+      const double v = w[a];
+      int b = a - 1;
+      while (b >= 0 && w[b] > v) { w[b + 1] = w[b]; --b; }
+      w[b + 1] = v;
+    }
+    y[i * ldy + c] = w[h];
+  }
+}
+
+// np.gradient(x[:, c]) (unit spacing, edge_order 1) for every column, optionally divided by np.gradient(t)
+// (examples/tiago/identification.py:91-98: acceleration = gradient(dq) / gradient(t)).
+__global__ void gradient_kernel(const double* __restrict__ x, int64_t N, int ncols, int64_t ldx,
+                                const double* __restrict__ t, double* __restrict__ y, int64_t ldy) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < N * ncols;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = idx / ncols;
+    const int c = (int)(idx % ncols);
+    const int64_t lo = i == 0 ? 0 : i - 1, hi = i == N - 1 ? N - 1 : i + 1;
+    const double den = (i == 0 || i == N - 1) ? 1.0 : 2.0;
+    double g = (x[hi * ldx + c] - x[lo * ldx + c]) / den;
+    if (t != nullptr) g /= (t[hi] - t[lo]) / den;
+    y[i * ldy + c] = g;
   }
 }
 

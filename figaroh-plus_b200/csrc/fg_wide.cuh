@@ -171,15 +171,27 @@ __device__ __forceinline__ void wide_fold(double (&B)[TR][NSLOT], double* __rest
       wide_publish<TR, NSLOT>(B, sc, alpha, xs + (c_begin & 1) * XS);
     }
   }
-  wd_bar<NT>();
-  for (int c = c_begin; c < p1; ++c) {
-    double rho_n[NSLOT];
-    const int roff = tri_off(c, p1);
-    const int rn = roff + (p1 - c);  // tri_off(c + 1, p1)
+  // R rows are requested TWO steps ahead: the owner of column c + 1 needs R[c+1][c+1] while step c runs, and an
+  // L2 round trip (330 cycles idle, more under load) must not sit on the path to the barrier
+  double rho_n[NSLOT];
+  {
+    const int rn = tri_off(c_begin, p1) + (p1 - c_begin);
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) {
       const int col = tid + NT * s;
-      rho_n[s] = (c + 1 < p1 && col > c && col < p1) ? __ldcg(Rt + rn + col - c - 1) : 0.0;
+      rho_n[s] = (c_begin + 1 < p1 && col > c_begin && col < p1) ? __ldcg(Rt + rn + col - c_begin - 1) : 0.0;
+    }
+  }
+  wd_bar<NT>();
+  for (int c = c_begin; c < p1; ++c) {
+    double rho_nn[NSLOT];
+    const int roff = tri_off(c, p1);
+    const int rn = roff + (p1 - c);       // tri_off(c + 1, p1)
+    const int rnn = rn + (p1 - c - 1);    // tri_off(c + 2, p1)
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) {
+      const int col = tid + NT * s;
+      rho_nn[s] = (c + 2 < p1 && col > c + 1 && col < p1) ? __ldcg(Rt + rnn + col - c - 2) : 0.0;
     }
     const double* xb = xs + (c & 1) * XS;
     const double alpha = xb[TRP], sigma = xb[TRP + 1];
@@ -198,7 +210,7 @@ __device__ __forceinline__ void wide_fold(double (&B)[TR][NSLOT], double* __rest
     const int pub_slot = (cn < p1 && tid == (cn & (NT - 1))) ? cn / NT : -1;
     wide_apply_slots<NT, TR, NSLOT, 0>(B, xb, inv, tauh, rho, rho_n, Rt + roff, c, p1, tid, pub_slot, xs + (cn & 1) * XS);
 #pragma unroll
-    for (int s = 0; s < NSLOT; ++s) rho[s] = rho_n[s];
+    for (int s = 0; s < NSLOT; ++s) { rho[s] = rho_n[s]; rho_n[s] = rho_nn[s]; }
     wd_bar<NT>();
   }
 }

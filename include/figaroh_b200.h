@@ -204,6 +204,19 @@ int fg_state_solve(fg_state* s, double tol_e, const int32_t* drop_host, int32_t 
 int fg_filtfilt(const double* x_dev, int64_t N, int32_t ncols, int64_t ldx, const double* b_host, int32_t nb,
                 const double* a_host, int32_t na, const double* zi_host, int32_t padlen, int64_t trim,
                 double* y_dev, int64_t ldy, void* stream);
+/* scipy.signal.decimate(x, q, zero_phase=True) per column (examples/tiago/identification.py:142-187 applies it to
+ * tau and to every column of the reduced regressor): filtfilt(b, a, padtype="odd", padlen) with the caller's design
+ * (scipy's default is cheby1(8, 0.05, 0.8 / q), padlen 3 * max(len(a), len(b))), rows 0, q, 2q, ... written to y
+ * (ceil(N / q) rows). */
+int fg_filtfilt_decimate(const double* x_dev, int64_t N, int32_t ncols, int64_t ldx, const double* b_host, int32_t nb,
+                         const double* a_host, int32_t na, const double* zi_host, int32_t padlen, int32_t q,
+                         double* y_dev, int64_t ldy, void* stream);
+/* scipy.signal.medfilt(x[:, c], k) per column, zero padded (examples/tiago/identification.py:70,80). */
+int fg_medfilt(const double* x_dev, int64_t N, int32_t ncols, int64_t ldx, int32_t k, double* y_dev, int64_t ldy,
+               void* stream);
+/* np.gradient(x[:, c]) per column, divided by np.gradient(t) when t_dev != NULL (examples/tiago/identification.py:91-98). */
+int fg_gradient(const double* x_dev, int64_t N, int32_t ncols, int64_t ldx, const double* t_dev, double* y_dev,
+                int64_t ldy, void* stream);
 int fg_differentiate(const double* q_dev, int64_t N, int32_t nq, int64_t ldq, double dt, const double* dt_dev,
                      double* dq_dev, double* ddq_dev, int64_t ldo, void* stream);
 
