@@ -1097,6 +1097,23 @@ extern "C" int fg_state_merge_packed(fg_state* s, const double* packed, int32_t 
   return merge_parts_into_state(s, n, max_smem, st);
 }
 
+// diag(W^T W) of a dense device matrix of any width (get_index_eliminate, regressor.py:258-279): no QR needed
+extern "C" int fg_colsq_dense(const double* W, int64_t ldw, int64_t rows, int32_t p, double* out_host, void* stream) {
+  if (!W || !out_host || rows < 0 || p < 1 || ldw < p) return set_err(FG_ERR_INVALID, "fg_colsq_dense: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nslab = (int)std::max<int64_t>(1, std::min<int64_t>(rows / 64 + 1, 592));
+  double* d = nullptr;
+  FG_CUDA(cudaMallocAsync(&d, sizeof(double) * ((size_t)nslab + 1) * p, st));
+  colsq_partial_kernel<<<dim3((p + 255) / 256, nslab), 256, 0, st>>>(W, ldw, rows, p, d);
+  colsq_final_kernel<<<(p + 255) / 256, 256, 0, st>>>(d, nslab, p, d + (size_t)nslab * p);
+  FG_CUDA(cudaGetLastError());
+  FG_LAUNCHED(); FG_LAUNCHED();
+  FG_CUDA(cudaMemcpyAsync(out_host, d + (size_t)nslab * p, sizeof(double) * p, cudaMemcpyDeviceToHost, st));
+  FG_CUDA(cudaFreeAsync(d, st));
+  FG_CUDA(cudaStreamSynchronize(st));
+  return FG_OK;
+}
+
 // ------------------------------------------------------------------------------------ small stage
 extern "C" int fg_state_colsq(fg_state* s, double* out, void* stream) {
   if (!s || !out) return set_err(FG_ERR_INVALID, "fg_state_colsq: null argument");

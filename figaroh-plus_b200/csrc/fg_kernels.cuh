@@ -256,6 +256,32 @@ __global__ void __launch_bounds__(32) merge_pairs_kernel(double* __restrict__ pa
   for (int i = lane; i < p1; i += 32) pa[ntri + i] += pb[ntri + i];
 }
 
+// ------------------------------------------------------------------ squared column norms of a dense matrix
+// diag(W^T W) of get_index_eliminate / eliminate_non_dynaffect (regressor.py:243,271) for ANY width: CTA b sums the
+// squares of its row slab per column (thread = column, coalesced rows), a second launch adds the slabs in order.
+__global__ void __launch_bounds__(256) colsq_partial_kernel(const double* __restrict__ W, int64_t ldw, int64_t rows,
+                                                            int p, double* __restrict__ partial) {
+  const int64_t slab = (rows + gridDim.y - 1) / gridDim.y;
+  const int64_t r0 = (int64_t)blockIdx.y * slab, r1 = r0 + slab < rows ? r0 + slab : rows;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= p) return;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int64_t r = r0;
+  for (; r + 3 < r1; r += 4) {
+    const double x0 = W[r * ldw + c], x1 = W[(r + 1) * ldw + c], x2 = W[(r + 2) * ldw + c], x3 = W[(r + 3) * ldw + c];
+    a0 = fma(x0, x0, a0); a1 = fma(x1, x1, a1); a2 = fma(x2, x2, a2); a3 = fma(x3, x3, a3);
+  }
+  for (; r < r1; ++r) { const double x = W[r * ldw + c]; a0 = fma(x, x, a0); }
+  partial[(size_t)blockIdx.y * p + c] = (a0 + a1) + (a2 + a3);
+}
+__global__ void colsq_final_kernel(const double* __restrict__ partial, int nslab, int p, double* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= p) return;
+  double acc = 0.0;
+  for (int s = 0; s < nslab; ++s) acc += partial[(size_t)s * p + c];
+  out[c] = acc;
+}
+
 // ------------------------------------------------------------------ packing helpers
 __global__ void tri_to_dense_kernel(const double* __restrict__ part, int p1, double* __restrict__ dense,
                                     double nrows_as_double) {

@@ -13,21 +13,31 @@ numpy inputs as well.
 import numpy as np
 import torch
 
+from figaroh_b200 import _lib
 from figaroh_b200 import engine as _eng
 from figaroh_b200._lib import FgError
+from figaroh_b200._lib import check as _check
 
 RETURN_DEVICE = False
 
 
 def _device_model(robot):
+    """DeviceModel of robot.model, cached on the model and keyed on (content of the flattened arrays, CUDA device):
+    a script that edits jointPlacements / gravity after the first call, or switches GPU, gets a fresh upload."""
+    from figaroh_b200.model import flatten_model
     model = robot.model
-    dm = getattr(model, "_fg_device_model", None)
-    if dm is None:
-        dm = _eng.DeviceModel(model)
-        try:
-            model._fg_device_model = dm
-        except Exception:  # noqa: BLE001 - e.g. a pinocchio Model without __dict__
-            pass
+    fm = flatten_model(model)
+    key = (hash(b"".join(np.ascontiguousarray(x).tobytes() for x in (fm.parent, fm.jtype, fm.axis, fm.plc_R, fm.plc_p,
+                                                                      fm.idx_q, fm.idx_v, fm.gravity, fm.mass))),
+           torch.cuda.current_device() if torch.cuda.is_available() else -1)
+    cached = getattr(model, "_fg_device_model", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    dm = _eng.DeviceModel(fm)
+    try:
+        model._fg_device_model = (key, dm)
+    except Exception:  # noqa: BLE001 - e.g. a pinocchio Model without __dict__
+        pass
     return dm
 
 
@@ -75,10 +85,12 @@ def add_coupling_TX40(W, model, data, N, nq, nv, njoints, q, v, a):
 
 
 def _column_sq_norms(W):
-    """diag(W^T W) (regressor.py:243,271) from the TSQR state of W."""
+    """diag(W^T W) (regressor.py:243,271) by a column reduction on the device: any width, no QR."""
     Wd = _eng.as_device(W)
-    st = _eng.TsqrState(Wd.shape[1]).accumulate_dense(Wd, None)
-    return st.colsq()[:Wd.shape[1]]
+    out = np.empty(Wd.shape[1])
+    _check(_lib.lib().fg_colsq_dense(Wd.data_ptr(), Wd.stride(0), Wd.shape[0], Wd.shape[1], out.ctypes.data,
+                                     _eng._stream()))
+    return out
 
 
 def eliminate_non_dynaffect(W, params_std, tol_e=1e-6):

@@ -530,6 +530,9 @@ def identify(dm: DeviceModel, cfg: RegressorConfig, q, v, a, tau, names, tol_e=1
     are not generated at all unless prune=False."""
     _, cols = dm.shape(cfg)
     col_map = None
+    # identically-zero columns are eliminated by get_index_eliminate only for tol_e > 0 (regressor.py:271-274);
+    # with tol_e None / <= 0 the reference keeps them (they end up regrouped), so they are generated here too
+    prune = prune and tol_e is not None and tol_e > 0
     if cfg.col_sel is None and prune:
         col_map = structural_columns(dm, cfg)
         cfg = cfg.with_columns(col_map)

@@ -204,6 +204,9 @@ int fg_state_solve(fg_state* s, double tol_e, const int32_t* drop_host, int32_t 
 int fg_filtfilt(const double* x_dev, int64_t N, int32_t ncols, int64_t ldx, const double* b_host, int32_t nb,
                 const double* a_host, int32_t na, const double* zi_host, int32_t padlen, int64_t trim,
                 double* y_dev, int64_t ldy, void* stream);
+/* diag(W^T W) of a dense device matrix (rows x p, ld = ldw) - the column norms get_index_eliminate and
+ * eliminate_non_dynaffect threshold (regressor.py:243,271: np.diag(np.dot(W.T, W))).  Any width. */
+int fg_colsq_dense(const double* W_dev, int64_t ldw, int64_t rows, int32_t p, double* colsq_host, void* stream);
 /* scipy.signal.decimate(x, q, zero_phase=True) per column (examples/tiago/identification.py:142-187 applies it to
  * tau and to every column of the reduced regressor): filtfilt(b, a, padtype="odd", padlen) with the caller's design
  * (scipy's default is cheby1(8, 0.05, 0.8 / q), padlen 3 * max(len(a), len(b))), rows 0, q, 2q, ... written to y

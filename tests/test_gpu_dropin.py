@@ -117,25 +117,69 @@ def test_device_resident_pipeline_and_errors():
 
 
 def test_tiago_golden_csv_on_gpu():
-    """The reference's TIAGo golden (44 expressions, phi_b to 6 decimals) with the regressor built
-    by kernel (1) and double_QR run by kernels (2)+(3); the per-column decimation between them is
-    scipy on the host exactly as in examples/tiago/identification.py:142-187."""
+    """The reference's TIAGo golden (44 expressions, phi_b to 6 decimals) GPU-only from the processed log to the
+    base parameters: regressor by kernel (1), elimination on the column norms, the per-column zero-phase
+    decimation of examples/tiago/identification.py:142-187 by fg_filtfilt_decimate (active joints' row blocks
+    only), double_QR by kernels (2)+(3).  The scipy decimation of the same matrix is the cross-check."""
+    import torch
     from figaroh.tools.qrdecomposition import double_QR
     from figaroh.tools.regressor import build_regressor_basic, build_regressor_reduced, get_index_eliminate
+    from figaroh_b200 import signal as fsig
+    from figaroh_b200.engine import DeviceMatrix
     from test_oracle_golden import tiago_decimate, tiago_inputs
     meta = json.load(open(golden_path("tiago_kat.json")))
     robot = _Robot("tiago")
     param = make_param(False, False, False)
     p, v, a, tau, idxv = tiago_inputs()
+    N = len(p)
     std = robot.get_standard_parameters(param)
-    W = build_regressor_basic(robot, p, v, a, param)
+    pd, vd, ad = (torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (p, v, a))
+    W = build_regressor_basic(robot, pd, vd, ad, param)            # DeviceMatrix: stays in HBM
+    assert isinstance(W, DeviceMatrix)
     idx_e, params_r = get_index_eliminate(W, std, tol_e=0.001)
     assert idx_e == meta["idx_e"]
-    W_rf, tau_rf = tiago_decimate(build_regressor_reduced(W, idx_e), tau, idxv, len(p))
-    W_b, bp, base, phi_b, phi_std = double_QR(tau_rf, W_rf, params_r, std)
+    W_e = build_regressor_reduced(W, idx_e)
+    rows = torch.cat([torch.arange(int(i) * N, (int(i) + 1) * N) for i in idxv]).cuda()
+    W_act = W_e.t.index_select(0, rows)                               # the active joints' row blocks
+    W_rf = fsig.decimate_blocks(W_act, len(idxv), q=10)
+    tau_rf = fsig.decimate(torch.from_numpy(np.ascontiguousarray(tau)).cuda(), 10).t().reshape(-1)
+    W_rf_ref, tau_rf_ref = tiago_decimate(W_e.numpy(), tau, idxv, N)
+    assert W_rf.shape == W_rf_ref.shape
+    assert np.abs(W_rf.cpu().numpy() - W_rf_ref).max() <= 1e-9 * np.abs(W_rf_ref).max()
+    assert np.abs(tau_rf.cpu().numpy() - tau_rf_ref).max() <= 1e-9 * np.abs(tau_rf_ref).max()
+    W_b, bp, base, phi_b, phi_std = double_QR(tau_rf, DeviceMatrix(W_rf), params_r, std)
     assert base == [g[0] for g in meta["golden_csv"]]
     np.testing.assert_allclose(phi_b, [g[1] for g in meta["golden_csv"]], atol=1.01e-6)
     assert np.mean(phi_b == np.array([g[1] for g in meta["golden_csv"]])) > 0.9
+
+
+def test_signal_ops_match_scipy():
+    """medfilt / filtfilt / gradient / decimate of figaroh_b200.signal against scipy / numpy (per column)."""
+    from scipy import signal
+    from figaroh_b200 import signal as fsig
+    rng = np.random.default_rng(5)
+    N, nc = 5870, 7
+    t = np.cumsum(rng.uniform(0.009, 0.011, N))
+    x = np.sin(2 * np.pi * 0.3 * t)[:, None] * rng.uniform(0.5, 2, nc) + 0.05 * rng.normal(size=(N, nc))
+    x[100:103, 2] += 5.0  # spikes for the median filter
+    m = fsig.medfilt(x, 5)
+    assert np.array_equal(m, np.stack([signal.medfilt(x[:, j], 5) for j in range(nc)], 1))
+    b, a = signal.butter(4, 2 / 50, "low")
+    f = fsig.filtfilt(b, a, m, padlen=3 * (max(len(a), len(b)) - 1))
+    fref = np.stack([signal.filtfilt(b, a, m[:, j], padtype="odd", padlen=3 * (max(len(a), len(b)) - 1)) for j in range(nc)], 1)
+    assert np.abs(f - fref).max() <= 1e-9 * np.abs(fref).max()
+    g = fsig.gradient(f, t)
+    gref = np.stack([np.gradient(fref[:, j]) / np.gradient(t) for j in range(nc)], 1)
+    assert np.abs(g - gref).max() <= 1e-9 * np.abs(gref).max()
+    assert np.abs(fsig.gradient(x[:, 0]) - np.gradient(x[:, 0])).max() <= 1e-12
+    d = fsig.decimate(x, 10)
+    dref = np.stack([signal.decimate(x[:, j], q=10, zero_phase=True) for j in range(nc)], 1)
+    assert d.shape == dref.shape == ((N + 9) // 10, nc)
+    assert np.abs(d - dref).max() <= 1e-9 * np.abs(dref).max()
+    d1 = fsig.decimate(x[:, 3], 10)
+    assert d1.shape == (dref.shape[0],) and np.abs(d1 - dref[:, 3]).max() <= 1e-9 * np.abs(dref).max()
+    with pytest.raises(Exception):
+        fsig.medfilt(x, 4)
 
 
 def test_qr_pivoting_matches_reference_semantics():
@@ -256,3 +300,25 @@ def test_statistics_on_the_factor_match_reference():
     out = weigthed_least_squares(R, phi_ls, W_b, tau, tau_est, param)
     ref = pre.weigthed_least_squares(nq, phi_ls, W_b, tau, tau_est, param)
     np.testing.assert_allclose(out, ref, atol=2e-6)
+
+
+def test_human_free_flyer_560_columns_drop_in():
+    """examples/human/identification.py calls get_index_eliminate / get_baseParams on the full 14 x 40 = 560-column
+    external-wrench regressor of the 41-joint human model: wider than one TSQR pass used to take."""
+    from figaroh.tools.qrdecomposition import get_baseIndex
+    from figaroh.tools.regressor import build_regressor_basic, build_regressor_reduced, get_index_eliminate
+    from oracle import ref_path
+    robot, om = _Robot("human_ff"), load_oracle_model("human_ff")
+    fm = load_flat("human_ff")
+    param = make_param(False, False, False, is_joint_torques=False, is_external_wrench=True, force_torque=["All"])
+    N = 300
+    q, v, a = rand_inputs(fm, N, 3, ((-1, 1), (-1, 1), (-2, 2)))
+    std = robot.get_standard_parameters(param)
+    W = build_regressor_basic(robot, q, v, a, param)
+    Wref = ref_path.build_regressor_basic(om, q, v, a, param, per_sample=False)
+    assert W.shape == Wref.shape == (6 * N, 14 * (fm.njoints - 1)) and W.shape[1] == 560
+    assert np.abs(W - Wref).max() <= 1e-9 * np.abs(Wref).max()
+    idx_e, params_r = get_index_eliminate(W, std, 1e-6)
+    assert (idx_e, params_r) == ref_path.get_index_eliminate(Wref, std, 1e-6)
+    W_e = build_regressor_reduced(W, idx_e)
+    assert get_baseIndex(W_e, params_r) == ref_path.get_baseIndex(ref_path.build_regressor_reduced(Wref, idx_e), params_r)
