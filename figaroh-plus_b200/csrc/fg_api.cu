@@ -959,35 +959,31 @@ extern "C" int fg_state_accumulate_samples_host(fg_state* s, const fg_model* mc,
 // scipy.signal.filtfilt(b, a, x, axis=0, padtype="odd", padlen) followed by dropping `trim` rows at both ends
 // (low_pass_filter_data, identification_tools.py:390-424).  b, a, zi are HOST arrays (a[0] != 0; zi =
 // scipy.signal.lfilter_zi(b, a), order entries); x and y are device matrices.
-static int filtfilt_impl(const double* x, int64_t N, int32_t ncols, int64_t ldx, const double* b, int32_t nb,
-                         const double* a, int32_t na, const double* zi, int32_t padlen, int64_t trim, int64_t step,
-                         double* y, int64_t ldy, void* stream) {
-  if (!x || !y || !b || !a || !zi || N < 1 || ncols < 1 || ldx < ncols || ldy < ncols || nb < 1 || na < 1 || a[0] == 0.0 ||
-      step < 1)
-    return set_err(FG_ERR_INVALID, "fg_filtfilt: bad argument");
-  const int n = std::max(nb, na) - 1;
-  if (n < 1 || n > IIR_MAXN) return set_err(FG_ERR_UNSUPPORTED, "fg_filtfilt: filter order %d outside [1,%d]", n, IIR_MAXN);
-  if (padlen < 0 || padlen >= N) return set_err(FG_ERR_INVALID, "fg_filtfilt: padlen=%d needs more than %d samples", padlen, padlen);
-  if (trim < 0 || 2 * trim >= N) return set_err(FG_ERR_INVALID, "fg_filtfilt: trim=%lld leaves no row", (long long)trim);
+// Filtering core shared by the (b, a) and the second-order-section entries.  F: coefficients with F.n states and the
+// scipy initial-state vector zi; A^L (the homogeneous part of the recurrence over one chunk) is obtained here by
+// running the recurrence itself from every unit state, so it is exactly what the kernels iterate.
+static int filtfilt_run(IirCoef& F, const double* x, int64_t N, int32_t ncols, int64_t ldx, int32_t padlen, int64_t trim,
+                        int64_t step, double* y, int64_t ldy, void* stream) {
+  const int n = F.n;
   cudaStream_t st = (cudaStream_t)stream;
-  IirCoef F;
-  memset(&F, 0, sizeof F);
-  F.n = n;
-  for (int i = 0; i <= n; ++i) { F.b[i] = (i < nb ? b[i] : 0.0) / a[0]; F.a[i] = (i < na ? a[i] : 0.0) / a[0]; }
-  for (int i = 0; i < n; ++i) F.zi[i] = zi[i];
-  {  // A^L by repeated multiplication (A: homogeneous part of the recurrence)
-    std::vector<double> A(n * n, 0.0), Pw(n * n, 0.0), T(n * n);
-    for (int i = 0; i < n; ++i) { A[i * n] = -F.a[i + 1]; if (i + 1 < n) A[i * n + i + 1] += 1.0; Pw[i * n + i] = 1.0; }
+  for (int i0 = 0; i0 < n; ++i0) {
+    double z[IIR_MAXN] = {0};
+    z[i0] = 1.0;
     for (int l = 0; l < IIR_L; ++l) {
-      for (int i = 0; i < n; ++i)
-        for (int j = 0; j < n; ++j) {
-          double acc = 0.0;
-          for (int k = 0; k < n; ++k) acc += A[i * n + k] * Pw[k * n + j];
-          T[i * n + j] = acc;
+      if (F.nsec > 0) {
+        double u = 0.0;
+        for (int s = 0; s < F.nsec; ++s) {
+          const double ys = F.sos[s][0] * u + z[2 * s];
+          z[2 * s] = F.sos[s][1] * u - F.sos[s][4] * ys + z[2 * s + 1];
+          z[2 * s + 1] = F.sos[s][2] * u - F.sos[s][5] * ys;
+          u = ys;
         }
-      Pw = T;
+      } else {
+        const double yv = z[0];
+        for (int i = 0; i < n; ++i) z[i] = -F.a[i + 1] * yv + (i + 1 < n ? z[i + 1] : 0.0);
+      }
     }
-    for (int i = 0; i < n * n; ++i) F.AL[i] = Pw[i];
+    for (int i = 0; i < n; ++i) F.AL[i * n + i0] = z[i];
   }
   const int64_t M = N + 2 * (int64_t)padlen;
   const int64_t nchunks = (M + IIR_L - 1) / IIR_L;
@@ -1012,6 +1008,47 @@ static int filtfilt_impl(const double* x, int64_t N, int32_t ncols, int64_t ldx,
   FG_CUDA(cudaFreeAsync(S, st));
   FG_CUDA(cudaFreeAsync(Z0, st));
   return FG_OK;
+}
+
+static int filtfilt_impl(const double* x, int64_t N, int32_t ncols, int64_t ldx, const double* b, int32_t nb,
+                         const double* a, int32_t na, const double* zi, int32_t padlen, int64_t trim, int64_t step,
+                         double* y, int64_t ldy, void* stream) {
+  if (!x || !y || !b || !a || !zi || N < 1 || ncols < 1 || ldx < ncols || ldy < ncols || nb < 1 || na < 1 || a[0] == 0.0 ||
+      step < 1)
+    return set_err(FG_ERR_INVALID, "fg_filtfilt: bad argument");
+  const int n = std::max(nb, na) - 1;
+  if (n < 1 || n > IIR_MAXN) return set_err(FG_ERR_UNSUPPORTED, "fg_filtfilt: filter order %d outside [1,%d]", n, IIR_MAXN);
+  if (padlen < 0 || padlen >= N) return set_err(FG_ERR_INVALID, "fg_filtfilt: padlen=%d needs more than %d samples", padlen, padlen);
+  if (trim < 0 || 2 * trim >= N) return set_err(FG_ERR_INVALID, "fg_filtfilt: trim=%lld leaves no row", (long long)trim);
+  IirCoef F;
+  memset(&F, 0, sizeof F);
+  F.n = n;
+  for (int i = 0; i <= n; ++i) { F.b[i] = (i < nb ? b[i] : 0.0) / a[0]; F.a[i] = (i < na ? a[i] : 0.0) / a[0]; }
+  for (int i = 0; i < n; ++i) F.zi[i] = zi[i];
+  return filtfilt_run(F, x, N, ncols, ldx, padlen, trim, step, y, ldy, stream);
+}
+
+// scipy.signal.sosfiltfilt(sos, x, axis=0, padtype="odd", padlen) [::step] for every column.  sos: nsec x 6 host
+// array (a0 == 1), zi = scipy.signal.sosfilt_zi(sos) flattened (nsec x 2).  This is what scipy.signal.decimate(x, q,
+// zero_phase=True) runs (cheby1(8, 0.05, 0.8 / q, output="sos")) - examples/tiago/identification.py:142-187.
+extern "C" int fg_sosfiltfilt(const double* x, int64_t N, int32_t ncols, int64_t ldx, const double* sos, int32_t nsec,
+                              const double* zi, int32_t padlen, int64_t trim, int32_t step, double* y, int64_t ldy,
+                              void* stream) {
+  if (!x || !y || !sos || !zi || N < 1 || ncols < 1 || ldx < ncols || ldy < ncols || step < 1)
+    return set_err(FG_ERR_INVALID, "fg_sosfiltfilt: bad argument");
+  if (nsec < 1 || 2 * nsec > IIR_MAXN) return set_err(FG_ERR_UNSUPPORTED, "fg_sosfiltfilt: %d sections outside [1,%d]", nsec, IIR_MAXN / 2);
+  if (padlen < 0 || padlen >= N) return set_err(FG_ERR_INVALID, "fg_sosfiltfilt: padlen=%d needs more than %d samples", padlen, padlen);
+  if (trim < 0 || 2 * trim >= N) return set_err(FG_ERR_INVALID, "fg_sosfiltfilt: trim=%lld leaves no row", (long long)trim);
+  IirCoef F;
+  memset(&F, 0, sizeof F);
+  F.n = 2 * nsec;
+  F.nsec = nsec;
+  for (int s = 0; s < nsec; ++s) {
+    if (sos[6 * s + 3] != 1.0) return set_err(FG_ERR_INVALID, "fg_sosfiltfilt: sos[%d][3] must be 1", s);
+    for (int k = 0; k < 6; ++k) F.sos[s][k] = sos[6 * s + k];
+  }
+  for (int i = 0; i < 2 * nsec; ++i) F.zi[i] = zi[i];
+  return filtfilt_run(F, x, N, ncols, ldx, padlen, trim, step, y, ldy, stream);
 }
 
 extern "C" int fg_filtfilt(const double* x, int64_t N, int32_t ncols, int64_t ldx, const double* b, int32_t nb,

@@ -27,7 +27,9 @@ constexpr int IIR_MAXN = 8;   // filter order (len(a) - 1)
 constexpr int IIR_L = 256;    // samples per chunk
 
 struct IirCoef {
-  int n;                      // order
+  int n;                      // number of states: the order of the (b, a) filter, or 2 * nsec
+  int nsec;                   // > 0: cascade of second-order sections (scipy.signal.sosfilt), state z[2 s], z[2 s + 1]
+  double sos[IIR_MAXN / 2][6];  // b0 b1 b2 1 a1 a2 of every section
   double b[IIR_MAXN + 1];     // normalised (a[0] == 1)
   double a[IIR_MAXN + 1];
   double zi[IIR_MAXN];        // lfilter_zi(b, a)
@@ -75,12 +77,27 @@ __global__ void __launch_bounds__(128) iir_chunk_kernel(const __grid_constant__ 
   const int64_t e0 = k * IIR_L, e1 = e0 + IIR_L < io.M ? e0 + IIR_L : io.M;
   for (int64_t e = e0; e < e1; ++e) {
     const double x = iir_input(io, e, c);
-    const double y = fma(F.b[0], x, z[0]);
+    double y;
+    if (F.nsec > 0) {  // uniform: cascade of direct-form-II-transposed biquads, like scipy's sosfilt
+      double u = x;
 #pragma unroll
-    for (int i = 0; i < IIR_MAXN; ++i) {
-      if (i < F.n) {
-        const double zn = (i + 1 < IIR_MAXN && i + 1 < F.n) ? z[i + 1] : 0.0;
-        z[i] = fma(F.b[i + 1], x, fma(-F.a[i + 1], y, zn));
+      for (int sct = 0; sct < IIR_MAXN / 2; ++sct) {
+        if (sct < F.nsec) {
+          const double ys = fma(F.sos[sct][0], u, z[2 * sct]);
+          z[2 * sct] = fma(F.sos[sct][1], u, fma(-F.sos[sct][4], ys, z[2 * sct + 1]));
+          z[2 * sct + 1] = fma(F.sos[sct][2], u, -F.sos[sct][5] * ys);
+          u = ys;
+        }
+      }
+      y = u;
+    } else {
+      y = fma(F.b[0], x, z[0]);
+#pragma unroll
+      for (int i = 0; i < IIR_MAXN; ++i) {
+        if (i < F.n) {
+          const double zn = (i + 1 < IIR_MAXN && i + 1 < F.n) ? z[i + 1] : 0.0;
+          z[i] = fma(F.b[i + 1], x, fma(-F.a[i + 1], y, zn));
+        }
       }
     }
     if (APPLY) {

@@ -2,6 +2,7 @@
 // (kinematic tree, row groups, column selection) into the producers' depth-first walk program and one local
 // dense problem per row group, the split of the warps into producers and consumers, and the launcher.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
@@ -214,9 +215,11 @@ RqLaunch rq_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, co
   // ---- cost model (warp instructions per 32-sample tile; calibrated on the generation-4 per-line counts)
   std::vector<double> cost(ms);
   double csum = 0.0;
+  double c_base = 250.0, c_panel = 1070.0, c_trail = 100.0;
+  if (const char* e = getenv("FG_RQ_COST")) sscanf(e, "%lf,%lf,%lf", &c_base, &c_panel, &c_trail);  // A/B only
   for (int g = 0; g < ms; ++g) {
     const GqGroup& G = T.gen.grp[g];
-    cost[g] = 250.0 + 1070.0 * G.nb + 100.0 * G.nb * (G.nb - 1) / 2;
+    cost[g] = c_base + c_panel * G.nb + c_trail * G.nb * (G.nb - 1) / 2;
     csum += cost[g];
   }
   const double pcost = 1.07 * (400.0 + 420.0 * nproc + 45.0 * n_transports + 190.0 * n_emits + 25.0 * n_simple + 60.0 * (nops - nproc));  // 1.07: A/B on UR10 (26 producer SMs of 148)

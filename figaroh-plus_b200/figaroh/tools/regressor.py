@@ -118,3 +118,71 @@ def build_regressor_reduced(W, idx_e):
         Wm = W if isinstance(W, _eng.DeviceMatrix) else _eng.DeviceMatrix(W)
         return Wm.drop_columns(list(idx_e))
     return np.delete(W, idx_e, 1)
+
+
+# ---- total-least-squares payload regressors (reference: regressor.py:296-500) --------------------------------
+def _block_columns(x, nblocks):
+    """(len(x), nblocks) device matrix: column j carries block j of x in its own rows, zeros elsewhere."""
+    xd = _eng.as_device(x).reshape(-1)
+    n = xd.shape[0] // nblocks
+    out = torch.zeros((xd.shape[0], nblocks), dtype=torch.float64, device=xd.device)
+    for j in range(nblocks):
+        out[j * n:(j + 1) * n, j] = xd[j * n:(j + 1) * n]
+    return out
+
+
+def _tls_finish(W_tot, mass_load, dev):
+    """SVD step of regressor.py:405-410 on the R factor: W_tot = Q R has the right singular vectors of R, so the
+    tall matrix is reduced once on the GPU (TSQR) and only the small triangle is decomposed."""
+    p = W_tot.shape[1]
+    st = _eng.TsqrState(p).accumulate_dense(W_tot, None)
+    st.reduce(np.arange(p))
+    _, _, R, _ = st.regroup_solve(np.arange(p), np.zeros(0, dtype=np.int32))
+    _, _, Vh = np.linalg.svd(R, full_matrices=False)
+    V = Vh.T.conj()
+    V_norm = mass_load * np.divide(V[:, -1], V[-1, -1])
+    residue = W_tot @ torch.from_numpy(V_norm).to(W_tot.device)
+    if dev or RETURN_DEVICE:
+        return _eng.DeviceMatrix(W_tot), V_norm, residue
+    return W_tot.cpu().numpy(), V_norm, residue.cpu().numpy()
+
+
+def build_total_regressor_current(W_b_u, W_b_l, W_l, I_u, I_l, param_standard_l, param):
+    """Total-least-squares regressor of a payload identification from joint currents (regressor.py:296-410).
+
+    Returns (W_tot, V_norm, residue) like the reference."""
+    dev = _on_device(W_l)
+    Wbu, Wbl, Wl = _eng.as_device(W_b_u), _eng.as_device(W_b_l), _eng.as_device(W_l)
+    n_samples = param["nb_samples"]
+    nb_joints = int(len(I_u) / n_samples)
+    cur = torch.cat([_block_columns(_eng.as_device(I_u).reshape(-1)[:nb_joints * n_samples], nb_joints),
+                     _block_columns(_eng.as_device(I_l).reshape(-1)[:nb_joints * n_samples], nb_joints)], dim=0)
+    if param["has_friction"]:
+        width, ks, wt = 12, [0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 11], 12
+    elif param["has_actuator_inertia"]:
+        width, ks, wt = 14, [0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 11, 12, 13], 14
+    else:
+        width, ks, wt = 10, list(range(9)), 9
+    base = param["which_body_loaded"] * width
+    W_l_temp = torch.zeros((Wl.shape[0], wt), dtype=torch.float64, device=Wl.device)
+    for k in ks:
+        W_l_temp[:, k] = Wl[:, base + k]
+    idx_e, _ = get_index_eliminate(_eng.DeviceMatrix(W_l_temp), param_standard_l, 1e-6)
+    keep = [k for k in range(wt) if k not in set(idx_e)]
+    W_e_l = W_l_temp[:, keep]
+    zeros = torch.zeros((Wl.shape[0], W_e_l.shape[1] + 1), dtype=torch.float64, device=Wl.device)
+    payload = torch.cat([zeros, torch.cat([-W_e_l, -Wl[:, base + 9:base + 10]], dim=1)], dim=0)
+    W_tot = torch.cat([torch.cat([-Wbu, -Wbl], dim=0), cur, payload], dim=1).contiguous()
+    return _tls_finish(W_tot, param["mass_load"], dev)
+
+
+def build_total_regressor_wrench(W_b_u, W_b_l, W_l, tau_u, tau_l, param_standard_l, param):
+    """Total-least-squares regressor with external-wrench measurements (regressor.py:413-500)."""
+    dev = _on_device(W_l)
+    Wbu, Wbl, Wl = _eng.as_device(W_b_u), _eng.as_device(W_b_l), _eng.as_device(W_l)
+    wr = torch.cat([_block_columns(tau_u, 6), _block_columns(tau_l, 6)], dim=0)
+    base = param["which_body_loaded"] * 10
+    zeros = torch.zeros((Wl.shape[0], 10), dtype=torch.float64, device=Wl.device)
+    payload = torch.cat([zeros, -Wl[:, base:base + 10]], dim=0)
+    W_tot = torch.cat([torch.cat([-Wbu, -Wbl], dim=0), wr, payload], dim=1).contiguous()
+    return _tls_finish(W_tot, param["mass_load"], dev)

@@ -21,7 +21,7 @@ SYMBOLS = (
     "fg_regressor_materialize", "fg_state_create", "fg_state_destroy", "fg_state_reset", "fg_state_p",
     "fg_state_rows", "fg_state_accumulate_dense", "fg_state_accumulate_samples", "fg_state_packed_doubles",
     "fg_state_export", "fg_state_merge_packed", "fg_state_colsq", "fg_state_reduce", "fg_state_regroup_solve",
-    "fg_state_solve", "fg_state_pivot_qr", "fg_filtfilt", "fg_differentiate", "fg_state_accumulate_samples_host", "fg_state_get_perm", "fg_state_set_perm", "fg_launch_count", "fg_state_set_timing", "fg_state_get_timing", "fg_plan_describe", "fg_colsq_dense", "fg_filtfilt_decimate", "fg_medfilt", "fg_gradient",
+    "fg_state_solve", "fg_state_pivot_qr", "fg_filtfilt", "fg_differentiate", "fg_state_accumulate_samples_host", "fg_state_get_perm", "fg_state_set_perm", "fg_launch_count", "fg_state_set_timing", "fg_state_get_timing", "fg_plan_describe", "fg_colsq_dense", "fg_sosfiltfilt", "fg_filtfilt_decimate", "fg_medfilt", "fg_gradient",
 )
 
 
@@ -92,6 +92,7 @@ def lib():
     L.fg_state_set_timing.argtypes = [vp, C.c_int]
     L.fg_state_get_timing.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
     L.fg_filtfilt_decimate.argtypes = [dp, i64, i32, i64, vp, i32, vp, i32, vp, i32, i32, dp, i64, vp]
+    L.fg_sosfiltfilt.argtypes = [dp, i64, i32, i64, vp, i32, vp, i32, i64, i32, dp, i64, vp]
     L.fg_medfilt.argtypes = [dp, i64, i32, i64, i32, dp, i64, vp]
     L.fg_gradient.argtypes = [dp, i64, i32, i64, dp, dp, i64, vp]
     L.fg_colsq_dense.argtypes = [dp, i64, i64, i32, vp, vp]

@@ -73,24 +73,34 @@ def gradient(x, t=None):
     return _finish(y, on_dev, one_d)
 
 
+def sosfiltfilt(sos, x, padlen=None, step=1):
+    """scipy.signal.sosfiltfilt(sos, x, axis=0, padtype="odd", padlen)[::step] for every column."""
+    sos = np.ascontiguousarray(sos, dtype=np.float64).reshape(-1, 6)
+    nsec = sos.shape[0]
+    zi = np.ascontiguousarray(_sp.sosfilt_zi(sos), dtype=np.float64)
+    if padlen is None:  # scipy/signal/_signaltools.py sosfiltfilt()
+        ntaps = 2 * nsec + 1 - min(int((sos[:, 2] == 0).sum()), int((sos[:, 5] == 0).sum()))
+        padlen = 3 * ntaps
+    t, on_dev, one_d = _prep(x)
+    if t.shape[0] <= padlen:
+        raise ValueError("The length of the input vector x must be greater than padlen, which is %d." % padlen)
+    step = int(step)
+    rows = (t.shape[0] + step - 1) // step
+    y = torch.empty((rows, t.shape[1]), dtype=torch.float64, device=t.device)
+    _lib.check(_lib.lib().fg_sosfiltfilt(t.data_ptr(), t.shape[0], t.shape[1], t.stride(0), sos.ctypes.data, nsec,
+                                         zi.ctypes.data, int(padlen), 0, step, y.data_ptr(), y.stride(0), _eng._stream()))
+    return _finish(y, on_dev, one_d)
+
+
 def decimate(x, q, n=None, zero_phase=True):
-    """scipy.signal.decimate(x, q, n, ftype="iir", axis=0, zero_phase=True) for every column."""
+    """scipy.signal.decimate(x, q, n, ftype="iir", axis=0, zero_phase=True) for every column: Chebyshev type I
+    low-pass of order n (default 8) as second-order sections, forwards and backwards, then every q-th sample."""
     if not zero_phase:
         raise NotImplementedError("decimate: only the zero-phase (filtfilt) variant the scripts use")
     q = int(q)
     n = 8 if n is None else int(n)
-    b, a = _sp.cheby1(n, 0.05, 0.8 / q)                    # scipy/signal/_signaltools.py decimate(), ftype="iir"
-    b, a, zi = _design(b, a)
-    padlen = 3 * max(len(a), len(b))                        # filtfilt's default
-    t, on_dev, one_d = _prep(x)
-    if t.shape[0] <= padlen:
-        raise ValueError("The length of the input vector x must be greater than padlen, which is %d." % padlen)
-    rows = (t.shape[0] + q - 1) // q
-    y = torch.empty((rows, t.shape[1]), dtype=torch.float64, device=t.device)
-    _lib.check(_lib.lib().fg_filtfilt_decimate(t.data_ptr(), t.shape[0], t.shape[1], t.stride(0), b.ctypes.data, len(b),
-                                               a.ctypes.data, len(a), zi.ctypes.data, int(padlen), q, y.data_ptr(),
-                                               y.stride(0), _eng._stream()))
-    return _finish(y, on_dev, one_d)
+    sos = _sp.cheby1(n, 0.05, 0.8 / q, output="sos")      # scipy/signal/_signaltools.py decimate(), ftype="iir"
+    return sosfiltfilt(sos, x, step=q)
 
 
 def decimate_blocks(W, nblocks, q=10):

@@ -207,13 +207,18 @@ int fg_filtfilt(const double* x_dev, int64_t N, int32_t ncols, int64_t ldx, cons
 /* diag(W^T W) of a dense device matrix (rows x p, ld = ldw) - the column norms get_index_eliminate and
  * eliminate_non_dynaffect threshold (regressor.py:243,271: np.diag(np.dot(W.T, W))).  Any width. */
 int fg_colsq_dense(const double* W_dev, int64_t ldw, int64_t rows, int32_t p, double* colsq_host, void* stream);
-/* scipy.signal.decimate(x, q, zero_phase=True) per column (examples/tiago/identification.py:142-187 applies it to
- * tau and to every column of the reduced regressor): filtfilt(b, a, padtype="odd", padlen) with the caller's design
- * (scipy's default is cheby1(8, 0.05, 0.8 / q), padlen 3 * max(len(a), len(b))), rows 0, q, 2q, ... written to y
- * (ceil(N / q) rows). */
+/* filtfilt(b, a, padtype="odd", padlen) per column followed by y[::q] - the transfer-function form of a zero-phase
+ * decimation (scipy < 1.5 and complex designs; current scipy decimates through fg_sosfiltfilt's second-order
+ * sections).  Rows 0, q, 2q, ... are written to y (ceil(N / q) rows). */
 int fg_filtfilt_decimate(const double* x_dev, int64_t N, int32_t ncols, int64_t ldx, const double* b_host, int32_t nb,
                          const double* a_host, int32_t na, const double* zi_host, int32_t padlen, int32_t q,
                          double* y_dev, int64_t ldy, void* stream);
+/* scipy.signal.sosfiltfilt(sos, x, axis=0, padtype="odd", padlen)[trim : N - trim : step] per column: what
+ * scipy.signal.decimate(x, q, zero_phase=True) runs on its cheby1(8, 0.05, 0.8 / q, output="sos") design
+ * (examples/tiago/identification.py:142-187).  sos: nsec x 6 host array (a0 == 1), zi = sosfilt_zi(sos) (nsec x 2). */
+int fg_sosfiltfilt(const double* x_dev, int64_t N, int32_t ncols, int64_t ldx, const double* sos_host, int32_t nsec,
+                   const double* zi_host, int32_t padlen, int64_t trim, int32_t step, double* y_dev, int64_t ldy,
+                   void* stream);
 /* scipy.signal.medfilt(x[:, c], k) per column, zero padded (examples/tiago/identification.py:70,80). */
 int fg_medfilt(const double* x_dev, int64_t N, int32_t ncols, int64_t ldx, int32_t k, double* y_dev, int64_t ldy,
                void* stream);

@@ -254,3 +254,62 @@ def relative_stdev(W_b, phi_b, tau):
     sig2 = np.linalg.norm(tau - np.dot(W_b, phi_b)) ** 2 / (W_b.shape[0] - phi_b.shape[0])
     C = sig2 * np.linalg.inv(np.dot(W_b.T, W_b))
     return np.round(100 * np.sqrt(np.diag(C)) / np.abs(phi_b), 2)
+
+
+def _block_diag_columns(x, nblocks):
+    """(len(x), nblocks) matrix whose column j holds block j of x (len(x) / nblocks entries) in its own rows and zeros
+    elsewhere - what regressor.py:319-345 / :436-470 assemble with nested concatenations."""
+    x = np.asarray(x, dtype=float).reshape(-1)
+    n = len(x) // nblocks
+    out = np.zeros((len(x), nblocks))
+    for j in range(nblocks):
+        out[j * n:(j + 1) * n, j] = x[j * n:(j + 1) * n]
+    return out
+
+
+def _tls_solution(W_tot, mass_load):
+    """regressor.py:405-410 / :495-500: last right singular vector, scaled so that its last entry is the payload mass."""
+    _, _, Vh = np.linalg.svd(W_tot, full_matrices=False)
+    V = Vh.T.conj()
+    V_norm = mass_load * np.divide(V[:, -1], V[-1, -1])
+    return V_norm, W_tot @ V_norm
+
+
+def build_total_regressor_current(W_b_u, W_b_l, W_l, I_u, I_l, param_standard_l, param):
+    """regressor.py:296-410 - total-least-squares regressor of a payload identification from joint currents:
+    [-W_b (unloaded; loaded) | currents, one column per joint | payload columns of the loaded body | its mass column]."""
+    n_samples = param["nb_samples"]
+    nb_joints = int(len(I_u) / n_samples)
+    top = len(W_b_u)
+    cur = np.vstack([_block_diag_columns(np.asarray(I_u)[:nb_joints * n_samples], nb_joints),
+                     _block_diag_columns(np.asarray(I_l)[:nb_joints * n_samples], nb_joints)])
+    if param["has_friction"]:
+        width, ks = 12, [0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 11]
+    elif param["has_actuator_inertia"]:
+        width, ks = 14, [0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 11, 12, 13]
+    else:
+        width, ks = 10, list(range(9))
+    base = param["which_body_loaded"] * width
+    W_l_temp = np.zeros((len(W_l), width if width != 10 else 9))
+    for k in ks:
+        W_l_temp[:, k] = W_l[:, base + k]
+    idx_e, _ = get_index_eliminate(W_l_temp, param_standard_l, 1e-6)
+    W_e_l = build_regressor_reduced(W_l_temp, idx_e)
+    upayload = np.vstack([np.zeros((len(W_l), W_e_l.shape[1])), -W_e_l])
+    kpayload = np.vstack([np.zeros((len(W_l), 1)), -W_l[:, base + 9].reshape(-1, 1)])
+    W_tot = np.hstack([np.vstack([-W_b_u, -W_b_l]), cur, upayload, kpayload])
+    assert top + len(W_b_l) == len(W_tot)
+    V_norm, residue = _tls_solution(W_tot, param["mass_load"])
+    return W_tot, V_norm, residue
+
+
+def build_total_regressor_wrench(W_b_u, W_b_l, W_l, tau_u, tau_l, param_standard_l, param):
+    """regressor.py:413-500 - the same with external-wrench measurements: six wrench columns instead of the currents,
+    the nine payload columns kept without elimination."""
+    wr = np.vstack([_block_diag_columns(tau_u, 6), _block_diag_columns(tau_l, 6)])
+    base = param["which_body_loaded"] * 10
+    upayload = np.vstack([np.zeros((len(W_l), 9)), -W_l[:, base:base + 9]])
+    kpayload = np.vstack([np.zeros((len(W_l), 1)), -W_l[:, base + 9].reshape(-1, 1)])
+    W_tot = np.hstack([np.vstack([-W_b_u, -W_b_l]), wr, upayload, kpayload])
+    V_norm, residue = _tls_solution(W_tot, param["mass_load"])
+    return W_tot, V_norm, residue

@@ -322,3 +322,32 @@ def test_human_free_flyer_560_columns_drop_in():
     assert (idx_e, params_r) == ref_path.get_index_eliminate(Wref, std, 1e-6)
     W_e = build_regressor_reduced(W, idx_e)
     assert get_baseIndex(W_e, params_r) == ref_path.get_baseIndex(ref_path.build_regressor_reduced(Wref, idx_e), params_r)
+
+
+def test_total_least_squares_payload_regressors():
+    """build_total_regressor_current / _wrench (regressor.py:296-500): W_tot identical to the oracle's, the TLS
+    vector (last right singular vector, from the R factor instead of the tall matrix) and the residue to 1e-9."""
+    from figaroh.tools.regressor import build_total_regressor_current, build_total_regressor_wrench
+    from oracle import ref_path
+    rng = np.random.default_rng(4)
+    ns, nj = 400, 6
+    for flags in ((True, False), (False, True), (False, False)):
+        width = 12 if flags[0] else (14 if flags[1] else 10)
+        W_l = rng.normal(size=(nj * ns, width * nj))
+        W_l[:, 5 * width + 2] = 0.0  # an eliminated payload column
+        W_b_u, W_b_l = rng.normal(size=(nj * ns, 20)), rng.normal(size=(nj * ns, 20))
+        I_u, I_l = rng.normal(size=nj * ns), rng.normal(size=nj * ns)
+        std = {f"p{i}": 0.0 for i in range(width * nj)}
+        param = dict(nb_samples=ns, has_friction=flags[0], has_actuator_inertia=flags[1], which_body_loaded=5, mass_load=3.0)
+        W, V, r = build_total_regressor_current(W_b_u, W_b_l, W_l, I_u, I_l, std, param)
+        W0, V0, r0 = ref_path.build_total_regressor_current(W_b_u, W_b_l, W_l, I_u, I_l, std, param)
+        assert np.array_equal(W, W0)
+        assert np.abs(V - V0).max() <= 1e-9 * np.abs(V0).max() and np.abs(r - r0).max() <= 1e-9 * np.abs(r0).max()
+    W_l = rng.normal(size=(6 * ns, 10 * nj))
+    W_b_u, W_b_l = rng.normal(size=(6 * ns, 25)), rng.normal(size=(6 * ns, 25))
+    tu, tl = rng.normal(size=6 * ns), rng.normal(size=6 * ns)
+    param = dict(which_body_loaded=5, mass_load=2.5)
+    W, V, r = build_total_regressor_wrench(W_b_u, W_b_l, W_l, tu, tl, {}, param)
+    W0, V0, r0 = ref_path.build_total_regressor_wrench(W_b_u, W_b_l, W_l, tu, tl, {}, param)
+    assert np.array_equal(W, W0)
+    assert np.abs(V - V0).max() <= 1e-9 * np.abs(V0).max() and np.abs(r - r0).max() <= 1e-9 * np.abs(r0).max()

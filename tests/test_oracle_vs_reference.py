@@ -120,3 +120,27 @@ def test_statistics_restatement_equals_reference():
     p = dict(idx_tau_stop=[100, 200, 300])
     assert np.array_equal(idt.weigthed_least_squares(R, phi, W, tau, W @ phi, p),
                           pre.weigthed_least_squares(3, phi, W, tau, W @ phi, p))
+
+
+def test_total_least_squares_regressors_equal_reference():
+    """regressor.py:296-500 (payload identification, total least squares) against the restatement."""
+    reg = pinshim.load_reference("regressor")
+    rng = np.random.default_rng(4)
+    ns, nj = 50, 6
+    for flags in ((True, False), (False, True), (False, False)):
+        width = 12 if flags[0] else (14 if flags[1] else 10)
+        W_l = rng.normal(size=(nj * ns, width * nj))
+        W_b_u, W_b_l = rng.normal(size=(nj * ns, 20)), rng.normal(size=(nj * ns, 20))
+        I_u, I_l = rng.normal(size=nj * ns), rng.normal(size=nj * ns)
+        std = {f"p{i}": 0.0 for i in range(width * nj)}
+        param = dict(nb_samples=ns, has_friction=flags[0], has_actuator_inertia=flags[1], which_body_loaded=5, mass_load=3.0)
+        a = reg.build_total_regressor_current(W_b_u, W_b_l, W_l, I_u, I_l, std, param)
+        b = ref_path.build_total_regressor_current(W_b_u, W_b_l, W_l, I_u, I_l, std, param)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    W_l = rng.normal(size=(6 * ns, 10 * nj))
+    W_b_u, W_b_l = rng.normal(size=(6 * ns, 25)), rng.normal(size=(6 * ns, 25))
+    tu, tl = rng.normal(size=6 * ns), rng.normal(size=6 * ns)
+    param = dict(which_body_loaded=5, mass_load=2.5)
+    a = reg.build_total_regressor_wrench(W_b_u, W_b_l, W_l, tu, tl, {}, param)
+    b = ref_path.build_total_regressor_wrench(W_b_u, W_b_l, W_l, tu, tl, {}, param)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
