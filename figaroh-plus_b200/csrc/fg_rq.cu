@@ -307,7 +307,7 @@ RqLaunch rq_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, co
     break;
   }
   if (rl.nw < 1) { rq_fail(why, "tile does not fit shared memory"); return rl; }
-  R.ring = std::max(8, env_int("FG_RQ_RING", 1024));
+  R.ring = std::max(8, env_int("FG_RQ_RING", 512));
   rl.ring_doubles = (int64_t)R.ring * R.slot_doubles;
   rl.rfull_doubles = (int64_t)T.nbf * (T.nbf + 1) / 2 * 64;
   rl.ok = true;

@@ -200,6 +200,18 @@ class TsqrState:
             self._h = None
 
     @property
+    def params_base(self):
+        if self._params_base is None:
+            nb_ = [self.params_r[i] for i in self.idx_base]
+            ng_ = [self.params_r[i] for i in self.idx_regroup]
+            self._params_base = expressions(nb_, ng_, self.beta)
+        return self._params_base
+
+    @params_base.setter
+    def params_base(self, value):
+        self._params_base = value
+
+    @property
     def rows(self):
         return int(_lib.lib().fg_state_rows(self._h))
 
@@ -390,7 +402,7 @@ class BaseSolution:
         self.phi_b = None        # np.round(., 6)
         self.R1 = None
         self.resid2 = None       # |tau - W_b phi_b|^2
-        self.params_base = []    # expression strings
+        self._params_base = None  # expression strings, built on first access (string work stays off the hot loop)
         self.phi_std = None
         self._rows = None        # rows of the regressor (fetched lazily: after a multi-GPU merge it lives on the device)
         self._state = None
@@ -505,7 +517,6 @@ def solve_state(state: TsqrState, names, tol_e=None, idx_e=None, tol_qr=TOL_QR, 
             for j in range(sol.beta.shape[1]):
                 ps[i] = ps[i] + sol.beta[i, j] * params_std[ng_[j]]
         sol.phi_std = np.around(ps, 5)
-    sol.params_base = expressions(nb_, ng_, sol.beta)
     return sol
 
 
