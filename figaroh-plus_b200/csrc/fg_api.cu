@@ -16,6 +16,7 @@
 #include "fg_gq.h"
 #include "fg_rq.h"
 #include "fg_wide.h"
+#include "fg_matz.h"
 #include "fg_prefilter.cuh"
 
 using namespace fg;
@@ -48,12 +49,16 @@ struct DevPlan {
   std::vector<int> nact, fullcol;
   void* d_blob = nullptr;  // one allocation holding everything
   DevPlanPtrs ptrs{};
+  // materialising kernel, second version (fg_matz.cuh)
+  bool matz_tried = false;
+  MatzPlan matz;
+  void* d_matz_tab = nullptr;
   // fifth-generation kernel (fg_ringqr.cuh)
   bool rq_tried = false;
   RqLaunch rql;
   std::unique_ptr<RqParams> rq;
   void* d_rq_tab = nullptr;
-  ~DevPlan() { if (d_blob) cudaFree(d_blob); if (d_rq_tab) cudaFree(d_rq_tab); }
+  ~DevPlan() { if (d_blob) cudaFree(d_blob); if (d_rq_tab) cudaFree(d_rq_tab); if (d_matz_tab) cudaFree(d_matz_tab); }
 };
 
 struct fg_model {
@@ -480,6 +485,24 @@ extern "C" int fg_regressor_materialize(const fg_model* mc, const fg_regressor_c
   if (ldw < pl->P.ncols) return set_err(FG_ERR_INVALID, "ldw=%lld smaller than %d columns", (long long)ldw, pl->P.ncols);
   cudaStream_t st = (cudaStream_t)stream;
   const int ms = pl->P.ms;
+  {  // second version: the producers' walk, one sample per lane, 14-column patches (fg_matz.cuh)
+    const char* e = getenv("FG_USE_MATZ");
+    const bool use = !(e && e[0] == '0');
+    if (use && !pl->matz_tried) {
+      pl->matz_tried = true;
+      pl->matz = matz_build(pl->P, m->joints.data(), pl->rows.data(), m->mass.data(), pl->P.ncols, m->sm_count, m->max_smem);
+      if (pl->matz.ok) {
+        FG_CUDA(cudaMalloc(&pl->d_matz_tab, matz_tables_bytes()));
+        FG_CUDA(cudaMemcpy(pl->d_matz_tab, pl->matz.tab.get(), matz_tables_bytes(), cudaMemcpyHostToDevice));
+      }
+    }
+    if (use && pl->matz.ok) {
+      cudaError_t ce = matz_launch(pl->matz, static_cast<const MatzTables*>(pl->d_matz_tab), q, v, a, N, W, ldw, st);
+      if (ce != cudaSuccess) return set_err(FG_ERR_CUDA, "materialise kernel failed: %s", cudaGetErrorString(ce));
+      FG_LAUNCHED();
+      return FG_OK;
+    }
+  }
   if (ms <= 8) return launch_materialize<8, 4>(m, pl, q, v, a, N, W, ldw, st);
   if (ms <= 24) return launch_materialize<24, 1>(m, pl, q, v, a, N, W, ldw, st);
   if (ms <= 48) return launch_materialize<48, 1>(m, pl, q, v, a, N, W, ldw, st);

@@ -1,0 +1,75 @@
+// fg_matz.cu - host side of the materialising kernel (fg_matz.cuh): tables of the walk over the whole tree for all row
+// blocks, launch.
+#include <algorithm>
+#include <cstring>
+
+#include "fg_matz.cuh"
+#include "fg_matz.h"
+
+namespace fg {
+
+size_t matz_tables_bytes() { return sizeof(MatzTables); }
+
+MatzPlan matz_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, const double* mass, int ncols_full,
+                    int sm_count, int max_smem) {
+  MatzPlan mp;
+  const int nj = P.nj, ms = P.ms, nb = nj - 1;
+  if (ms < 1 || ms > 32 || nj > kMaxJoints) return mp;
+  std::vector<char> need(nj, 1);
+  need[0] = 0;
+  std::vector<unsigned> own(nj, 0u), live(nj, 0u);
+  for (int g = 0; g < ms; ++g) own[rows[g].joint] |= 1u << g;
+  for (int i = 1; i < nj; ++i) live[i] = live[joints[i].parent] | own[i];
+  const RqWalk walk = rq_build_walk(nj, joints, need, own, live, kMaxJoints, 2 * kMaxJoints);
+  if (!walk.ok || (int)walk.order.size() != nb) return mp;
+  mp.tab.reset(new MatzTables);
+  MatzTables& T = *mp.tab;
+  memset(&T, 0, sizeof T);
+  MatzParams& M = mp.prm;
+  memset(&M, 0, sizeof M);
+  M.nj = nj; M.nq = P.nq; M.nv = P.nv; M.ms = ms; M.nops = (int)walk.ops.size(); M.nproc = nb;
+  M.mode = P.mode; M.flags = P.flags; M.nvslots = walk.nvslots; M.nmslots = walk.nmslots;
+  M.coupling = ncols_full > 14 * nb ? 1 : 0;
+  for (int k = 0; k < 3; ++k) M.gravity[k] = P.gravity[k];
+  for (int t = 0; t < nb; ++t) { T.pj[t] = joints[walk.order[t]]; T.body_of_t[t] = walk.order[t]; }
+  for (int o = 0; o < M.nops; ++o) T.ops[o] = walk.ops[o];
+  for (int g = 0; g < ms; ++g) {
+    for (int k = 0; k < 6; ++k) T.S[g][k] = rows[g].S[k];
+    T.rowblock[g] = rows[g].rowblock;
+    T.rowjoint[g] = rows[g].joint;
+  }
+  for (int b = 1; b < nj; ++b) {
+    T.inertial[b] = !(P.mode == 1 /* external wrench */ && mass[b] == 0.0);
+    int eg = -2;
+    if (b - 1 < P.nv) {  // the reference indexes v[i, b] (regressor.py:145-158)
+      if (P.mode == 1) eg = -1;
+      else
+        for (int g = 0; g < ms; ++g)
+          if (rows[g].rowblock == b - 1) eg = g;
+    }
+    T.extra_grp[b] = eg;
+  }
+  M.smem_per_warp = (ms * 6 + 12 * (M.nvslots + M.nmslots)) * 32 + MATZ_STAGE + 2;
+  M.smem_per_warp += M.smem_per_warp & 1;
+  const int tab_bytes = (int)((sizeof(MatzTables) + 15) / 16) * 16;
+  int nw = 16;
+  while (nw > 0 && tab_bytes + nw * M.smem_per_warp * 8 > max_smem) --nw;
+  if (nw < 4) { mp.tab.reset(); return mp; }
+  mp.nw = nw;
+  mp.smem = tab_bytes + nw * M.smem_per_warp * 8;
+  mp.sm_count = sm_count;
+  mp.ok = true;
+  return mp;
+}
+
+cudaError_t matz_launch(const MatzPlan& mp, const MatzTables* d_tab, const double* q, const double* v, const double* a,
+                        int64_t N, double* W, int64_t ldw, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(matz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mp.smem);
+  if (e != cudaSuccess) return e;
+  const int64_t ntiles = (N + 31) / 32;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((ntiles + mp.nw - 1) / mp.nw, mp.sm_count));
+  matz_kernel<<<grid, mp.nw * 32, mp.smem, st>>>(mp.prm, d_tab, q, v, a, N, W, ldw);
+  return cudaGetLastError();
+}
+
+}  // namespace fg

@@ -89,48 +89,58 @@ __device__ __forceinline__ void rq_emit(double* gslot, int ed, const double* sl,
 }
 
 // ---------------------------------------------------------------------------------------------
-// One tile (32 samples, one per lane) of EVERY row group into a ring slot.
-// ps: this producer warp's shared memory: axes [ms][6][32], saved (v, a) [nvslots][12][32], saved joint
-// transforms [nmslots][12][32].
-static __device__ __forceinline__ void rq_produce_tile(const RqParams& P, const GqGen& S, const RqOp* ops, double* ps,
-                                                       double* slot, const double* __restrict__ q,
-                                                       const double* __restrict__ qd, const double* __restrict__ qdd,
-                                                       const double* __restrict__ tau, int64_t ld_tau, int64_t s0,
-                                                       int64_t N, int lane) {
-  const int ms = P.gq.ms;
+// The producers' depth-first walk over the kinematic tree for one tile (32 samples, one per lane).
+// ps: this warp's shared memory: axes [ms][6][32], saved (v, a) [nvslots][12][32], saved joint transforms
+// [nmslots][12][32].  What happens to the entries s_g^T B_b is the Sink's business:
+//   sink.body_begin(op, cv0, ca0)                     before the entries of the body of a DESCEND step
+//   sink.emit(g, t, sl, sa, om, al, ap)               row group g (axis [sl; sa] in the body frame), walk index t
+//   sink.body_end(op)                                 after them
+struct RqWalkCtx {
+  const DevJoint* pj;   // joints in walk order
+  const RqOp* ops;
+  int nops, ms, nq, nv, nvslots;
+  double gravity[3];
+};
+
+template <class Sink>
+static __device__ __forceinline__ void rq_walk_tile(const RqWalkCtx& C, const double* Sbase, int Sstride /* doubles */,
+                                                    double* ps, const double* __restrict__ q,
+                                                    const double* __restrict__ qd, const double* __restrict__ qdd,
+                                                    int64_t s0, int64_t N, int lane, Sink& sink) {
+  const int ms = C.ms;
   const int64_t smp = s0 + lane;
   const bool valid = smp < N;
   const int64_t sc = valid ? smp : N - 1;
-  const double* qs = q + sc * P.gq.nq;
-  const double* vs = qd + sc * P.gq.nv;
-  const double* as = qdd + sc * P.gq.nv;
+  const double* qs = q + sc * C.nq;
+  const double* vs = qd + sc * C.nv;
+  const double* as = qdd + sc * C.nv;
   double* AX = ps + lane;                         // AX[(g * 6 + k) * 32]
   double* VS = ps + ms * 6 * 32 + lane;           // VS[(slot * 12 + k) * 32]
-  double* MS = VS + P.nvslots * 12 * 32;          // MS[(slot * 12 + k) * 32]
+  double* MS = VS + C.nvslots * 12 * 32;          // MS[(slot * 12 + k) * 32]
   double v[6] = {0, 0, 0, 0, 0, 0}, a[6] = {0, 0, 0, 0, 0, 0};
   double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0};
   // inputs of the first joint; afterwards requested one descend ahead
   double nq0 = 0.0, nv0 = 0.0, na0 = 0.0;
   {
-    const DevJoint& j0 = S.pj[ops[0].t];
+    const DevJoint& j0 = C.pj[C.ops[0].t];
     nq0 = __ldg(qs + j0.idx_q); nv0 = __ldg(vs + j0.idx_v); na0 = __ldg(as + j0.idx_v);
   }
-  const int nops = P.nops;
+  const int nops = C.nops;
   for (int o = 0; o < nops; ++o) {
-    const RqOp op = ops[o];
+    const RqOp op = C.ops[o];
     if (op.kind == 0) {
-      const DevJoint& jt = S.pj[op.t];
+      const DevJoint& jt = C.pj[op.t];
       if (op.vsave != 255) {
         for (int k = 0; k < 6; ++k) { VS[(op.vsave * 12 + k) * 32] = v[k]; VS[(op.vsave * 12 + 6 + k) * 32] = a[k]; }
       }
       if (op.from_universe) {
         for (int k = 0; k < 6; ++k) v[k] = 0.0;
-        a[0] = -P.gq.gravity[0]; a[1] = -P.gq.gravity[1]; a[2] = -P.gq.gravity[2];
+        a[0] = -C.gravity[0]; a[1] = -C.gravity[1]; a[2] = -C.gravity[2];
         a[3] = a[4] = a[5] = 0.0;
       }
       const double cq0 = nq0, cv0 = nv0, ca0 = na0;
       if (op.pad != 255) {  // the next descend's joint
-        const DevJoint& jn = S.pj[op.pad];
+        const DevJoint& jn = C.pj[op.pad];
         nq0 = __ldg(qs + jn.idx_q); nv0 = __ldg(vs + jn.idx_v); na0 = __ldg(as + jn.idx_v);
       }
       double Rj[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, pj[3] = {0, 0, 0};
@@ -179,6 +189,7 @@ static __device__ __forceinline__ void rq_produce_tile(const RqParams& P, const 
       double ap[3];
       cross3(v + 3, v, ap);  // classical acceleration a' = a_lin + w x v_lin
       for (int k = 0; k < 3; ++k) ap[k] += a[k];
+      sink.body_begin(op, cv0, ca0);
       // row groups whose axis is live: transport into this frame and emit; then the groups that start here
       for (unsigned m = op.live; m; m &= m - 1) {
         const int g = __ffs(m) - 1;
@@ -186,17 +197,16 @@ static __device__ __forceinline__ void rq_produce_tile(const RqParams& P, const 
         for (int k = 0; k < 3; ++k) { sl[k] = AX[(g * 6 + k) * 32]; sa[k] = AX[(g * 6 + 3 + k) * 32]; }
         rq_actinv(R, p, sl, sa, nl, na);
         for (int k = 0; k < 3; ++k) { AX[(g * 6 + k) * 32] = nl[k]; AX[(g * 6 + 3 + k) * 32] = na[k]; }
-        const int ed = S.emit[g][op.t];
-        if (ed) rq_emit(slot + P.goff[g], ed, nl, na, v + 3, a + 3, ap, valid, lane);
+        sink.emit(g, op.t, nl, na, v + 3, a + 3, ap);
       }
       for (unsigned m = op.own; m; m &= m - 1) {
         const int g = __ffs(m) - 1;
         double sl[3], sa[3];
-        for (int k = 0; k < 3; ++k) { sl[k] = S.grp[g].S[k]; sa[k] = S.grp[g].S[3 + k]; }
+        for (int k = 0; k < 3; ++k) { sl[k] = Sbase[g * Sstride + k]; sa[k] = Sbase[g * Sstride + 3 + k]; }
         for (int k = 0; k < 3; ++k) { AX[(g * 6 + k) * 32] = sl[k]; AX[(g * 6 + 3 + k) * 32] = sa[k]; }
-        const int ed = S.emit[g][op.t];
-        if (ed) rq_emit(slot + P.goff[g], ed, sl, sa, v + 3, a + 3, ap, valid, lane);
+        sink.emit(g, op.t, sl, sa, v + 3, a + 3, ap);
       }
+      sink.body_end(op);
     } else {
       for (int k = 0; k < 9; ++k) R[k] = MS[(op.mslot * 12 + k) * 32];
       for (int k = 0; k < 3; ++k) p[k] = MS[(op.mslot * 12 + 9 + k) * 32];
@@ -212,6 +222,42 @@ static __device__ __forceinline__ void rq_produce_tile(const RqParams& P, const 
       }
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One tile (32 samples, one per lane) of EVERY row group into a ring slot.
+struct RqRingSink {
+  const RqParams* P;
+  const GqGen* S;
+  double* slot;
+  bool valid;
+  int lane;
+  __device__ __forceinline__ void body_begin(const RqOp&, double, double) {}
+  __device__ __forceinline__ void body_end(const RqOp&) {}
+  __device__ __forceinline__ void emit(int g, int t, const double* sl, const double* sa, const double* om, const double* al,
+                                       const double* ap) {
+    const int ed = S->emit[g][t];
+    if (ed) rq_emit(slot + P->goff[g], ed, sl, sa, om, al, ap, valid, lane);
+  }
+};
+
+static __device__ __forceinline__ void rq_produce_tile(const RqParams& P, const GqGen& S, const RqOp* ops, double* ps,
+                                                       double* slot, const double* __restrict__ q,
+                                                       const double* __restrict__ qd, const double* __restrict__ qdd,
+                                                       const double* __restrict__ tau, int64_t ld_tau, int64_t s0,
+                                                       int64_t N, int lane) {
+  const int ms = P.gq.ms;
+  const int64_t smp = s0 + lane;
+  const bool valid = smp < N;
+  const int64_t sc = valid ? smp : N - 1;
+  const double* vs = qd + sc * P.gq.nv;
+  const double* as = qdd + sc * P.gq.nv;
+  RqWalkCtx C;
+  C.pj = S.pj; C.ops = ops; C.nops = P.nops; C.ms = ms; C.nq = P.gq.nq; C.nv = P.gq.nv; C.nvslots = P.nvslots;
+  for (int k = 0; k < 3; ++k) C.gravity[k] = P.gq.gravity[k];
+  static_assert(sizeof(GqGroup) % 8 == 0, "GqGroup must be a whole number of doubles");
+  RqRingSink sink{&P, &S, slot, valid, lane};
+  rq_walk_tile(C, S.grp[0].S, (int)(sizeof(GqGroup) / 8), ps, q, qd, qdd, s0, N, lane, sink);
   // columns read straight off the inputs (friction / actuator inertia / offset / coupling / rhs)
   for (int g = 0; g < ms; ++g) {
     const GqGroup& G = S.grp[g];

@@ -21,6 +21,95 @@ static int env_int(const char* name, int dflt) {
   return atoi(e);
 }
 
+// Depth-first walk program over the joints marked in `need` (fg_rq.h: RqOp).  Children are visited with the deepest
+// needed subtree last, so the main chain is never walked back up; every other child subtree is a side trip: the
+// parent's (v, a) is saved before it, the joint transforms inside it are saved as it descends, and it is walked
+// back up (axes transported with the inverse action) when it is done.
+RqWalk rq_build_walk(int nj, const DevJoint* joints, const std::vector<char>& need, const std::vector<unsigned>& own,
+                     const std::vector<unsigned>& live, int max_proc, int max_ops) {
+  RqWalk W;
+  std::vector<std::vector<int>> kids(nj);
+  std::vector<int> height(nj, 0);
+  for (int i = nj - 1; i >= 1; --i)
+    if (need[i]) {
+      const int pa = joints[i].parent;
+      height[pa] = std::max(height[pa], height[i] + 1);
+    }
+  for (int i = 1; i < nj; ++i)
+    if (need[i]) kids[joints[i].parent].push_back(i);
+  for (int b = 0; b < nj; ++b)
+    std::stable_sort(kids[b].begin(), kids[b].end(), [&](int x, int y) { return height[x] < height[y]; });
+  int vdepth = 0;
+  bool fail = false;
+  std::vector<int> path;   // nodes of the current side trip (every one of them has its transform saved)
+  std::vector<int> mslot_of(nj, 255), tof(nj, -1);
+  auto push_op = [&](const RqOp& op) {
+    if ((int)W.ops.size() >= max_ops) { fail = true; return; }
+    W.ops.push_back(op);
+  };
+  std::function<void(int, bool)> visit = [&](int b, bool in_trip) {
+    for (size_t ci = 0; ci < kids[b].size() && !fail; ++ci) {
+      const int c = kids[b][ci];
+      const bool last = ci + 1 == kids[b].size();
+      const bool side = !last && b != 0;          // we come back to b afterwards
+      const bool trip = in_trip || side;
+      if ((int)W.order.size() >= max_proc) { fail = true; return; }
+      tof[c] = (int)W.order.size();
+      W.order.push_back(c);
+      RqOp op;
+      memset(&op, 0, sizeof op);
+      op.kind = 0; op.t = (unsigned char)tof[c];
+      op.vsave = 255; op.msave = 255; op.vload = 255; op.mslot = 255; op.pad = 255;
+      op.from_universe = b == 0;
+      int my_vslot = 255;
+      if (side) {
+        if (vdepth >= RQ_MAXSLOTS) { fail = true; return; }
+        my_vslot = vdepth++;
+        W.nvslots = std::max(W.nvslots, vdepth);
+        op.vsave = (unsigned char)my_vslot;
+      }
+      const size_t path_mark = path.size();
+      if (trip) {
+        if ((int)path.size() >= RQ_MAXSLOTS) { fail = true; return; }
+        mslot_of[c] = (int)path.size();
+        op.msave = (unsigned char)mslot_of[c];
+        path.push_back(c);
+        W.nmslots = std::max(W.nmslots, (int)path.size());
+      }
+      op.live = b == 0 ? 0u : live[b];
+      op.own = own[c];
+      push_op(op);
+      visit(c, trip);
+      if (side) {  // walk back up to b
+        while (path.size() > path_mark && !fail) {
+          const int x = path.back();
+          path.pop_back();
+          RqOp up;
+          memset(&up, 0, sizeof up);
+          up.kind = 1; up.t = (unsigned char)tof[x];
+          up.vsave = 255; up.msave = 255; up.vload = 255; up.pad = 255;
+          up.mslot = (unsigned char)mslot_of[x];
+          up.live = live[joints[x].parent];
+          if (path.size() == path_mark) up.vload = (unsigned char)my_vslot;
+          push_op(up);
+        }
+        --vdepth;
+      } else if (b == 0 && !last) {
+        path.resize(path_mark);  // a chain hanging off the universe is simply left behind
+      }
+    }
+  };
+  visit(0, false);
+  if (fail) return W;
+  {  // input prefetch: walk index of the next descend
+    int nxt = 255;
+    for (int o = (int)W.ops.size() - 1; o >= 0; --o)
+      if (W.ops[o].kind == 0) { W.ops[o].pad = (unsigned char)nxt; nxt = W.ops[o].t; }
+  }
+  W.ok = true;
+  return W;
+}
+
 RqLaunch rq_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, const ColDesc* cols, int sm_count,
                   int max_smem, RqParams* out, const char** why) {
   RqLaunch rl;
@@ -64,96 +153,22 @@ RqLaunch rq_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, co
     }
   for (int g = 0; g < ms; ++g)
     for (int i = rows[g].joint; i > 0; i = joints[i].parent) need[i] = 1;
-  // children lists, the child with the deepest needed subtree last (the main chain is never walked back up)
-  std::vector<std::vector<int>> kids(nj);
-  std::vector<int> height(nj, 0);
-  for (int i = nj - 1; i >= 1; --i)
-    if (need[i]) {
-      const int pa = joints[i].parent;
-      height[pa] = std::max(height[pa], height[i] + 1);
-    }
-  for (int i = 1; i < nj; ++i)
-    if (need[i]) kids[joints[i].parent].push_back(i);
-  for (int b = 0; b < nj; ++b)
-    std::stable_sort(kids[b].begin(), kids[b].end(), [&](int x, int y) { return height[x] < height[y]; });
   // row groups carried by a joint / live at a body
   std::vector<unsigned> own(nj, 0u), live(nj, 0u);
   for (int g = 0; g < ms; ++g) own[rows[g].joint] |= 1u << g;
   for (int i = 1; i < nj; ++i) live[i] = live[joints[i].parent] | own[i];
-  // ---- depth-first walk program
-  std::vector<int> tof(nj, -1);
-  int nproc = 0, nops = 0, nv_used = 0, nm_used = 0, vdepth = 0;
-  bool fail = false;
-  std::vector<int> path;   // nodes of the current side trip (every one of them has its transform saved)
-  std::vector<int> mslot_of(nj, 255);
-  auto push_op = [&](const RqOp& op) {
-    if (nops >= RQ_MAXOPS) { fail = true; return; }
-    R.ops[nops++] = op;
-  };
-  std::function<void(int, bool)> visit = [&](int b, bool in_trip) {
-    for (size_t ci = 0; ci < kids[b].size() && !fail; ++ci) {
-      const int c = kids[b][ci];
-      const bool last = ci + 1 == kids[b].size();
-      const bool side = !last && b != 0;          // we come back to b afterwards
-      const bool trip = in_trip || side;
-      if (nproc >= GQ_MAXPROC) { fail = true; return; }
-      T.gen.pj[nproc] = joints[c];
-      tof[c] = nproc++;
-      RqOp op;
-      memset(&op, 0, sizeof op);
-      op.kind = 0; op.t = (unsigned char)tof[c];
-      op.vsave = 255; op.msave = 255; op.vload = 255; op.mslot = 255; op.pad = 255;
-      op.from_universe = b == 0;
-      int my_vslot = 255;
-      if (side) {
-        if (vdepth >= RQ_MAXSLOTS) { fail = true; return; }
-        my_vslot = vdepth++;
-        nv_used = std::max(nv_used, vdepth);
-        op.vsave = (unsigned char)my_vslot;
-      }
-      const size_t path_mark = path.size();
-      if (trip) {
-        if ((int)path.size() >= RQ_MAXSLOTS) { fail = true; return; }
-        mslot_of[c] = (int)path.size();
-        op.msave = (unsigned char)mslot_of[c];
-        path.push_back(c);
-        nm_used = std::max(nm_used, (int)path.size());
-      }
-      op.live = b == 0 ? 0u : live[b];
-      op.own = own[c];
-      push_op(op);
-      visit(c, trip);
-      if (side) {  // walk back up to b
-        while (path.size() > path_mark && !fail) {
-          const int x = path.back();
-          path.pop_back();
-          RqOp up;
-          memset(&up, 0, sizeof up);
-          up.kind = 1; up.t = (unsigned char)tof[x];
-          up.vsave = 255; up.msave = 255; up.vload = 255; up.pad = 255;
-          up.mslot = (unsigned char)mslot_of[x];
-          up.live = live[joints[x].parent];
-          if (path.size() == path_mark) up.vload = (unsigned char)my_vslot;
-          push_op(up);
-        }
-        --vdepth;
-      } else if (b == 0 && !last) {
-        path.resize(path_mark);  // a chain hanging off the universe is simply left behind
-      }
-    }
-  };
-  visit(0, false);
-  if (fail) { rq_fail(why, "kinematic tree too large for the walk program"); return rl; }
+  const RqWalk walk = rq_build_walk(nj, joints, need, own, live, GQ_MAXPROC, RQ_MAXOPS);
+  if (!walk.ok) { rq_fail(why, "kinematic tree too large for the walk program"); return rl; }
+  const int nproc = (int)walk.order.size(), nops = (int)walk.ops.size();
   if (nproc < 1) { rq_fail(why, "no joint to walk"); return rl; }
+  std::vector<int> tof(nj, -1);
+  for (int t = 0; t < nproc; ++t) { tof[walk.order[t]] = t; T.gen.pj[t] = joints[walk.order[t]]; }
+  for (int o = 0; o < nops; ++o) R.ops[o] = walk.ops[o];
+  const int nv_used = walk.nvslots, nm_used = walk.nmslots;
   T.nproc = nproc;
   R.nops = nops;
   R.nvslots = nv_used;
   R.nmslots = nm_used;
-  {  // input prefetch: walk index of the next descend
-    int nxt = 255;
-    for (int o = nops - 1; o >= 0; --o)
-      if (R.ops[o].kind == 0) { R.ops[o].pad = (unsigned char)nxt; nxt = R.ops[o].t; }
-  }
   // ---- the local problem of every row group: per walked body its selected inertial columns in pinocchio
   //      parameter order, then the input-fed columns in the caller's order, then the rhs
   int maxnb = 0, n_emits = 0, n_simple = 0, n_transports = 0;

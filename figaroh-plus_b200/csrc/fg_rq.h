@@ -77,6 +77,16 @@ struct RqLaunch {
   const unsigned short* d_tab_i = nullptr;
 };
 
+// walk program over the joints marked in `need` (see fg_rq.cu); order[t] = joint index of walk index t
+struct RqWalk {
+  bool ok = false;
+  std::vector<RqOp> ops;
+  std::vector<int> order;
+  int nvslots = 0, nmslots = 0;
+};
+RqWalk rq_build_walk(int nj, const DevJoint* joints, const std::vector<char>& need, const std::vector<unsigned>& own,
+                     const std::vector<unsigned>& live, int max_proc, int max_ops);
+
 RqLaunch rq_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, const ColDesc* cols, int sm_count,
                   int max_smem, RqParams* out, const char** why);
 

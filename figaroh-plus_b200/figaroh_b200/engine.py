@@ -200,18 +200,6 @@ class TsqrState:
             self._h = None
 
     @property
-    def params_base(self):
-        if self._params_base is None:
-            nb_ = [self.params_r[i] for i in self.idx_base]
-            ng_ = [self.params_r[i] for i in self.idx_regroup]
-            self._params_base = expressions(nb_, ng_, self.beta)
-        return self._params_base
-
-    @params_base.setter
-    def params_base(self, value):
-        self._params_base = value
-
-    @property
     def rows(self):
         return int(_lib.lib().fg_state_rows(self._h))
 
@@ -406,6 +394,18 @@ class BaseSolution:
         self.phi_std = None
         self._rows = None        # rows of the regressor (fetched lazily: after a multi-GPU merge it lives on the device)
         self._state = None
+
+    @property
+    def params_base(self):
+        if self._params_base is None:
+            nb_ = [self.params_r[i] for i in self.idx_base]
+            ng_ = [self.params_r[i] for i in self.idx_regroup]
+            self._params_base = expressions(nb_, ng_, self.beta)
+        return self._params_base
+
+    @params_base.setter
+    def params_base(self, value):
+        self._params_base = value
 
     @property
     def rows(self):

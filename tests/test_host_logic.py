@@ -150,3 +150,13 @@ def test_shard_range_partitions_everything():
         assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
         sizes = [hi - lo for lo, hi in parts]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_base_solution_builds_expressions_lazily():
+    """The expression strings of qrdecomposition.py:160-183 are built on first access, not in the solve."""
+    import numpy as np
+    from figaroh_b200 import engine as eng
+    s = eng.BaseSolution()
+    s.params_r, s.idx_base, s.idx_regroup = ["a", "b", "c"], [0, 2], [1]
+    s.beta = np.array([[0.5], [-2e-7]])
+    assert s.params_base == ["a + 0.5*b", "c"] and s.rows == 0
