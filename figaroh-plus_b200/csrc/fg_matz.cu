@@ -52,7 +52,7 @@ MatzPlan matz_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, 
   M.smem_per_warp = (ms * 6 + 12 * (M.nvslots + M.nmslots)) * 32 + MATZ_STAGE + 2;
   M.smem_per_warp += M.smem_per_warp & 1;
   const int tab_bytes = (int)((sizeof(MatzTables) + 15) / 16) * 16;
-  int nw = 16;
+  int nw = MATZ_WARPS;
   while (nw > 0 && tab_bytes + nw * M.smem_per_warp * 8 > max_smem) --nw;
   if (nw < 4) { mp.tab.reset(); return mp; }
   mp.nw = nw;

@@ -25,8 +25,14 @@ struct MatzTables {          // one device blob, staged into shared memory by ev
   unsigned char inertial[kMaxJoints];     // body has inertial columns (external-wrench mode skips massless bodies)
 };
 
-constexpr int MATZ_STAGE = 14 * 33;       // one patch: [column][row] padded to 33 rows
+constexpr int MATZ_STAGE = 16 * 33;       // one patch: [column][row] padded to 33 rows; columns 0, 1 = the fs / off
+                                          // columns of the body to the left (sector-aligned patches, see below)
 
+// Patches and 32-byte sectors.  A body's 14 columns are 112 bytes: every other body starts in the middle of a sector,
+// and a partially written sector costs a DRAM read-modify-write (first version of this kernel: 1.04 GB read for
+// 0.19 GB of inputs, profiles/ncu_matz_r02_v1.md).  When the rows are sector aligned (W 32-byte aligned, ldw % 4 == 0)
+// the patches are cut on sector boundaries instead: body k (0-based) even -> its first 12 columns (96 bytes), body k
+// odd -> the fs / off columns of body k - 1 and its own 14 (128 bytes); an even last body writes all 14.
 struct MatzSink {
   const MatzParams* P;
   const MatzTables* T;
@@ -35,24 +41,80 @@ struct MatzSink {
   int64_t ldw, N, s0;
   const double* vs;
   const double* as;
-  bool valid;
-  int lane;
+  bool valid, aligned;
+  int lane, nrows;
   unsigned done;   // row groups that got a patch for the current body
-  int body;
+  int body, mode;  // mode 0: 14 columns, 1: first 12, 2: 2 + 14
+  int eg, egp;     // extra_grp of the body and of the body to its left
+  double vv, aa, pv;
 
-  __device__ __forceinline__ void write_patch(int g, bool zero) {
-    const int64_t row0 = (int64_t)T->rowblock[g] * N + s0;
-    const int cb = 14 * (body - 1);
-#pragma unroll 2
-    for (int it = 0; it < 14; ++it) {
-      const int e = it * 32 + lane;
-      const int row = e / 14, col = e - 14 * row;
-      if (s0 + row < N) W[(row0 + row) * ldw + cb + col] = zero ? 0.0 : stage[col * 33 + row];
+  template <int NC, int SC0>
+  __device__ __forceinline__ void store_cols(double* Wp, bool zero) {
+    if (NC == 16) {
+      double* p = Wp + (int64_t)(lane >> 4) * ldw + (lane & 15);
+      const double* sp = stage + (SC0 + (lane & 15)) * 33 + (lane >> 4);
+      const int64_t step = 2 * ldw;
+#pragma unroll
+      for (int it = 0; it < 16; ++it) {
+        if (2 * it + (lane >> 4) < nrows) *p = zero ? 0.0 : sp[2 * it];
+        p += step;
+      }
+    } else {
+#pragma unroll
+      for (int it = 0; it < NC; ++it) {
+        const int e = it * 32 + lane;
+        const int row = e / NC, col = e - NC * row;
+        if (row < nrows) Wp[(int64_t)row * ldw + col] = zero ? 0.0 : stage[(SC0 + col) * 33 + row];
+      }
     }
+  }
+  // one (row group, body) patch; val: the ten inertial entries in FIGAROH order or nullptr (outside the subtree)
+#ifndef MATZ_NOINLINE_PATCH
+  __device__ __forceinline__ void patch(int g, const double* val) {
+#else
+  __device__ __noinline__ void patch(int g, const double* val) {
+#endif
+    const bool own = eg == -1 || eg == g;                   // uniform
+    const bool prv = mode == 2 && (egp == -1 || egp == g);  // uniform
+    const bool any = val != nullptr || own || prv;
+    if (any) {
+      const bool inert = T->inertial[body] != 0;
+#pragma unroll
+      for (int f = 0; f < 10; ++f) stage[(2 + f) * 33 + lane] = (val != nullptr && valid && inert) ? val[f] : 0.0;
+      // Ia, fv, fs, off of body b in row group g (regressor.py:55-70 joint torques, :142-169 external wrench: v[i, b])
+      double e10 = 0.0, e11 = 0.0, e12 = 0.0, e13 = 0.0;
+      if (valid && own) {
+        if (P->flags & 2) e10 = aa;                       // FG_FLAG_ACTUATOR_INERTIA
+        if (P->flags & 1) { e11 = vv; e12 = sgn(vv); }    // FG_FLAG_FRICTION
+        if (P->flags & 4) e13 = 1.0;                      // FG_FLAG_JOINT_OFFSET
+      }
+      stage[12 * 33 + lane] = e10;
+      stage[13 * 33 + lane] = e11;
+      stage[14 * 33 + lane] = e12;
+      stage[15 * 33 + lane] = e13;
+      if (mode == 2) {
+        stage[lane] = (valid && prv && (P->flags & 1)) ? sgn(pv) : 0.0;
+        stage[33 + lane] = (valid && prv && (P->flags & 4)) ? 1.0 : 0.0;
+      }
+      __syncwarp();
+    }
+    double* Wp = W + ((int64_t)T->rowblock[g] * N + s0) * ldw + 14 * (body - 1);
+    if (mode == 2) store_cols<16, 0>(Wp - 2, !any);
+    else if (mode == 1) store_cols<12, 2>(Wp, !any);
+    else store_cols<14, 2>(Wp, !any);
+    if (any) __syncwarp();
+    done |= 1u << g;
   }
   __device__ __forceinline__ void body_begin(const RqOp& op, double, double) {
     done = 0u;
     body = T->body_of_t[op.t];
+    const int k = body - 1;
+    mode = !aligned ? 0 : ((k & 1) ? 2 : (k + 1 < P->nj - 1 ? 1 : 0));
+    eg = T->extra_grp[body];
+    egp = k >= 1 ? T->extra_grp[body - 1] : -2;
+    vv = aa = pv = 0.0;
+    if (eg != -2) { vv = __ldg(vs + k); aa = __ldg(as + k); }
+    if (mode == 2 && egp != -2) pv = __ldg(vs + k - 1);
   }
   __device__ __forceinline__ void emit(int g, int, const double* sl, const double* sa, const double* om, const double* al,
                                        const double* ap) {
@@ -72,51 +134,20 @@ struct MatzSink {
     val[2] = sa[0] * al[2] + sa[2] * al[0] + h[0] * om[2] + h[2] * om[0];   // Ixz
     val[4] = sa[1] * al[2] + sa[2] * al[1] + h[1] * om[2] + h[2] * om[1];   // Iyz
     val[5] = sa[2] * al[2] + h[2] * om[2];                                   // Izz
-    const bool inert = T->inertial[body] != 0;
-#pragma unroll
-    for (int f = 0; f < 10; ++f) stage[f * 33 + lane] = (valid && inert) ? val[f] : 0.0;
-    extras(g);
-    __syncwarp();
-    write_patch(g, false);
-    __syncwarp();
-    done |= 1u << g;
-  }
-  // Ia, fv, fs, off of body b in row group g (regressor.py:55-70 joint torques, :142-169 external wrench: v[i, b])
-  __device__ __forceinline__ void extras(int g) {
-    const int eg = T->extra_grp[body];
-    double e10 = 0.0, e11 = 0.0, e12 = 0.0, e13 = 0.0;
-    if (valid && (eg == -1 || eg == g)) {
-      const double vv = __ldg(vs + (body - 1)), aa = __ldg(as + (body - 1));
-      if (P->flags & 2) e10 = aa;                       // FG_FLAG_ACTUATOR_INERTIA
-      if (P->flags & 1) { e11 = vv; e12 = sgn(vv); }    // FG_FLAG_FRICTION
-      if (P->flags & 4) e13 = 1.0;                      // FG_FLAG_JOINT_OFFSET
-    }
-    stage[10 * 33 + lane] = e10;
-    stage[11 * 33 + lane] = e11;
-    stage[12 * 33 + lane] = e12;
-    stage[13 * 33 + lane] = e13;
+    patch(g, val);
   }
   __device__ __forceinline__ void body_end(const RqOp&) {
     // row groups outside whose subtree this body lies: zero inertial entries; the body's own columns only where the
     // reference writes them
-    const int eg = T->extra_grp[body];
-    for (int g = 0; g < P->ms; ++g) {
-      if ((done >> g) & 1u) continue;
-      if (eg == -1 || eg == g) {
-#pragma unroll
-        for (int f = 0; f < 10; ++f) stage[f * 33 + lane] = 0.0;
-        extras(g);
-        __syncwarp();
-        write_patch(g, false);
-        __syncwarp();
-      } else {
-        write_patch(g, true);
-      }
-    }
+    for (int g = 0; g < P->ms; ++g)
+      if (!((done >> g) & 1u)) patch(g, nullptr);
   }
 };
 
-__global__ void __launch_bounds__(512, 1)
+#ifndef MATZ_WARPS
+#define MATZ_WARPS 8   // 205 registers, no spills (A/B on B200: 16 warps at 128 registers with spills 2.26 ms, 12: 1.63, 8: 1.09)
+#endif
+__global__ void __launch_bounds__(MATZ_WARPS * 32, 1)
 matz_kernel(const __grid_constant__ MatzParams P, const MatzTables* __restrict__ tab, const double* __restrict__ q,
             const double* __restrict__ qd, const double* __restrict__ qdd, int64_t N, double* __restrict__ W, int64_t ldw) {
   extern __shared__ __align__(16) double mz_smem[];
@@ -143,6 +174,9 @@ matz_kernel(const __grid_constant__ MatzParams P, const MatzTables* __restrict__
     MatzSink sink;
     sink.P = &P; sink.T = T; sink.stage = stage; sink.W = W; sink.ldw = ldw; sink.N = N; sink.s0 = s0;
     sink.vs = qd + sc * P.nv; sink.as = qdd + sc * P.nv; sink.valid = valid; sink.lane = lane; sink.done = 0u; sink.body = 1;
+    sink.aligned = (ldw & 3) == 0 && (reinterpret_cast<uintptr_t>(W) & 31) == 0;
+    sink.nrows = (int)(N - s0 < 32 ? N - s0 : 32);
+    sink.mode = 0; sink.eg = sink.egp = -2; sink.vv = sink.aa = sink.pv = 0.0;
     rq_walk_tile(C, &T->S[0][0], 6, ps, q, qd, qdd, s0, N, lane, sink);
     if (P.coupling) {
       // add_coupling_TX40 (regressor.py:216-225): row block 4 <- [a5, v5, sign(v4+v5)], 5 <- [a4, v4, sign(v4+v5)]
