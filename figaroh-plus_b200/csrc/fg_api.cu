@@ -55,6 +55,7 @@ struct DevPlan {
   void* d_matz_tab = nullptr;
   // fifth-generation kernel (fg_ringqr.cuh)
   bool rq_tried = false;
+  bool rq_calibrated = false;   // warps re-apportioned by measured per-tile cycles (rq_calibrate)
   RqLaunch rql;
   std::unique_ptr<RqParams> rq;
   void* d_rq_tab = nullptr;
@@ -788,8 +789,151 @@ static int check_rq_error(fg_state* s) {
   return FG_OK;
 }
 
+static int rq_upload_tables(DevPlan* pl) {
+  RqLaunch& rl = pl->rql;
+  if (pl->d_rq_tab) { cudaFree(pl->d_rq_tab); pl->d_rq_tab = nullptr; }
+  const size_t nb_i = rl.tab_i.size() * sizeof(unsigned short), nb_g = (rl.tab_g.size() + 15) / 16 * 16;
+  FG_CUDA(cudaMalloc(&pl->d_rq_tab, nb_g + nb_i));
+  FG_CUDA(cudaMemcpy(pl->d_rq_tab, rl.tab_g.data(), rl.tab_g.size(), cudaMemcpyHostToDevice));
+  FG_CUDA(cudaMemcpy(static_cast<char*>(pl->d_rq_tab) + nb_g, rl.tab_i.data(), nb_i, cudaMemcpyHostToDevice));
+  rl.d_tab_g = static_cast<const unsigned char*>(pl->d_rq_tab);
+  rl.d_tab_i = reinterpret_cast<const unsigned short*>(static_cast<char*>(pl->d_rq_tab) + nb_g);
+  return FG_OK;
+}
+
+static int launch_rq(fg_state* s, fg_model* m, DevPlan* pl, const double* q, const double* v, const double* a,
+                     const double* tau, int64_t ld_tau, int64_t N, int phase, cudaStream_t st);
+
+// The row groups advance in lockstep (a ring of a few hundred tiles couples them) and the producers feed all of them,
+// so the launch runs at the pace of whichever role has too small a share of the SMs: a cost model that is 10 % off
+// for one row group costs 10 %.  The first large launch of a plan therefore calibrates the split on the caller's
+// first samples: timed trial launches walk the number of producer SMs downhill from the model's guess (TIAGo: 22
+// instead of 26, -2 % kernel time; UR10: the model's 26 confirmed).  A launch of the profiling instantiation of the
+// kernel also measures the warp cycles of a fold per row group and of a produced tile (diagnosis).  One-off per plan,
+// ~10 ms; FG_RQ_CALIBRATE=0 keeps the instruction-count model, FG_RQ_CALIBRATE=2 prints what was measured.
+static int rq_calibrate(fg_state* s, fg_model* m, DevPlan* pl, const double* q, const double* v, const double* a,
+                        const double* tau, int64_t ld_tau, int64_t N, cudaStream_t st) {
+  const char* e = getenv("FG_RQ_CALIBRATE");
+  const int mode = e && *e ? atoi(e) : 1;
+  pl->rq_calibrated = true;
+  if (mode == 0 || getenv("FG_RQ_NPCTA") || getenv("FG_RQ_COST")) return FG_OK;
+  const int64_t ncal = std::min<int64_t>(N, 1 << 18);
+  unsigned long long* d_prof = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  FG_CUDA(cudaMalloc(&d_prof, sizeof(unsigned long long) * RQ_PROF_WORDS));
+  FG_CUDA(cudaEventCreate(&ev0));
+  FG_CUDA(cudaEventCreate(&ev1));
+  int rc = FG_OK;
+  // one launch of the current pl->rql / pl->rq over the first ncal samples; ms < 0 on failure
+  auto trial = [&](unsigned long long* prof, float* ms) -> int {
+    const RqLaunch& rl = pl->rql;
+    const RqParams& prm = *pl->rq;
+    const int64_t cnt_doubles = ((int64_t)GQ_MAXG * prm.gq.maxinst + 3) / 2 + 1;
+    int r = ensure_gR(s, rl.r_doubles + rl.rfull_doubles + cnt_doubles);
+    if (r) return r;
+    const int64_t ring_need = rl.ring_doubles + (2 * (int64_t)prm.ring + 4 + 1) / 2;
+    if (ring_need > s->ring_cap) {
+      if (s->d_ring) cudaFree(s->d_ring);
+      s->d_ring = nullptr; s->ring_cap = 0; s->ring_plan = nullptr;
+      if (cudaMalloc(&s->d_ring, sizeof(double) * ring_need) != cudaSuccess) return set_err(FG_ERR_CUDA, "ring allocation failed");
+      s->ring_cap = ring_need;
+    }
+    if (s->ring_plan != (const void*)pl) {
+      cudaMemsetAsync(s->d_ring, 0, sizeof(double) * s->ring_cap, st);
+      s->ring_plan = (const void*)pl;
+    }
+    unsigned* ctl = reinterpret_cast<unsigned*>(s->d_ring + rl.ring_doubles);
+    if (prof) cudaMemsetAsync(prof, 0, sizeof(unsigned long long) * RQ_PROF_WORDS, st);
+    cudaEventRecord(ev0, st);
+    cudaError_t ce = rq_launch(rl, prm, q, v, a, tau, ld_tau, ncal, s->d_gR, s->d_ring, ctl, 1, st, prof);
+    cudaEventRecord(ev1, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    if (ce != cudaSuccess) return set_err(FG_ERR_CUDA, "calibration launch failed: %s", cudaGetErrorString(ce));
+    if (ms) cudaEventElapsedTime(ms, ev0, ev1);
+    return FG_OK;
+  };
+  auto rebuild = [&](const RqCost& mc) -> bool {
+    std::unique_ptr<RqParams> np(new RqParams);
+    const char* why = "";
+    RqLaunch nl = rq_build(pl->P, m->joints.data(), pl->rows.data(), pl->cols.data(), m->sm_count, m->max_smem, np.get(),
+                           &why, &mc);
+    if (!nl.ok) return false;
+    pl->rql = std::move(nl);
+    pl->rq = std::move(np);
+    return rq_upload_tables(pl) == FG_OK;
+  };
+  do {
+    // (1) fold cycles per row group
+    rc = trial(d_prof, nullptr);
+    if (rc) break;
+    unsigned long long h[RQ_PROF_WORDS];
+    if (cudaMemcpy(h, d_prof, sizeof h, cudaMemcpyDeviceToHost) != cudaSuccess) { rc = set_err(FG_ERR_CUDA, "calibration read-back failed"); break; }
+    const int ms_ = pl->rq->gq.ms;
+    RqCost mc;
+    mc.have = h[25] > 0;
+    for (int g = 0; g < ms_; ++g) {
+      if (h[8 + g] == 0) mc.have = false;
+      else mc.grp[g] = (double)h[g] / (double)h[8 + g];
+    }
+    if (!mc.have) break;
+    mc.prod = (double)h[24] / (double)h[25];
+    if (mode >= 2) {
+      fprintf(stderr, "[fg] rq calibration (%lld samples, %d producer SMs):", (long long)ncal, pl->rq->npc);
+      for (int g = 0; g < ms_; ++g)
+        fprintf(stderr, " g%d[%d warps] fold %.0f wait %.0f |", g, pl->rq->gq.gen.grp[g].ninst, mc.grp[g],
+                (double)h[16 + g] / (double)h[8 + g]);
+      fprintf(stderr, " producer tile %.0f wait %.0f\n", mc.prod, (double)h[26] / (double)h[25]);
+    }
+    // Measured and rejected as the apportionment of the consumer warps (UR10: 3.54 ms against 3.48 ms with the
+    // instruction-count model): a fold's cycles depend on what its neighbours on the SM are doing.  The numbers are
+    // printed for diagnosis (mode 2) and only used with FG_RQ_CALIBRATE=3.
+    if (mode < 3) mc.have = false;
+    // (2) producer SMs: timed trials, downhill from the model's count
+    const int start = pl->rq->npc;
+    int best_n = start;
+    float best_ms = 0.f;
+    auto eval = [&](int n, float* ms) -> bool {
+      if (n < 1 || n > m->sm_count - 1) return false;
+      mc.force_npcta = n;
+      if (!rebuild(mc)) return false;
+      float t1 = 0.f, t2 = 0.f;
+      if (trial(nullptr, &t1) || trial(nullptr, &t2)) return false;
+      *ms = std::min(t1, t2);
+      if (mode >= 2) fprintf(stderr, "[fg]   %d producer SMs: %.4f ms\n", n, *ms);
+      return true;
+    };
+    if (!eval(start, &best_ms)) { rc = check_rq_error(s); break; }
+    for (int dir = -1; dir <= 1; dir += 2) {
+      bool moved = false;
+      for (int n = best_n + 2 * dir;; n += 2 * dir) {
+        float t = 0.f;
+        if (!eval(n, &t) || t >= best_ms) break;
+        best_ms = t; best_n = n; moved = true;
+      }
+      if (moved) break;
+    }
+    for (int dir = -1; dir <= 1; dir += 2) {  // odd neighbours
+      float t = 0.f;
+      if (eval(best_n + dir, &t) && t < best_ms) { best_ms = t; best_n += dir; break; }
+    }
+    mc.force_npcta = best_n;
+    if (!rebuild(mc)) rc = set_err(FG_ERR_INVALID, "internal: calibrated split could not be rebuilt");
+    if (mode >= 2) fprintf(stderr, "[fg] rq calibration: %d producer SMs (model %d)\n", best_n, start);
+  } while (false);
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  cudaFree(d_prof);
+  if (rc == FG_OK) rc = check_rq_error(s);
+  return rc;
+}
+
 static int launch_rq(fg_state* s, fg_model* m, DevPlan* pl, const double* q, const double* v, const double* a,
                      const double* tau, int64_t ld_tau, int64_t N, int phase, cudaStream_t st) {
+  if ((phase & FG_PHASE_FIRST) && !pl->rq_calibrated && N >= (1 << 15)) {
+    if (!pl->d_rq_tab) { int rc0 = rq_upload_tables(pl); if (rc0) return rc0; }
+    int rc0 = rq_calibrate(s, m, pl, q, v, a, tau, ld_tau, N, st);
+    if (rc0) return rc0;
+  }
   RqLaunch& rl = pl->rql;
   const RqParams& prm = *pl->rq;
   if (!pl->d_rq_tab) {

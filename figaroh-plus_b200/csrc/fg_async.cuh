@@ -33,6 +33,18 @@ __device__ __forceinline__ void rq_bulk_g2s(void* dst_smem, const void* src_gmem
                "l"(src_gmem), "r"(bytes), "r"(rq_smem_u32(bar))
                : "memory");
 }
+// shared -> global bulk copy tracked by the issuing thread's bulk groups (16-byte aligned, size a multiple of 16)
+__device__ __forceinline__ void rq_bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(rq_smem_u32(src_smem)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void rq_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// at most N of this thread's bulk groups may still be READING their shared-memory source
+template <int N>
+__device__ __forceinline__ void rq_bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ void rq_fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 // shared-memory only: orders this thread's generic-proxy accesses to the tile before a bulk copy into it, without
 // waiting for the thread's outstanding global stores (the R blocks)

@@ -49,7 +49,8 @@ MatzPlan matz_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, 
     }
     T.extra_grp[b] = eg;
   }
-  M.smem_per_warp = (ms * 6 + 12 * (M.nvslots + M.nmslots)) * 32 + MATZ_STAGE + 2;
+  // walk | patch stage | staged inputs of one tile | mbarrier
+  M.smem_per_warp = (ms * 6 + 12 * (M.nvslots + M.nmslots)) * 32 + MATZ_STAGE + (MATZ_STAGE & 1) + 32 * (P.nq + 2 * P.nv) + 2;
   M.smem_per_warp += M.smem_per_warp & 1;
   const int tab_bytes = (int)((sizeof(MatzTables) + 15) / 16) * 16;
   int nw = MATZ_WARPS;

@@ -25,47 +25,68 @@ struct MatzTables {          // one device blob, staged into shared memory by ev
   unsigned char inertial[kMaxJoints];     // body has inertial columns (external-wrench mode skips massless bodies)
 };
 
-constexpr int MATZ_STAGE = 16 * 33;       // one patch: [column][row] padded to 33 rows; columns 0, 1 = the fs / off
-                                          // columns of the body to the left (sector-aligned patches, see below)
+#ifndef MATZ_NBUF
+#define MATZ_NBUF 2                        // stage buffers per warp (rotating)
+#endif
+constexpr int MATZ_ROW = 18;               // doubles per staged row: 16 columns + 2 of padding (144 bytes: the
+                                           // 16-byte column pairs of the 32 rows fall on 8 bank groups x 4 rows, the
+                                           // optimum for a 512-byte warp store; rows stay contiguous for bulk copies)
+constexpr int MATZ_STAGE = MATZ_NBUF * 32 * MATZ_ROW + MATZ_ROW;   // buffers + one row of zeros
 
 // Patches and 32-byte sectors.  A body's 14 columns are 112 bytes: every other body starts in the middle of a sector,
 // and a partially written sector costs a DRAM read-modify-write (first version of this kernel: 1.04 GB read for
 // 0.19 GB of inputs, profiles/ncu_matz_r02_v1.md).  When the rows are sector aligned (W 32-byte aligned, ldw % 4 == 0)
 // the patches are cut on sector boundaries instead: body k (0-based) even -> its first 12 columns (96 bytes), body k
 // odd -> the fs / off columns of body k - 1 and its own 14 (128 bytes); an even last body writes all 14.
+// A staged row holds 8 column pairs: (fs, off of the body to the left) | Ixx Ixy | Ixz Iyy | Iyz Izz | mx my | mz m |
+// Ia fv | fs off.  Every lane stages its own sample's row with 16-byte stores; the patch leaves either as 16-byte
+// global stores (8 lanes per row, 4 rows per instruction) or, with MATZ_BULK, as one cp.async.bulk per row issued by
+// the lane that staged it (no cross-lane dependency at all).
 struct MatzSink {
   const MatzParams* P;
   const MatzTables* T;
-  double* stage;
+  double* stage;   // MATZ_NBUF buffers of 32 rows, then the zero row
   double* W;
   int64_t ldw, N, s0;
   const double* vs;
   const double* as;
-  bool valid, aligned;
-  int lane, nrows;
+  bool valid, aligned, aligned16;
+  int lane, nrows, buf;
   unsigned done;   // row groups that got a patch for the current body
   int body, mode;  // mode 0: 14 columns, 1: first 12, 2: 2 + 14
   int eg, egp;     // extra_grp of the body and of the body to its left
   double vv, aa, pv;
 
-  template <int NC, int SC0>
-  __device__ __forceinline__ void store_cols(double* Wp, bool zero) {
-    if (NC == 16) {
-      double* p = Wp + (int64_t)(lane >> 4) * ldw + (lane & 15);
-      const double* sp = stage + (SC0 + (lane & 15)) * 33 + (lane >> 4);
-      const int64_t step = 2 * ldw;
+  // NC2 column pairs starting at pair C20 of the staged rows -> Wp (first column of the patch, row 0 of the tile)
+  template <int NC2, int C20>
+  __device__ __forceinline__ void store_pairs(const double* sb, double* Wp, bool zero) {
+#ifdef MATZ_BULK
+    if (lane < nrows) {
+      const double* src = zero ? stage + MATZ_NBUF * 32 * MATZ_ROW : sb + lane * MATZ_ROW + 2 * C20;
+      rq_bulk_s2g(Wp + (int64_t)lane * ldw, src, NC2 * 16);
+    }
+    rq_bulk_commit();
+#else
+    const int r0 = lane >> 3, c2 = lane & 7;
+    double2* p = reinterpret_cast<double2*>(Wp + (int64_t)r0 * ldw) + c2;
+    const double2* sp = reinterpret_cast<const double2*>(sb + r0 * MATZ_ROW) + C20 + c2;
+    const int64_t step = 2 * ldw;  // 4 rows, in double2 units
+    if (c2 < NC2) {
 #pragma unroll
-      for (int it = 0; it < 16; ++it) {
-        if (2 * it + (lane >> 4) < nrows) *p = zero ? 0.0 : sp[2 * it];
+      for (int it = 0; it < 8; ++it) {
+        if (4 * it + r0 < nrows) *p = zero ? make_double2(0.0, 0.0) : sp[it * (4 * MATZ_ROW / 2)];
         p += step;
       }
-    } else {
-#pragma unroll
-      for (int it = 0; it < NC; ++it) {
-        const int e = it * 32 + lane;
-        const int row = e / NC, col = e - NC * row;
-        if (row < nrows) Wp[(int64_t)row * ldw + col] = zero ? 0.0 : stage[(SC0 + col) * 33 + row];
-      }
+    }
+#endif
+  }
+  // rows that are not 16-byte aligned (odd ldw: the TX40 coupling columns): 14 columns with 8-byte stores
+  __device__ __forceinline__ void store_scalar(const double* sb, double* Wp, bool zero) {
+#pragma unroll 2
+    for (int it = 0; it < 14; ++it) {
+      const int e = it * 32 + lane;
+      const int row = e / 14, col = e - 14 * row;
+      if (row < nrows) Wp[(int64_t)row * ldw + col] = zero ? 0.0 : sb[row * MATZ_ROW + 2 + col];
     }
   }
   // one (row group, body) patch; val: the ten inertial entries in FIGAROH order or nullptr (outside the subtree)
@@ -77,10 +98,15 @@ struct MatzSink {
     const bool own = eg == -1 || eg == g;                   // uniform
     const bool prv = mode == 2 && (egp == -1 || egp == g);  // uniform
     const bool any = val != nullptr || own || prv;
+    double* sb = stage + buf * (32 * MATZ_ROW);
     if (any) {
-      const bool inert = T->inertial[body] != 0;
+#ifdef MATZ_BULK
+      rq_bulk_wait_read<MATZ_NBUF - 1>();  // this lane's copy out of the buffer it is about to overwrite has been read
+#endif
+      double2* row = reinterpret_cast<double2*>(sb + lane * MATZ_ROW);
+      const bool inert = val != nullptr && valid && T->inertial[body] != 0;
 #pragma unroll
-      for (int f = 0; f < 10; ++f) stage[(2 + f) * 33 + lane] = (val != nullptr && valid && inert) ? val[f] : 0.0;
+      for (int f = 0; f < 5; ++f) row[1 + f] = inert ? make_double2(val[2 * f], val[2 * f + 1]) : make_double2(0.0, 0.0);
       // Ia, fv, fs, off of body b in row group g (regressor.py:55-70 joint torques, :142-169 external wrench: v[i, b])
       double e10 = 0.0, e11 = 0.0, e12 = 0.0, e13 = 0.0;
       if (valid && own) {
@@ -88,21 +114,22 @@ struct MatzSink {
         if (P->flags & 1) { e11 = vv; e12 = sgn(vv); }    // FG_FLAG_FRICTION
         if (P->flags & 4) e13 = 1.0;                      // FG_FLAG_JOINT_OFFSET
       }
-      stage[12 * 33 + lane] = e10;
-      stage[13 * 33 + lane] = e11;
-      stage[14 * 33 + lane] = e12;
-      stage[15 * 33 + lane] = e13;
-      if (mode == 2) {
-        stage[lane] = (valid && prv && (P->flags & 1)) ? sgn(pv) : 0.0;
-        stage[33 + lane] = (valid && prv && (P->flags & 4)) ? 1.0 : 0.0;
-      }
+      row[6] = make_double2(e10, e11);
+      row[7] = make_double2(e12, e13);
+      if (mode == 2)
+        row[0] = make_double2((valid && prv && (P->flags & 1)) ? sgn(pv) : 0.0, (valid && prv && (P->flags & 4)) ? 1.0 : 0.0);
+#ifdef MATZ_BULK
+      rq_fence_proxy_async_smem();
+#else
       __syncwarp();
+#endif
+      buf = buf + 1 == MATZ_NBUF ? 0 : buf + 1;
     }
     double* Wp = W + ((int64_t)T->rowblock[g] * N + s0) * ldw + 14 * (body - 1);
-    if (mode == 2) store_cols<16, 0>(Wp - 2, !any);
-    else if (mode == 1) store_cols<12, 2>(Wp, !any);
-    else store_cols<14, 2>(Wp, !any);
-    if (any) __syncwarp();
+    if (mode == 2) store_pairs<8, 0>(sb, Wp - 2, !any);
+    else if (mode == 1) store_pairs<6, 1>(sb, Wp, !any);
+    else if (aligned16) store_pairs<7, 1>(sb, Wp, !any);
+    else store_scalar(sb, Wp, !any);
     done |= 1u << g;
   }
   __device__ __forceinline__ void body_begin(const RqOp& op, double, double) {
@@ -113,8 +140,8 @@ struct MatzSink {
     eg = T->extra_grp[body];
     egp = k >= 1 ? T->extra_grp[body - 1] : -2;
     vv = aa = pv = 0.0;
-    if (eg != -2) { vv = __ldg(vs + k); aa = __ldg(as + k); }
-    if (mode == 2 && egp != -2) pv = __ldg(vs + k - 1);
+    if (eg != -2) { vv = vs[k]; aa = as[k]; }
+    if (mode == 2 && egp != -2) pv = vs[k - 1];
   }
   __device__ __forceinline__ void emit(int g, int, const double* sl, const double* sa, const double* om, const double* al,
                                        const double* ap) {
@@ -162,25 +189,70 @@ matz_kernel(const __grid_constant__ MatzParams P, const MatzTables* __restrict__
   constexpr int TAB_DOUBLES = (int)((sizeof(MatzTables) + 15) / 16) * 2;
   double* ps = mz_smem + TAB_DOUBLES + (size_t)warp * P.smem_per_warp;
   double* stage = ps + (P.ms * 6 + 12 * (P.nvslots + P.nmslots)) * 32;
+  for (int i = lane; i < MATZ_ROW; i += 32) stage[MATZ_NBUF * 32 * MATZ_ROW + i] = 0.0;
+#ifdef MATZ_BULK
+  rq_fence_proxy_async_smem();
+#endif
+  __syncwarp();
   RqWalkCtx C;
   C.pj = T->pj; C.ops = T->ops; C.nops = P.nops; C.ms = P.ms; C.nq = P.nq; C.nv = P.nv; C.nvslots = P.nvslots;
   for (int k = 0; k < 3; ++k) C.gravity[k] = P.gravity[k];
   const int64_t ntiles = (N + 31) / 32;
   const int nb = P.nj - 1;
-  for (int64_t tl = (int64_t)blockIdx.x * nw + warp; tl < ntiles; tl += (int64_t)gridDim.x * nw) {
+  // inputs of a tile, staged by the copy engine while the previous tile's patches drain (the per-lane loads at a
+  // 48-byte stride were the walk's top stall under the write stream: profiles/ncu_matz_r02_v2.md)
+  double* in_q = stage + MATZ_STAGE + (MATZ_STAGE & 1);
+  double* in_v = in_q + 32 * P.nq;
+  double* in_a = in_v + 32 * P.nv;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(in_a + 32 * P.nv);
+  const bool in16 = ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(qd) | reinterpret_cast<uintptr_t>(qdd)) & 15) == 0;
+  if (lane == 0) {
+    rq_mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  uint32_t parity = 0;
+  // a full tile goes through cp.async.bulk (sizes are multiples of 256 bytes); the ragged last one is copied by hand
+  auto request = [&](int64_t tl) {
+    const int64_t s0 = tl * 32;
+    if (s0 + 32 <= N && in16) {
+      if (lane == 0) {
+        rq_mbar_expect_tx(bar, (uint32_t)(32 * 8 * (P.nq + 2 * P.nv)));
+        rq_bulk_g2s(in_q, q + s0 * P.nq, 32 * 8 * P.nq, bar);
+        rq_bulk_g2s(in_v, qd + s0 * P.nv, 32 * 8 * P.nv, bar);
+        rq_bulk_g2s(in_a, qdd + s0 * P.nv, 32 * 8 * P.nv, bar);
+      }
+    }
+  };
+  int buf = 0;
+  int64_t tl = (int64_t)blockIdx.x * nw + warp;
+  if (tl < ntiles) request(tl);
+  for (; tl < ntiles; tl += (int64_t)gridDim.x * nw) {
     const int64_t s0 = tl * 32, smp = s0 + lane;
     const bool valid = smp < N;
-    const int64_t sc = valid ? smp : N - 1;
+    const int nrows = (int)(N - s0 < 32 ? N - s0 : 32);
+    if (nrows == 32 && in16) {
+      while (!rq_mbar_try_wait(bar, parity)) {}
+      parity ^= 1u;
+    } else {
+      for (int i = lane; i < nrows * P.nq; i += 32) in_q[i] = __ldg(q + s0 * P.nq + i);
+      for (int i = lane; i < nrows * P.nv; i += 32) { in_v[i] = __ldg(qd + s0 * P.nv + i); in_a[i] = __ldg(qdd + s0 * P.nv + i); }
+      __syncwarp();
+    }
+    const int sc = valid ? lane : nrows - 1;
     MatzSink sink;
     sink.P = &P; sink.T = T; sink.stage = stage; sink.W = W; sink.ldw = ldw; sink.N = N; sink.s0 = s0;
-    sink.vs = qd + sc * P.nv; sink.as = qdd + sc * P.nv; sink.valid = valid; sink.lane = lane; sink.done = 0u; sink.body = 1;
+    sink.vs = in_v + sc * P.nv; sink.as = in_a + sc * P.nv; sink.valid = valid; sink.lane = lane; sink.done = 0u; sink.body = 1;
     sink.aligned = (ldw & 3) == 0 && (reinterpret_cast<uintptr_t>(W) & 31) == 0;
-    sink.nrows = (int)(N - s0 < 32 ? N - s0 : 32);
+    sink.aligned16 = (ldw & 1) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0;
+    sink.buf = buf;  // the rotation runs across tiles: one __syncwarp lies between two uses of a buffer
+    sink.nrows = nrows;
     sink.mode = 0; sink.eg = sink.egp = -2; sink.vv = sink.aa = sink.pv = 0.0;
-    rq_walk_tile(C, &T->S[0][0], 6, ps, q, qd, qdd, s0, N, lane, sink);
+    rq_walk_tile<true>(C, &T->S[0][0], 6, ps, in_q, in_v, in_a, 0, nrows, lane, sink);
+    buf = sink.buf;
     if (P.coupling) {
       // add_coupling_TX40 (regressor.py:216-225): row block 4 <- [a5, v5, sign(v4+v5)], 5 <- [a4, v4, sign(v4+v5)]
-      const double v4 = __ldg(sink.vs + 4), v5 = __ldg(sink.vs + 5), a4 = __ldg(sink.as + 4), a5 = __ldg(sink.as + 5);
+      const double v4 = sink.vs[4], v5 = sink.vs[5], a4 = sink.as[4], a5 = sink.as[5];
       const double sg = sgn(v4 + v5);
       if (valid) {
         for (int g = 0; g < P.ms; ++g) {
@@ -192,7 +264,15 @@ matz_kernel(const __grid_constant__ MatzParams P, const MatzTables* __restrict__
         }
       }
     }
+    // every lane has read its inputs: the next tile may land
+    rq_fence_proxy_async_smem();
+    __syncwarp();
+    const int64_t nx = tl + (int64_t)gridDim.x * nw;
+    if (nx < ntiles) request(nx);
   }
+#ifdef MATZ_BULK
+  rq_bulk_wait_read<0>();  // the copies read this CTA's shared memory
+#endif
 }
 
 }  // namespace fg

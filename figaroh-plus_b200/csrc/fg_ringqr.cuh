@@ -22,11 +22,13 @@ constexpr unsigned RQ_SPIN_LIMIT = 1u << 22;  // bounded waits: ~1 s, then the e
 constexpr int RQ_ERR_CONSUMER = 1, RQ_ERR_PRODUCER = 2, RQ_ERR_MBAR = 3;
 
 // lane 0 waits until *flag >= want (monotonic counters); false = gave up (error flag raised by the caller)
-__device__ __forceinline__ bool rq_spin_ge(const unsigned* flag, unsigned want, const unsigned* err) {
+// (first version: __nanosleep(20..200) - at those values the warp does not sleep at all; the consumers' polls after
+// a fold were 25 % of all executed instructions, each with an L1 invalidate: profiles/ncu_rq_ur10_r02.md)
+__device__ __forceinline__ bool rq_spin_ge(const unsigned* flag, unsigned want, const unsigned* err, int sleep_ns) {
   for (unsigned it = 0; it < RQ_SPIN_LIMIT; ++it) {
     if (rq_ld_acquire(flag) >= want) return true;
     if ((it & 255u) == 255u && rq_ld_acquire(err) != 0u) return false;
-    __nanosleep(it < 32 ? 20 : 200);
+    __nanosleep((unsigned)sleep_ns);
   }
   return false;
 }
@@ -102,7 +104,13 @@ struct RqWalkCtx {
   double gravity[3];
 };
 
-template <class Sink>
+// SIN: the inputs were staged (q, qd, qdd point to a tile in shared memory, s0 = 0, N = rows of the tile)
+template <bool SIN>
+__device__ __forceinline__ double rq_ldin(const double* p) {
+  if (SIN) return *p;
+  return __ldg(p);
+}
+template <bool SIN, class Sink>
 static __device__ __forceinline__ void rq_walk_tile(const RqWalkCtx& C, const double* Sbase, int Sstride /* doubles */,
                                                     double* ps, const double* __restrict__ q,
                                                     const double* __restrict__ qd, const double* __restrict__ qdd,
@@ -123,7 +131,7 @@ static __device__ __forceinline__ void rq_walk_tile(const RqWalkCtx& C, const do
   double nq0 = 0.0, nv0 = 0.0, na0 = 0.0;
   {
     const DevJoint& j0 = C.pj[C.ops[0].t];
-    nq0 = __ldg(qs + j0.idx_q); nv0 = __ldg(vs + j0.idx_v); na0 = __ldg(as + j0.idx_v);
+    nq0 = rq_ldin<SIN>(qs + j0.idx_q); nv0 = rq_ldin<SIN>(vs + j0.idx_v); na0 = rq_ldin<SIN>(as + j0.idx_v);
   }
   const int nops = C.nops;
   for (int o = 0; o < nops; ++o) {
@@ -141,7 +149,7 @@ static __device__ __forceinline__ void rq_walk_tile(const RqWalkCtx& C, const do
       const double cq0 = nq0, cv0 = nv0, ca0 = na0;
       if (op.pad != 255) {  // the next descend's joint
         const DevJoint& jn = C.pj[op.pad];
-        nq0 = __ldg(qs + jn.idx_q); nv0 = __ldg(vs + jn.idx_v); na0 = __ldg(as + jn.idx_v);
+        nq0 = rq_ldin<SIN>(qs + jn.idx_q); nv0 = rq_ldin<SIN>(vs + jn.idx_v); na0 = rq_ldin<SIN>(as + jn.idx_v);
       }
       double Rj[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, pj[3] = {0, 0, 0};
       double vj[6] = {0, 0, 0, 0, 0, 0}, aj[6] = {0, 0, 0, 0, 0, 0};
@@ -153,14 +161,14 @@ static __device__ __forceinline__ void rq_walk_tile(const RqWalkCtx& C, const do
         axis_rot(ax, c, s, Rj);
         for (int k = 0; k < 3; ++k) { vj[3 + k] = ax[k] * cv0; aj[3 + k] = ax[k] * ca0; }
       } else if (jt.jtype == 2) {
-        axis_rot(ax, cq0, __ldg(qs + iq + 1), Rj);
+        axis_rot(ax, cq0, rq_ldin<SIN>(qs + iq + 1), Rj);
         for (int k = 0; k < 3; ++k) { vj[3 + k] = ax[k] * cv0; aj[3 + k] = ax[k] * ca0; }
       } else if (jt.jtype == 3) {
         for (int k = 0; k < 3; ++k) { pj[k] = ax[k] * cq0; vj[k] = ax[k] * cv0; aj[k] = ax[k] * ca0; }
       } else {  // free-flyer
-        quat_rot(__ldg(qs + iq + 3), __ldg(qs + iq + 4), __ldg(qs + iq + 5), __ldg(qs + iq + 6), Rj);
-        for (int k = 0; k < 3; ++k) pj[k] = __ldg(qs + iq + k);
-        for (int k = 0; k < 6; ++k) { vj[k] = __ldg(vs + iv + k); aj[k] = __ldg(as + iv + k); }
+        quat_rot(rq_ldin<SIN>(qs + iq + 3), rq_ldin<SIN>(qs + iq + 4), rq_ldin<SIN>(qs + iq + 5), rq_ldin<SIN>(qs + iq + 6), Rj);
+        for (int k = 0; k < 3; ++k) pj[k] = rq_ldin<SIN>(qs + iq + k);
+        for (int k = 0; k < 6; ++k) { vj[k] = rq_ldin<SIN>(vs + iv + k); aj[k] = rq_ldin<SIN>(as + iv + k); }
       }
       // liMi = placement * Mj
       for (int r = 0; r < 3; ++r) {
@@ -257,8 +265,9 @@ static __device__ __forceinline__ void rq_produce_tile(const RqParams& P, const 
   for (int k = 0; k < 3; ++k) C.gravity[k] = P.gq.gravity[k];
   static_assert(sizeof(GqGroup) % 8 == 0, "GqGroup must be a whole number of doubles");
   RqRingSink sink{&P, &S, slot, valid, lane};
-  rq_walk_tile(C, S.grp[0].S, (int)(sizeof(GqGroup) / 8), ps, q, qd, qdd, s0, N, lane, sink);
+  rq_walk_tile<false>(C, S.grp[0].S, (int)(sizeof(GqGroup) / 8), ps, q, qd, qdd, s0, N, lane, sink);
   // columns read straight off the inputs (friction / actuator inertia / offset / coupling / rhs)
+  // (measured and rejected: issuing the loads of eight columns together before consuming them - 4.49 ms against 3.48)
   for (int g = 0; g < ms; ++g) {
     const GqGroup& G = S.grp[g];
     double* gs = slot + P.goff[g];
@@ -272,7 +281,6 @@ static __device__ __forceinline__ void rq_produce_tile(const RqParams& P, const 
         const double vv = __ldg(vs + s1.vidx), aa = __ldg(as + s1.vidx);
         val = s1.src == SRC_QDD ? aa : (s1.src == SRC_QD ? vv : (s1.src == SRC_SIGN_QD ? sgn(vv) : 1.0));
       } else {
-        // add_coupling_TX40 (regressor.py:216-225): row block 4 <- [a5, v5, sign(v4+v5)], 5 <- [a4, v4, sign(v4+v5)]
         const double v4 = __ldg(vs + 4), v5 = __ldg(vs + 5), a4 = __ldg(as + 4), a5 = __ldg(as + 5);
         const double sg = sgn(v4 + v5);
         val = G.rowblock == 4 ? (s1.src == 0 ? a5 : (s1.src == 1 ? v5 : sg)) : (s1.src == 0 ? a4 : (s1.src == 1 ? v4 : sg));
@@ -320,13 +328,14 @@ struct RqRefill {
 // ---------------------------------------------------------------------------------------------
 // ctl: ready[ring] | done[ring] | err
 // MAXNW: warps per CTA the kernel is compiled for (16: 128 registers per thread, 20: 96)
-template <int MAXNW>
+// PROF: count the cycles of every fold / produced tile / wait into prof (calibration launches only)
+template <int MAXNW, bool PROF>
 __global__ void __launch_bounds__(MAXNW * 32, 1)
 rq_accumulate_kernel(const __grid_constant__ RqParams P, const unsigned char* __restrict__ tab_g,
                      const unsigned short* __restrict__ tab_i, const double* __restrict__ q,
                      const double* __restrict__ qd, const double* __restrict__ qdd, const double* __restrict__ tau,
                      int64_t ld_tau, int64_t N, double* __restrict__ r_all, double* __restrict__ ring,
-                     unsigned* __restrict__ ctl, int first) {
+                     unsigned* __restrict__ ctl, int first, unsigned long long* __restrict__ prof) {
   extern __shared__ __align__(16) double gq_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   GqGen* Sg = reinterpret_cast<GqGen*>(gq_smem);
@@ -366,20 +375,24 @@ rq_accumulate_kernel(const __grid_constant__ RqParams P, const unsigned char* __
   const int64_t ntiles = (N + GQ_S - 1) / GQ_S;
   const int ms = P.gq.ms;
 
+  long long pf_work = 0, pf_wait = 0, pf_t = 0;
+  unsigned pf_n = 0;
   if (role == 255) {
     // ------------------------------------------------------------------ producer
     for (int64_t tl = inst; tl < ntiles; tl += P.nprod) {
+      if (PROF) pf_t = clock64();
       const int s = (int)(tl % P.ring);
       const unsigned round = (unsigned)(tl / P.ring);
       if (round > 0) {  // every row group must have copied the tile that used this slot before
         unsigned ok = 1;
-        if (lane == 0) ok = rq_spin_ge(done + s, (unsigned)ms * round, err) ? 1u : 0u;
+        if (lane == 0) ok = rq_spin_ge(done + s, (unsigned)ms * round, err, P.sleep_ns) ? 1u : 0u;
         ok = __shfl_sync(0xffffffffu, ok, 0);
         if (!ok) {
           if (lane == 0) atomicCAS(err, 0u, (unsigned)RQ_ERR_PRODUCER);
           return;
         }
       }
+      if (PROF) { const long long t = clock64(); pf_wait += t - pf_t; pf_t = t; }
       if (tl + P.nprod < ntiles) {  // pull the next tile's inputs towards L2
         const int64_t sn = (tl + P.nprod) * GQ_S + lane;
         if (sn < N) {
@@ -387,11 +400,21 @@ rq_accumulate_kernel(const __grid_constant__ RqParams P, const unsigned char* __
           asm volatile("prefetch.global.L2 [%0];" ::"l"(qd + sn * P.gq.nv));
           asm volatile("prefetch.global.L2 [%0];" ::"l"(qdd + sn * P.gq.nv));
         }
+        if (tau != nullptr && lane < 2 * ms) {  // the 256 bytes of every row group's rhs: two lines
+          const int64_t st = (tl + P.nprod) * GQ_S + 16 * (lane & 1);
+          if (st < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(tau + (int64_t)(lane >> 1) * ld_tau + st));
+        }
       }
       rq_produce_tile(P, S, ops, mine, ring + (size_t)s * P.slot_doubles, q, qd, qdd, tau, ld_tau, tl * GQ_S, N, lane);
       __threadfence();
       __syncwarp();
       if (lane == 0) rq_st_release(ready + s, (unsigned)(tl + 1));
+      if (PROF) { pf_work += clock64() - pf_t; ++pf_n; }
+    }
+    if (PROF && lane == 0 && pf_n) {
+      atomicAdd(prof + 24, (unsigned long long)pf_work);
+      atomicAdd(prof + 25, (unsigned long long)pf_n);
+      atomicAdd(prof + 26, (unsigned long long)pf_wait);
     }
     return;
   }
@@ -416,7 +439,7 @@ rq_accumulate_kernel(const __grid_constant__ RqParams P, const unsigned char* __
     const int s = (int)(tl % P.ring);
     unsigned ok = 1;
     if (lane == 0) {
-      ok = rq_spin_ge(ready + s, (unsigned)(tl + 1), err) ? 1u : 0u;
+      ok = rq_spin_ge(ready + s, (unsigned)(tl + 1), err, P.sleep_ns) ? 1u : 0u;
       if (ok) {
         rq_fence_proxy_async();
         rq_mbar_expect_tx(bar, (uint32_t)nb * GQ_BLK * 8);
@@ -431,6 +454,7 @@ rq_accumulate_kernel(const __grid_constant__ RqParams P, const unsigned char* __
     }
   }
   for (; tl < ntiles; tl += ninst) {
+    if (PROF) pf_t = clock64();
     {  // the tile's bytes have landed
       unsigned it = 0;
       while (!rq_mbar_try_wait(bar, parity)) {
@@ -441,6 +465,7 @@ rq_accumulate_kernel(const __grid_constant__ RqParams P, const unsigned char* __
       }
       parity ^= 1u;
     }
+    if (PROF) { const long long t = clock64(); pf_wait += t - pf_t; pf_t = t; }
     const int s = (int)(tl % P.ring);
     if (lane == 0) atomicAdd(done + s, 1u);  // the copy has read the slot: it may be refilled
     const int64_t nx = tl + ninst;
@@ -457,11 +482,12 @@ rq_accumulate_kernel(const __grid_constant__ RqParams P, const unsigned char* __
     rf.dst = tile;
     rf.bar = bar;
     gq_fold_h<false, 1, RqRefill>(tile, nb, Rg, 0, scr, offs, lane, rf);
+    if (PROF) { const long long t = clock64(); pf_work += t - pf_t; pf_t = t; ++pf_n; }
     if (rf.has_next) {
       unsigned ok = 1;
       if (lane == 0) {
         if (!rf.armed) {
-          ok = rq_spin_ge(rf.ready, rf.want, err) ? 1u : 0u;
+          ok = rq_spin_ge(rf.ready, rf.want, err, P.sleep_ns) ? 1u : 0u;
           if (ok) {
             rq_fence_proxy_async();
             rf.arm();
@@ -474,7 +500,13 @@ rq_accumulate_kernel(const __grid_constant__ RqParams P, const unsigned char* __
         if (lane == 0) atomicCAS(err, 0u, (unsigned)RQ_ERR_CONSUMER);
         return;
       }
+      if (PROF) pf_wait += clock64() - pf_t;
     }
+  }
+  if (PROF && lane == 0 && pf_n) {
+    atomicAdd(prof + g, (unsigned long long)pf_work);
+    atomicAdd(prof + 8 + g, (unsigned long long)pf_n);
+    atomicAdd(prof + 16 + g, (unsigned long long)pf_wait);
   }
 }
 

@@ -111,7 +111,7 @@ RqWalk rq_build_walk(int nj, const DevJoint* joints, const std::vector<char>& ne
 }
 
 RqLaunch rq_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, const ColDesc* cols, int sm_count,
-                  int max_smem, RqParams* out, const char** why) {
+                  int max_smem, RqParams* out, const char** why, const RqCost* measured) {
   RqLaunch rl;
   if (why) *why = "";
   const int ms = P.ms, nj = P.nj, ncols = P.ncols;
@@ -237,7 +237,12 @@ RqLaunch rq_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, co
     cost[g] = c_base + c_panel * G.nb + c_trail * G.nb * (G.nb - 1) / 2;
     csum += cost[g];
   }
-  const double pcost = 1.07 * (400.0 + 420.0 * nproc + 45.0 * n_transports + 190.0 * n_emits + 25.0 * n_simple + 60.0 * (nops - nproc));  // 1.07: A/B on UR10 (26 producer SMs of 148)
+  double pcost = 1.07 * (400.0 + 420.0 * nproc + 45.0 * n_transports + 190.0 * n_emits + 25.0 * n_simple + 60.0 * (nops - nproc));  // 1.07: A/B on UR10 (26 producer SMs of 148)
+  if (measured && measured->have) {  // warp cycles per tile, measured on this device with this plan
+    csum = 0.0;
+    for (int g = 0; g < ms; ++g) { cost[g] = std::max(1.0, measured->grp[g]); csum += cost[g]; }
+    pcost = std::max(1.0, measured->prod);
+  }
   rl.sm_count = std::max(1, sm_count);
   const int gen_doubles = GQ_GEN_DOUBLES + (int)(sizeof(RqOp) * RQ_MAXOPS / 8);
   // Roles are assigned per CTA (= per SM): a producer SM runs only the generator, a consumer SM only the fold, so
@@ -245,6 +250,7 @@ RqLaunch rq_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, co
   // other's load latencies.  (First version: producers and consumers mixed inside every CTA - the generator's code
   // was evicted between two uses, `no_instruction` became the top stall, profiles/ncu_rq_r02_v5a.md.)
   int npcta = (int)(rl.sm_count * pcost / (pcost + csum) + 0.5);
+  if (measured && measured->force_npcta > 0) npcta = measured->force_npcta;
   npcta = env_int("FG_RQ_NPCTA", npcta);
   npcta = std::max(1, std::min(npcta, rl.sm_count - 1));
   if (rl.sm_count < 2) { rq_fail(why, "needs at least two SMs"); return rl; }
@@ -323,6 +329,7 @@ RqLaunch rq_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, co
   }
   if (rl.nw < 1) { rq_fail(why, "tile does not fit shared memory"); return rl; }
   R.ring = std::max(8, env_int("FG_RQ_RING", 512));
+  R.sleep_ns = std::max(0, env_int("FG_RQ_SLEEP", 400));
   rl.ring_doubles = (int64_t)R.ring * R.slot_doubles;
   rl.rfull_doubles = (int64_t)T.nbf * (T.nbf + 1) / 2 * 64;
   rl.ok = true;
@@ -331,8 +338,9 @@ RqLaunch rq_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, co
 
 cudaError_t rq_launch(const RqLaunch& rl, const RqParams& prm, const double* q, const double* v, const double* a,
                       const double* tau, int64_t ld_tau, int64_t N, double* r_all, double* ring, unsigned* ring_ctl,
-                      int first, cudaStream_t st) {
-  const void* kern = rl.nw > 16 ? (const void*)rq_accumulate_kernel<20> : (const void*)rq_accumulate_kernel<16>;
+                      int first, cudaStream_t st, unsigned long long* prof) {
+  const void* kern = prof ? (rl.nw > 16 ? (const void*)rq_accumulate_kernel<20, true> : (const void*)rq_accumulate_kernel<16, true>)
+                          : (rl.nw > 16 ? (const void*)rq_accumulate_kernel<20, false> : (const void*)rq_accumulate_kernel<16, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, rl.smem);
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(ring_ctl, 0, sizeof(unsigned) * (2 * (size_t)prm.ring), st);  // ready / done; the error word stays until it is reported
@@ -340,7 +348,7 @@ cudaError_t rq_launch(const RqLaunch& rl, const RqParams& prm, const double* q, 
   const unsigned char* tg = rl.d_tab_g;
   const unsigned short* ti = rl.d_tab_i;
   void* args[] = {(void*)&prm, (void*)&tg, (void*)&ti, (void*)&q, (void*)&v, (void*)&a, (void*)&tau,
-                  (void*)&ld_tau, (void*)&N, (void*)&r_all, (void*)&ring, (void*)&ring_ctl, (void*)&first};
+                  (void*)&ld_tau, (void*)&N, (void*)&r_all, (void*)&ring, (void*)&ring_ctl, (void*)&first, (void*)&prof};
   // every CTA must be resident (producers and consumers wait for each other): cooperative launch
   return cudaLaunchCooperativeKernel(kern, dim3(rl.sm_count), dim3(rl.nw * 32), args, (size_t)rl.smem, st);
 }

@@ -62,6 +62,18 @@ struct RqParams {
   int npc;                 // producer CTAs (a CTA is all producers or all consumers)
   int prod_smem_doubles;   // shared memory of one producer warp
   int nvslots, nmslots;
+  int sleep_ns;            // back-off of a waiting warp between two polls of a ring flag
+};
+
+// Measured cost of one 32-sample tile in warp cycles (rq_accumulate_kernel<.., true> fills the counters): fold of row
+// group g by a consumer warp, walk + emits by a producer warp.  rq_build apportions the warps by these instead of its
+// instruction-count model when they are given.
+constexpr int RQ_PROF_WORDS = 32;  // u64: [g] fold cycles, [8+g] tiles, [16+g] wait cycles, [24] producer cycles, [25] tiles, [26] wait
+struct RqCost {
+  bool have = false;
+  double grp[GQ_MAXG] = {0};
+  double prod = 0.0;
+  int force_npcta = 0;   // > 0: this many producer SMs (the calibration's timing trials)
 };
 
 struct RqLaunch {
@@ -88,11 +100,11 @@ RqWalk rq_build_walk(int nj, const DevJoint* joints, const std::vector<char>& ne
                      const std::vector<unsigned>& live, int max_proc, int max_ops);
 
 RqLaunch rq_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, const ColDesc* cols, int sm_count,
-                  int max_smem, RqParams* out, const char** why);
+                  int max_smem, RqParams* out, const char** why, const RqCost* measured = nullptr);
 
 // ring_ctl: 2 * ring + 4 unsigneds (ready[ring], done[ring], error flag, ...), zeroed by the launcher.
 cudaError_t rq_launch(const RqLaunch& rl, const RqParams& prm, const double* q, const double* v, const double* a,
                       const double* tau, int64_t ld_tau, int64_t N, double* r_all, double* ring, unsigned* ring_ctl,
-                      int first, cudaStream_t st);
+                      int first, cudaStream_t st, unsigned long long* prof = nullptr);
 
 }  // namespace fg
