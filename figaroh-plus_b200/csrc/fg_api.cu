@@ -443,6 +443,19 @@ extern "C" int fg_plan_describe(const fg_model_desc* d, const fg_regressor_cfg* 
       }
       o += "]}";
     }
+    o += "], \"stepcols\": [";  // [walk step, row group, local column, ExtraSrc]: written when the walk is at that joint
+    {
+      bool firsts = true;
+      for (int i = 0; i < G.nproc; ++i)
+        for (int k = 0; k < rq->step.n[i]; ++k) {
+          const int e = rq->step.col[i][k];
+          int colpos = e >> 2, g = 0;
+          while (g + 1 < G.ms && colpos >= G.gen.grp[g].nb * 8) { colpos -= G.gen.grp[g].nb * 8; ++g; }
+          snprintf(t, sizeof t, "%s[%d, %d, %d, %d]", firsts ? "" : ", ", i, g, colpos, e & 3);
+          o += t;
+          firsts = false;
+        }
+    }
     o += "]";
   }
   o += "}";

@@ -49,6 +49,17 @@ __device__ __forceinline__ void rq_fence_proxy_async() { asm volatile("fence.pro
 // shared-memory only: orders this thread's generic-proxy accesses to the tile before a bulk copy into it, without
 // waiting for the thread's outstanding global stores (the R blocks)
 __device__ __forceinline__ void rq_fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// read-once input streams: L2 evict-first, so that they do not displace the ring and the factors
+__device__ __forceinline__ unsigned long long rq_policy_evict_first() {
+  unsigned long long p;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ double rq_ldg_stream(const double* p) {
+  double v;
+  asm("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(rq_policy_evict_first()));
+  return v;
+}
 __device__ __forceinline__ unsigned rq_ld_acquire(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");

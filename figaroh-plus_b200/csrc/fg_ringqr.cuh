@@ -237,10 +237,21 @@ static __device__ __forceinline__ void rq_walk_tile(const RqWalkCtx& C, const do
 struct RqRingSink {
   const RqParams* P;
   const GqGen* S;
+  const RqStepTab* ST;
   double* slot;
   bool valid;
   int lane;
-  __device__ __forceinline__ void body_begin(const RqOp&, double, double) {}
+  // the joint's own Ia / fv / fs / off columns (regressor.py:55-70): its (qd, qdd) are in registers here; at the end
+  // of the tile each of them cost a dependent load (a fifth of the producers' time, profiles/ncu_rq_ur10_r02.md)
+  __device__ __forceinline__ void body_begin(const RqOp& op, double cv0, double ca0) {
+    const int n = ST->n[op.t];
+    for (int k = 0; k < n; ++k) {
+      const int e = ST->col[op.t][k];
+      const int col = e >> 2, src = e & 3;
+      const double val = src == SRC_QDD ? ca0 : (src == SRC_QD ? cv0 : (src == SRC_SIGN_QD ? sgn(cv0) : 1.0));
+      slot[col * 32 + (lane ^ tq_sw(col & 7))] = valid ? val : 0.0;
+    }
+  }
   __device__ __forceinline__ void body_end(const RqOp&) {}
   __device__ __forceinline__ void emit(int g, int t, const double* sl, const double* sa, const double* om, const double* al,
                                        const double* ap) {
@@ -249,7 +260,8 @@ struct RqRingSink {
   }
 };
 
-static __device__ __forceinline__ void rq_produce_tile(const RqParams& P, const GqGen& S, const RqOp* ops, double* ps,
+static __device__ __forceinline__ void rq_produce_tile(const RqParams& P, const GqGen& S, const RqStepTab& ST,
+                                                       const RqOp* ops, double* ps,
                                                        double* slot, const double* __restrict__ q,
                                                        const double* __restrict__ qd, const double* __restrict__ qdd,
                                                        const double* __restrict__ tau, int64_t ld_tau, int64_t s0,
@@ -264,9 +276,10 @@ static __device__ __forceinline__ void rq_produce_tile(const RqParams& P, const 
   C.pj = S.pj; C.ops = ops; C.nops = P.nops; C.ms = ms; C.nq = P.gq.nq; C.nv = P.gq.nv; C.nvslots = P.nvslots;
   for (int k = 0; k < 3; ++k) C.gravity[k] = P.gq.gravity[k];
   static_assert(sizeof(GqGroup) % 8 == 0, "GqGroup must be a whole number of doubles");
-  RqRingSink sink{&P, &S, slot, valid, lane};
+  RqRingSink sink{&P, &S, &ST, slot, valid, lane};
   rq_walk_tile<false>(C, S.grp[0].S, (int)(sizeof(GqGroup) / 8), ps, q, qd, qdd, s0, N, lane, sink);
-  // columns read straight off the inputs (friction / actuator inertia / offset / coupling / rhs)
+  // columns read straight off the inputs that no single-dof joint's walk step took (rhs, coupling, free-flyer dofs)
+  // (measured and rejected: L2 evict-first loads of the inputs, 3.57 ms against 3.47; rings of 768 / 1024 slots)
   // (measured and rejected: issuing the loads of eight columns together before consuming them - 4.49 ms against 3.48)
   for (int g = 0; g < ms; ++g) {
     const GqGroup& G = S.grp[g];
@@ -340,8 +353,12 @@ rq_accumulate_kernel(const __grid_constant__ RqParams P, const unsigned char* __
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   GqGen* Sg = reinterpret_cast<GqGen*>(gq_smem);
   RqOp* ops = reinterpret_cast<RqOp*>(gq_smem + GQ_GEN_DOUBLES);
-  constexpr int OPS_DOUBLES = (int)(sizeof(RqOp) * RQ_MAXOPS / 8);
+  constexpr int OPS_DOUBLES = (int)(sizeof(RqOp) * RQ_MAXOPS / 8) + RQ_STEP_DOUBLES;
+  RqStepTab* STs = reinterpret_cast<RqStepTab*>(gq_smem + GQ_GEN_DOUBLES + (int)(sizeof(RqOp) * RQ_MAXOPS / 8));
   {
+    const int* ss = reinterpret_cast<const int*>(&P.step);
+    int* ds = reinterpret_cast<int*>(STs);
+    for (int i = threadIdx.x; i < (int)(sizeof(RqStepTab) / 4); i += blockDim.x) ds[i] = ss[i];
     const int* src = reinterpret_cast<const int*>(&P.gq.gen);
     int* dst = reinterpret_cast<int*>(Sg);
     for (int i = threadIdx.x; i < (int)(sizeof(GqGen) / 4); i += blockDim.x) dst[i] = src[i];
@@ -405,7 +422,7 @@ rq_accumulate_kernel(const __grid_constant__ RqParams P, const unsigned char* __
           if (st < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(tau + (int64_t)(lane >> 1) * ld_tau + st));
         }
       }
-      rq_produce_tile(P, S, ops, mine, ring + (size_t)s * P.slot_doubles, q, qd, qdd, tau, ld_tau, tl * GQ_S, N, lane);
+      rq_produce_tile(P, S, *STs, ops, mine, ring + (size_t)s * P.slot_doubles, q, qd, qdd, tau, ld_tau, tl * GQ_S, N, lane);
       __threadfence();
       __syncwarp();
       if (lane == 0) rq_st_release(ready + s, (unsigned)(tl + 1));

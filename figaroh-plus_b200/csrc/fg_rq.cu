@@ -218,6 +218,32 @@ RqLaunch rq_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, co
     maxnb = std::max(maxnb, G.nb);
   }
   if (maxnb > GQ_MAXB || T.nbf > GQ_MAXBF) { rq_fail(why, "too many column blocks"); return rl; }
+  static_assert(sizeof(RqStepTab) % 4 == 0, "RqStepTab is copied word by word");
+  {  // input-fed columns of single-dof joints move from the end of the tile to the joint's walk step
+    int goff_cols = 0;
+    for (int g = 0; g < ms; ++g) {
+      GqGroup& G = T.gen.grp[g];
+      int keep = 0;
+      for (int t = 0; t < G.nsimple; ++t) {
+        const GqSimple s1 = T.gen.simple[g][t];
+        int at = -1;
+        if (s1.kind == COL_EXTRA)
+          for (int w = 0; w < nproc; ++w) {
+            const DevJoint& jw = T.gen.pj[w];
+            if (jw.jtype >= 1 && jw.jtype <= 3 && jw.idx_v == s1.vidx) at = w;
+          }
+        const int colpos = goff_cols + s1.slot;
+        if (at >= 0 && R.step.n[at] < RQ_STEPCOLS && colpos < (1 << 14)) {
+          R.step.col[at][R.step.n[at]++] = (unsigned short)((colpos << 2) | (s1.src & 3));
+          --n_simple;
+        } else {
+          T.gen.simple[g][keep++] = s1;
+        }
+      }
+      G.nsimple = keep;
+      goff_cols += G.nb * 8;
+    }
+  }
   T.maxnb = maxnb;
   rl.smem_merge = (2 * std::max(maxnb, T.nbf) * GQ_BLK + GQ_SCRATCH) * 8;  // 64-row slabs
   if (rl.smem_merge > max_smem) { rq_fail(why, "tile does not fit shared memory"); return rl; }
@@ -244,7 +270,7 @@ RqLaunch rq_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, co
     pcost = std::max(1.0, measured->prod);
   }
   rl.sm_count = std::max(1, sm_count);
-  const int gen_doubles = GQ_GEN_DOUBLES + (int)(sizeof(RqOp) * RQ_MAXOPS / 8);
+  const int gen_doubles = GQ_GEN_DOUBLES + (int)(sizeof(RqOp) * RQ_MAXOPS / 8) + RQ_STEP_DOUBLES;
   // Roles are assigned per CTA (= per SM): a producer SM runs only the generator, a consumer SM only the fold, so
   // each SM's instruction cache holds one of the two code paths and the 16 producer warps of an SM hide each
   // other's load latencies.  (First version: producers and consumers mixed inside every CTA - the generator's code

@@ -51,6 +51,15 @@ struct RqOp {
   unsigned own;            // descend: row groups carried by this joint (their axis starts here)
 };
 
+// Input-fed columns that depend on ONE single-dof joint's (qd, qdd) are written when the walk is at that joint (the
+// values are in registers there); entry = (column position inside the ring slot << 2) | ExtraSrc.
+constexpr int RQ_STEPCOLS = 32;
+struct RqStepTab {
+  unsigned short col[GQ_MAXPROC][RQ_STEPCOLS];
+  unsigned char n[GQ_MAXPROC];
+};
+constexpr int RQ_STEP_DOUBLES = (int)((sizeof(RqStepTab) + 15) / 16) * 2;
+
 struct RqParams {
   GqParams gq;             // tables shared with the generation-4 merge kernel (groups, emit masks, simple columns)
   int nops;
@@ -62,6 +71,7 @@ struct RqParams {
   int npc;                 // producer CTAs (a CTA is all producers or all consumers)
   int prod_smem_doubles;   // shared memory of one producer warp
   int nvslots, nmslots;
+  RqStepTab step;
   int sleep_ns;            // back-off of a waiting warp between two polls of a ring flag
 };
 

@@ -132,6 +132,9 @@ def run_walk_program(fm, d, q, v, a):
                     AX[g] = _act(R, p, *AX[g])
             if vload != 255:
                 vv, aa = VS[vload][0].copy(), VS[vload][1].copy()
+    for t, g, slot, src in d.get("stepcols", []):  # the joint's own input-fed columns, written at its walk step
+        vidx = int(fm.idx_v[walk[t]])
+        tiles[g][:, slot] = (a[:, vidx], v[:, vidx], np.sign(v[:, vidx]), np.ones(N))[src]
     for g, G in enumerate(groups):
         for kind, src, vidx, slot in G["simple"]:
             if kind == 2:  # COL_EXTRA
