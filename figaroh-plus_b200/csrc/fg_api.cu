@@ -17,6 +17,7 @@
 #include "fg_rq.h"
 #include "fg_wide.h"
 #include "fg_matz.h"
+#include "fg_coop.h"
 #include "fg_prefilter.cuh"
 
 using namespace fg;
@@ -485,19 +486,17 @@ static int launch_materialize(fg_model* m, DevPlan* pl, const double* q, const d
   return FG_OK;
 }
 
-extern "C" int fg_regressor_materialize(const fg_model* mc, const fg_regressor_cfg* cfg, const double* q,
-                                        const double* v, const double* a, int64_t N, double* W, int64_t ldw,
-                                        void* stream) {
-  fg_model* m = const_cast<fg_model*>(mc);
+static int materialize_dev(fg_model* m, const fg_regressor_cfg* cfg, const double* q, const double* v, const double* a,
+                           int64_t N, double* W, int64_t ldw, cudaStream_t st, int* ncols_out = nullptr) {
   DevPlan* pl = nullptr;
   fg_regressor_cfg c2 = *cfg;
   c2.n_row_sel = 0; c2.row_sel = nullptr;  // the materialised matrix always has every row block
   c2.n_col_sel = 0; c2.col_sel = nullptr;  // ... and every column
   int rc = get_plan(m, &c2, nullptr, 0, &pl);
   if (rc) return rc;
+  if (ncols_out) *ncols_out = pl->P.ncols;
   if (N <= 0) return FG_OK;
   if (ldw < pl->P.ncols) return set_err(FG_ERR_INVALID, "ldw=%lld smaller than %d columns", (long long)ldw, pl->P.ncols);
-  cudaStream_t st = (cudaStream_t)stream;
   const int ms = pl->P.ms;
   {  // second version: the producers' walk, one sample per lane, 14-column patches (fg_matz.cuh)
     const char* e = getenv("FG_USE_MATZ");
@@ -521,6 +520,13 @@ extern "C" int fg_regressor_materialize(const fg_model* mc, const fg_regressor_c
   if (ms <= 24) return launch_materialize<24, 1>(m, pl, q, v, a, N, W, ldw, st);
   if (ms <= 48) return launch_materialize<48, 1>(m, pl, q, v, a, N, W, ldw, st);
   return set_err(FG_ERR_UNSUPPORTED, "materialise: %d row blocks per sample not supported", ms);
+}
+
+extern "C" int fg_regressor_materialize(const fg_model* mc, const fg_regressor_cfg* cfg, const double* q,
+                                        const double* v, const double* a, int64_t N, double* W, int64_t ldw,
+                                        void* stream) {
+  if (!mc || !cfg) return set_err(FG_ERR_INVALID, "fg_regressor_materialize: null argument");
+  return materialize_dev(const_cast<fg_model*>(mc), cfg, q, v, a, N, W, ldw, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------ state
@@ -759,10 +765,31 @@ extern "C" int fg_state_accumulate_dense(fg_state* s, const double* W, int64_t l
     return set_err(FG_ERR_UNSUPPORTED, "fg_state_accumulate_dense: the state holds a permuted factor (fused samples); use a fresh state");
   cudaStream_t st = (cudaStream_t)stream;
   const int nslot = (s->p1 + 31) / 32;
-  if (s->p1 > 96) {  // CTA-wide register tile (fg_wide.cuh)
+  if (s->p1 > 96) {  // wide: cooperative blocked TSQR (fg_coop.cuh); beyond its width the register tile (fg_wide.cuh)
     int sm_count, max_smem;
     int rc = device_limits(&sm_count, &max_smem);
     if (rc) return rc;
+    const char* ecq = getenv("FG_USE_CQ");
+    if (!(ecq && ecq[0] == '0') && s->p1 <= cq_max_p1(max_smem)) {
+      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((rows + 63) / 64, sm_count));
+      rc = ensure_parts(s, grid + 1);
+      if (rc) return rc;
+      rc = ensure_gR(s, (int64_t)grid * cq_r_doubles(s->p1));
+      if (rc) return rc;
+      rc = timing_begin(s, st);
+      if (rc) return rc;
+      CqArgs ca;
+      ca.W = W; ca.ldw = ldw; ca.tau = tau; ca.rows = rows; ca.p1 = s->p1;
+      cudaError_t e = cq_launch_dense(ca, s->d_gR, s->d_parts, grid, max_smem, st);
+      rc = timing_end(s, st);
+      if (rc) return rc;
+      if (e != cudaSuccess) return set_err(FG_ERR_CUDA, "cooperative dense kernel failed: %s", cudaGetErrorString(e));
+      FG_LAUNCHED();
+      rc = merge_parts_into_state(s, grid, max_smem, st);
+      if (rc) return rc;
+      s->rows += rows;
+      return FG_OK;
+    }
     const int tr = wide_dense_tile_rows(s->p1);
     if (tr <= 0) return set_err(FG_ERR_UNSUPPORTED, "fg_state_accumulate_dense: %d columns are too many", s->p);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((rows + tr - 1) / tr, sm_count));
@@ -1030,6 +1057,59 @@ static int accumulate_samples_dev(fg_state* s, fg_model* m, const fg_regressor_c
     if (use_rq && pl->rql.ok && s->perm.empty()) {
       if (chunkable) *chunkable = true;
       return launch_rq(s, m, pl, q, v, a, tau, ld_tau, N, phase, st);
+    }
+  }
+  {  // models the row-group streams do not take (Talos with free-flyer: 6 dense rows x 330 columns per sample): W is
+     // materialised a chunk of samples at a time and folded by the cooperative blocked TSQR (fg_coop.cuh)
+    const char* e = getenv("FG_USE_CQ");
+    const bool use_cq = !(e && e[0] == '0');
+    if (use_cq && s->perm.empty() && pl->P.p1 > 96 && pl->P.p1 <= cq_max_p1(m->max_smem)) {
+      fg_regressor_cfg cfull = *cfg;
+      cfull.n_col_sel = 0; cfull.col_sel = nullptr;
+      int ncols_full = 0;
+      rc = materialize_dev(m, &cfull, nullptr, nullptr, nullptr, 0, nullptr, 0, st, &ncols_full);
+      if (rc) return rc;
+      // the materialised matrix has every row block of the mode; the plan may select some of them
+      int ms_full = 0, cols_chk = 0;
+      rc = fg_regressor_shape(m, &cfull, &ms_full, &cols_chk);
+      if (rc) return rc;
+      if (ms_full == ms && !(phase != (FG_PHASE_FIRST | FG_PHASE_LAST))) {
+        const int64_t chunk = std::max<int64_t>(32, std::min<int64_t>(N, (int64_t)(768ll << 20) / ((int64_t)ms * ncols_full * 8)));
+        const int64_t w_doubles = chunk * ms * ncols_full;
+        if (w_doubles > s->ring_cap) {
+          if (s->d_ring) cudaFree(s->d_ring);
+          s->d_ring = nullptr; s->ring_cap = 0;
+          FG_CUDA(cudaMalloc(&s->d_ring, sizeof(double) * w_doubles));
+          s->ring_cap = w_doubles;
+        }
+        s->ring_plan = nullptr;
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((chunk * ms + 63) / 64, m->sm_count));
+        rc = ensure_parts(s, grid + 1);
+        if (rc) return rc;
+        rc = ensure_gR(s, (int64_t)grid * cq_r_doubles(pl->P.p1));
+        if (rc) return rc;
+        rc = timing_begin(s, st);
+        if (rc) return rc;
+        for (int64_t i0 = 0; i0 < N; i0 += chunk) {
+          const int64_t n = std::min(chunk, N - i0);
+          rc = materialize_dev(m, &cfull, q + i0 * m->nq, v + i0 * m->nv, a + i0 * m->nv, n, s->d_ring, ncols_full, st);
+          if (rc) return rc;
+          CqArgs ca;
+          ca.W = s->d_ring; ca.ldw = ncols_full; ca.colsel = pl->ptrs.fullcol;
+          ca.tau = tau ? tau + i0 : nullptr; ca.tau_blk = n; ca.tau_ld = ld_tau;
+          ca.rows = n * ms; ca.p1 = pl->P.p1;
+          ca.first = i0 == 0; ca.last = i0 + n >= N;
+          cudaError_t ce = cq_launch_dense(ca, s->d_gR, s->d_parts, grid, m->max_smem, st);
+          if (ce != cudaSuccess) return set_err(FG_ERR_CUDA, "cooperative dense kernel failed: %s", cudaGetErrorString(ce));
+          FG_LAUNCHED();
+        }
+        rc = timing_end(s, st);
+        if (rc) return rc;
+        rc = merge_parts_into_state(s, grid, m->max_smem, st);
+        if (rc) return rc;
+        s->rows += N * ms;
+        return FG_OK;
+      }
     }
   }
   {

@@ -1,0 +1,45 @@
+// fg_coop.cu - host side of the cooperative blocked TSQR (fg_coop.cuh).
+#include "fg_coop.cuh"
+#include "fg_coop.h"
+
+namespace fg {
+
+static int cq_smem_bytes(int rpl, int nb) {
+  return (int)(((size_t)rpl * nb * GQ_BLK + (size_t)nb * 64 + (size_t)CQ_NW * GQ_SCRATCH + 2) * 8);
+}
+
+int cq_max_p1(int max_smem) {
+  int nb = 0;
+  while (cq_smem_bytes(1, nb + 1) <= max_smem) ++nb;
+  return nb * 8;
+}
+
+int64_t cq_r_doubles(int p1) {
+  const int64_t nb = (p1 + 7) / 8;
+  return nb * (nb + 1) / 2 * 64;
+}
+
+cudaError_t cq_launch_dense(const CqArgs& a, double* r_all, double* parts, int grid, int max_smem, cudaStream_t st) {
+  CqParams P;
+  P.W = a.W; P.ldw = a.ldw; P.colsel = a.colsel; P.tau = a.tau; P.rows = a.rows; P.p1 = a.p1;
+  P.nb = (a.p1 + 7) / 8;
+  P.r_all = r_all; P.parts = parts;
+  P.tau_blk = a.tau_blk; P.tau_ld = a.tau_ld;
+  P.first = a.first ? 1 : 0; P.last = a.last ? 1 : 0;
+  const int rpl = cq_smem_bytes(2, P.nb) <= max_smem ? 2 : 1;
+  const int smem = cq_smem_bytes(rpl, P.nb);
+  if (smem > max_smem) return cudaErrorInvalidValue;
+  cudaError_t e;
+  if (rpl == 2) {
+    e = cudaFuncSetAttribute(cq_accumulate_dense_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    cq_accumulate_dense_kernel<2><<<grid, CQ_NW * 32, smem, st>>>(P);
+  } else {
+    e = cudaFuncSetAttribute(cq_accumulate_dense_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    cq_accumulate_dense_kernel<1><<<grid, CQ_NW * 32, smem, st>>>(P);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace fg

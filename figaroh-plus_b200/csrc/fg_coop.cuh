@@ -1,0 +1,249 @@
+// fg_coop.cuh - kernel (2) for WIDE dense problems: blocked Householder TSQR of a tall matrix that is already in
+// HBM, one CTA per SM working on ONE 64-row tile at a time, the column blocks shared out among its warps.
+//
+// Where it is used: Talos with free-flyer in external-wrench mode (6 rows x 330 kept columns per sample,
+// regressor.py:89-192 of the reference: every row depends on every body, there is no row-group sparsity to
+// exploit), the drop-in double_QR / get_baseParams on a wide W_e (qrdecomposition.py:89-296: two np.linalg.qr of
+// the tall matrix), and any model the row-group streams of fg_ringqr.cuh do not take.  W is materialised a chunk
+// of samples at a time by kernel (1) (fg_matz.cuh) - 2 x 3.7 KB of HBM traffic per row against 2.6 Mflop of
+// Householder work per row, i.e. the detour through HBM is 5 % of the FP64 time.
+//
+// What the column-at-a-time register-tile kernel of fg_wide.cuh showed (profiles/ncu_wide_talos_r02.md: 6.8 % of the
+// FP64 roofline): one CTA-wide barrier per column, 331 of them per tile, and no tensor-core work.  Here:
+//   * the tile (64 rows x nb 8-column blocks, fg_tile.cuh layout) lives in shared memory, the CTA's
+//     block-upper-triangular factor R in an L2-resident scratch (nb (nb + 1) / 2 blocks of 8 x 8);
+//   * warp w OWNS the column blocks j = w (mod NW): nobody else ever touches block j of the tile or column j of R,
+//     so there is no barrier inside a tile - only one flag, "panel k is published";
+//   * panel k (8 columns, two rows per lane) is factored by its owner with the row-group streams' Householder panel
+//     (gq_panel_factor: LAPACK dlarfg reflectors, compact-WY T from a DMMA); the owner leaves V_k in place of the
+//     block, T_k in a per-panel slot and raises the flag;
+//   * every warp then applies panel k to its own blocks j > k with DMMA (Y = R_kj + V^T B_j, W = T^T Y,
+//     R_kj -= W, B_j -= V W: gq_fold_h's trailing update).  The owner of block k + 1 does that block FIRST and
+//     factors panel k + 1 at once (look-ahead), so the serial chain of a tile is nb x (one update + one panel)
+//     while the other nb (nb - 1) / 2 updates fill the FP64 pipe around it.
+#pragma once
+#define FG_GQ_DEVICE_ONLY
+#include "fg_groupqr.cuh"
+
+namespace fg {
+
+constexpr int CQ_NW = 8;          // warps of the CTA
+// RPL rows per lane: 64-row tiles (RPL = 2) up to 49 column blocks, 32-row tiles (RPL = 1) up to 88
+
+struct CqParams {
+  const double* W;        // rows x ldw, row-major
+  int64_t ldw;
+  const int* colsel;      // p column indices into W, or nullptr (identity)
+  const double* tau;      // rhs: one entry per row, or nullptr
+  int64_t rows;
+  int p1;                 // columns incl. the rhs
+  int nb;                 // 8-column blocks
+  double* r_all;          // grid x nb (nb + 1) / 2 x 64 doubles
+  double* parts;          // grid x part_doubles(p1)
+  int64_t tau_blk, tau_ld;  // rhs of row r at tau[(r / tau_blk) * tau_ld + r % tau_blk] (tau_blk = 0: tau[r])
+  int first, last;        // first launch of a sequence zeroes the factors, the last one writes the parts
+};
+
+__device__ __forceinline__ void cq_wait(const volatile int* flag, int want) {
+  while (*flag < want) __nanosleep(100);
+  __threadfence_block();
+}
+
+// reflector fragments of panel k (kept in registers for the updates that follow)
+template <int RPL>
+struct CqFrag {
+  double vc0[RPL][4], vc1[RPL][4], vb0[RPL][4], vb1[RPL][4];
+  double t0, t1;
+};
+
+template <int RPL>
+__device__ __forceinline__ void cq_load_frag(CqFrag<RPL>& f, const double* tile, int nb, int k, const double* Tb,
+                                             const GqOffs& o, int lane) {
+  const int cq = lane >> 2, rq = lane & 3;
+  const double* Xk = tile + k * GQ_BLK;
+#pragma unroll
+  for (int sl = 0; sl < RPL; ++sl)
+#pragma unroll
+    for (int nn = 0; nn < 4; ++nn) {
+      f.vc0[sl][nn] = Xk[sl * nb * GQ_BLK + o.oc0[nn]];
+      f.vc1[sl][nn] = Xk[sl * nb * GQ_BLK + o.oc1[nn]];
+      f.vb0[sl][nn] = Xk[sl * nb * GQ_BLK + o.ob0[nn]];
+      f.vb1[sl][nn] = Xk[sl * nb * GQ_BLK + o.ob1[nn]];
+    }
+  const double* TS = Tb + k * 64;
+  f.t0 = 2 * rq <= cq ? TS[(2 * rq) * 8 + cq] : 0.0;
+  f.t1 = 2 * rq + 1 <= cq ? TS[(2 * rq + 1) * 8 + cq] : 0.0;
+}
+
+// panel k applied to block j of the tile and to R_kj (the trailing update of gq_fold_h)
+template <int RPL>
+__device__ __forceinline__ void cq_update(const CqFrag<RPL>& f, double* tile, int nb, int j, double* Rb, double r0, double r1,
+                                          const GqOffs& o, int lane) {
+  const int cq = lane >> 2, rq = lane & 3;
+  double* Bj = tile + j * GQ_BLK;
+  double c0[RPL][4], c1[RPL][4];
+#pragma unroll
+  for (int sl = 0; sl < RPL; ++sl)
+#pragma unroll
+    for (int nn = 0; nn < 4; ++nn) {
+      c0[sl][nn] = Bj[sl * nb * GQ_BLK + o.oc0[nn]];
+      c1[sl][nn] = Bj[sl * nb * GQ_BLK + o.oc1[nn]];
+    }
+  double y0 = 0.0, y1 = 0.0, z0 = 0.0, z1 = 0.0;
+#pragma unroll
+  for (int sl = 0; sl < RPL; ++sl)
+#pragma unroll
+    for (int nn = 0; nn < 4; ++nn) {
+      tq_dmma(y0, y1, c0[sl][nn], f.vc0[sl][nn]);
+      tq_dmma(z0, z1, c1[sl][nn], f.vc1[sl][nn]);
+    }
+  y0 += z0 + r0;
+  y1 += z1 + r1;
+  double w0 = 0.0, w1 = 0.0;
+  tq_dmma(w0, w1, y0, f.t0);
+  tq_dmma(w0, w1, y1, f.t1);
+  Rb[(2 * rq) * 8 + cq] = r0 - w0;
+  Rb[(2 * rq + 1) * 8 + cq] = r1 - w1;
+  const double nw0 = -w0, nw1 = -w1;
+#pragma unroll
+  for (int sl = 0; sl < RPL; ++sl)
+#pragma unroll
+    for (int nn = 0; nn < 4; ++nn) {
+      tq_dmma(c0[sl][nn], c1[sl][nn], nw0, f.vb0[sl][nn]);
+      tq_dmma(c0[sl][nn], c1[sl][nn], nw1, f.vb1[sl][nn]);
+      Bj[sl * nb * GQ_BLK + o.oc0[nn]] = c0[sl][nn];
+      Bj[sl * nb * GQ_BLK + o.oc1[nn]] = c1[sl][nn];
+    }
+}
+
+// panel k: Householder factorisation of [R_kk; block k of the tile]; V_k stays in the block, T_k goes to Tb[k]
+template <int RPL>
+__device__ __forceinline__ void cq_panel(double* tile, int nb, int k, double* R, double* Tb, double* scr, const GqOffs& o,
+                                         int lane) {
+  double* Rd = R + (size_t)tq_rblk(nb, k, k) * 64;
+  double* Xk = tile + k * GQ_BLK;
+  double* Rin = scr;
+  double* sc = scr + 64;
+  Rin[lane] = __ldcg(Rd + lane);
+  Rin[lane + 32] = __ldcg(Rd + lane + 32);
+  double x[RPL][8];
+#pragma unroll
+  for (int sl = 0; sl < RPL; ++sl)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) x[sl][c] = Xk[sl * nb * GQ_BLK + tq_idx(c, lane)];
+  __syncwarp();
+  gq_panel_factor<RPL>(x, Rin, Rin, sc, Xk, lane);
+  if ((lane >> 3) <= (lane & 7)) Rd[lane] = Rin[lane];
+  if ((lane >> 3) + 4 <= (lane & 7)) Rd[lane + 32] = Rin[lane + 32];
+#pragma unroll
+  for (int sl = 0; sl < RPL; ++sl)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) Xk[sl * nb * GQ_BLK + tq_idx(c, lane)] = x[sl][c];
+  __syncwarp();
+  double vc0[RPL][4], vc1[RPL][4];
+#pragma unroll
+  for (int sl = 0; sl < RPL; ++sl)
+#pragma unroll
+    for (int nn = 0; nn < 4; ++nn) {
+      vc0[sl][nn] = Xk[sl * nb * GQ_BLK + o.oc0[nn]];
+      vc1[sl][nn] = Xk[sl * nb * GQ_BLK + o.oc1[nn]];
+    }
+  gq_panel_T<RPL>(vc0, vc1, sc, Tb + k * 64, lane);
+}
+
+template <int RPL>
+__global__ void __launch_bounds__(CQ_NW * 32, 1)
+cq_accumulate_dense_kernel(const __grid_constant__ CqParams P) {
+  extern __shared__ __align__(16) double cq_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nb = P.nb, p1 = P.p1, p = p1 - 1;  // the last column is the rhs (zero without tau)
+  double* tile = cq_smem;                               // RPL x nb blocks
+  double* Tb = tile + (size_t)RPL * nb * GQ_BLK;     // nb x 64
+  double* scr = Tb + (size_t)nb * 64 + (size_t)warp * GQ_SCRATCH;
+  volatile int* flag = reinterpret_cast<volatile int*>(Tb + (size_t)nb * 64 + (size_t)CQ_NW * GQ_SCRATCH);
+  const size_t rsize = (size_t)nb * (nb + 1) / 2 * 64;
+  double* R = P.r_all + (size_t)blockIdx.x * rsize;
+  if (P.first)
+    for (size_t i = threadIdx.x; i < rsize; i += blockDim.x) R[i] = 0.0;
+  if (threadIdx.x == 0) *flag = 0;
+  GqOffs offs;
+  gq_make_offs(offs, lane);
+  const int ncol = nb * 8;
+  constexpr int CQ_TR = 32 * RPL;
+  const int64_t ntiles = (P.rows + CQ_TR - 1) / CQ_TR;
+  int base = 0;  // flag value before panel 0 of the current tile
+  for (int64_t tl = blockIdx.x; tl < ntiles; tl += gridDim.x, base += nb) {
+    __syncthreads();  // the previous tile is finished with by every warp (and R is zeroed before the first one)
+    // ---- the tile: rows row0 .. row0 + 63 of [W(:, colsel) | tau], zero padded
+    const int64_t row0 = tl * CQ_TR;
+    for (int e = threadIdx.x; e < CQ_TR * ncol; e += blockDim.x) {
+      const int r = e / ncol, c = e - r * ncol;
+      double val = 0.0;
+      if (row0 + r < P.rows) {
+        if (c < p) val = __ldg(P.W + (row0 + r) * P.ldw + (P.colsel ? P.colsel[c] : c));
+        else if (c < p1 && P.tau != nullptr) {
+          const int64_t rr = row0 + r;
+          val = __ldg(P.tau + (P.tau_blk ? (rr / P.tau_blk) * P.tau_ld + rr % P.tau_blk : rr));
+        }
+      }
+      tile[(size_t)(r >> 5) * nb * GQ_BLK + (c >> 3) * GQ_BLK + tq_idx(c & 7, r & 31)] = val;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      cq_panel<RPL>(tile, nb, 0, R, Tb, scr, offs, lane);
+      __threadfence_block();
+      __syncwarp();
+      if (lane == 0) *flag = base + 1;
+    }
+    const int cq = lane >> 2, rq = lane & 3;
+    for (int k = 0; k + 1 < nb; ++k) {
+      int j = k + 1 + ((warp - (k + 1)) % CQ_NW + CQ_NW) % CQ_NW;  // my first block to the right of k
+      if (j >= nb) continue;
+      cq_wait(flag, base + k + 1);
+      CqFrag<RPL> f;
+      cq_load_frag(f, tile, nb, k, Tb, offs, lane);
+      double* Rb = R + (size_t)tq_rblk(nb, k, j) * 64;
+      double r0 = __ldcg(Rb + (2 * rq) * 8 + cq), r1 = __ldcg(Rb + (2 * rq + 1) * 8 + cq);
+      if (j == k + 1) {  // look-ahead: this block first, then its panel, then the rest of panel k's updates
+        cq_update(f, tile, nb, j, Rb, r0, r1, offs, lane);
+        __syncwarp();
+        cq_panel<RPL>(tile, nb, j, R, Tb, scr, offs, lane);
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) *flag = base + k + 2;
+        j += CQ_NW;
+        if (j >= nb) continue;
+        cq_load_frag(f, tile, nb, k, Tb, offs, lane);
+        Rb = R + (size_t)tq_rblk(nb, k, j) * 64;
+        r0 = __ldcg(Rb + (2 * rq) * 8 + cq);
+        r1 = __ldcg(Rb + (2 * rq + 1) * 8 + cq);
+      }
+      for (; j < nb; j += CQ_NW) {
+        double nr0 = 0.0, nr1 = 0.0;
+        double* Rn = Rb + (size_t)CQ_NW * 64;  // blocks of one block row are consecutive
+        if (j + CQ_NW < nb) { nr0 = __ldcg(Rn + (2 * rq) * 8 + cq); nr1 = __ldcg(Rn + (2 * rq + 1) * 8 + cq); }
+        cq_update(f, tile, nb, j, Rb, r0, r1, offs, lane);
+        Rb = Rn; r0 = nr0; r1 = nr1;
+      }
+    }
+  }
+  __syncthreads();
+  if (!P.last) return;
+  // ---- packed upper triangle + squared column norms (the part format of merge_pairs / wide merge)
+  double* out = P.parts + (size_t)blockIdx.x * part_doubles(p1);
+  const int ntri = p1 * (p1 + 1) / 2;
+  for (int idx = threadIdx.x; idx < p1 * p1; idx += blockDim.x) {
+    const int r = idx / p1, c = idx - r * p1;
+    if (c >= r) out[tri_off(r, p1) + c - r] = __ldcg(R + (size_t)tq_rblk(nb, r >> 3, c >> 3) * 64 + (r & 7) * 8 + (c & 7));
+  }
+  for (int c = threadIdx.x; c < p1; c += blockDim.x) {
+    double sacc = 0.0;
+    for (int r = 0; r <= c; ++r) {
+      const double x = __ldcg(R + (size_t)tq_rblk(nb, r >> 3, c >> 3) * 64 + (r & 7) * 8 + (c & 7));
+      sacc = fma(x, x, sacc);
+    }
+    out[ntri + c] = sacc;
+  }
+}
+
+}  // namespace fg

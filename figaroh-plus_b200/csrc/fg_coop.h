@@ -1,0 +1,27 @@
+// fg_coop.h - host interface of the cooperative blocked TSQR of a dense matrix in HBM (fg_coop.cuh).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace fg {
+
+// widest problem (columns incl. the rhs) the kernel takes with max_smem bytes of shared memory per CTA; 0 = none
+int cq_max_p1(int max_smem);
+// doubles of one CTA's block-triangular factor
+int64_t cq_r_doubles(int p1);
+
+struct CqArgs {
+  const double* W = nullptr;   // rows x ldw, row-major (device)
+  int64_t ldw = 0;
+  const int* colsel = nullptr; // p1 - 1 column indices into W (device), or nullptr: columns 0 .. p1 - 2
+  const double* tau = nullptr; // rhs (device) or nullptr
+  int64_t tau_blk = 0, tau_ld = 0;  // rhs of row r at tau[(r / tau_blk) * tau_ld + r % tau_blk]; tau_blk = 0: tau[r]
+  int64_t rows = 0;
+  int p1 = 0;
+  bool first = true, last = true;   // a sequence of launches over row chunks shares the per-CTA factors
+};
+// CTA b of `grid` folds tiles b, b + grid, ... into its factor r_all + b * cq_r_doubles(p1); the last launch of a
+// sequence writes parts[b] (packed triangle + squared column norms).
+cudaError_t cq_launch_dense(const CqArgs& a, double* r_all, double* parts, int grid, int max_smem, cudaStream_t st);
+
+}  // namespace fg
