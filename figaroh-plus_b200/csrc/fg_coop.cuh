@@ -24,6 +24,7 @@
 #pragma once
 #define FG_GQ_DEVICE_ONLY
 #include "fg_groupqr.cuh"
+#include "fg_async.cuh"
 
 namespace fg {
 
@@ -44,9 +45,16 @@ struct CqParams {
   int first, last;        // first launch of a sequence zeroes the factors, the last one writes the parts
 };
 
-__device__ __forceinline__ void cq_wait(const volatile int* flag, int want) {
-  while (*flag < want) __nanosleep(100);
+// "panel k is published": one mbarrier per panel (arrival count 1, the owner's lane 0), phase = parity of the CTA's
+// tile counter.  Waiting warps sit in mbarrier.try_wait (the hardware suspends them) instead of polling a flag in
+// shared memory (first version: the polls were 42 % of all executed instructions, profiles/ncu_cq_talos_r02_v1.md).
+__device__ __forceinline__ void cq_wait(uint64_t* bar, uint32_t parity) {
+  while (!rq_mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void cq_publish(uint64_t* bar, int lane) {
   __threadfence_block();
+  __syncwarp();
+  if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rq_smem_u32(bar)) : "memory");
 }
 
 // reflector fragments of panel k (kept in registers for the updates that follow)
@@ -160,46 +168,73 @@ cq_accumulate_dense_kernel(const __grid_constant__ CqParams P) {
   double* tile = cq_smem;                               // RPL x nb blocks
   double* Tb = tile + (size_t)RPL * nb * GQ_BLK;     // nb x 64
   double* scr = Tb + (size_t)nb * 64 + (size_t)warp * GQ_SCRATCH;
-  volatile int* flag = reinterpret_cast<volatile int*>(Tb + (size_t)nb * 64 + (size_t)CQ_NW * GQ_SCRATCH);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Tb + (size_t)nb * 64 + (size_t)CQ_NW * GQ_SCRATCH);  // nb of them
   const size_t rsize = (size_t)nb * (nb + 1) / 2 * 64;
   double* R = P.r_all + (size_t)blockIdx.x * rsize;
   if (P.first)
     for (size_t i = threadIdx.x; i < rsize; i += blockDim.x) R[i] = 0.0;
-  if (threadIdx.x == 0) *flag = 0;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) rq_mbar_init(bars + i, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   GqOffs offs;
   gq_make_offs(offs, lane);
   const int ncol = nb * 8;
   constexpr int CQ_TR = 32 * RPL;
   const int64_t ntiles = (P.rows + CQ_TR - 1) / CQ_TR;
-  int base = 0;  // flag value before panel 0 of the current tile
-  for (int64_t tl = blockIdx.x; tl < ntiles; tl += gridDim.x, base += nb) {
+  uint32_t parity = 0;
+  for (int64_t tl = blockIdx.x; tl < ntiles; tl += gridDim.x, parity ^= 1u) {
     __syncthreads();  // the previous tile is finished with by every warp (and R is zeroed before the first one)
-    // ---- the tile: rows row0 .. row0 + 63 of [W(:, colsel) | tau], zero padded
+    // ---- the tile: rows row0 .. row0 + 32 RPL - 1 of [W(:, colsel) | tau], zero padded.  One warp instruction moves one
+    // column block x 4 rows (lane = (column, row mod 4): 64-byte row segments from HBM, conflict-free stores); eight
+    // of them are in flight per warp.
     const int64_t row0 = tl * CQ_TR;
-    for (int e = threadIdx.x; e < CQ_TR * ncol; e += blockDim.x) {
-      const int r = e / ncol, c = e - r * ncol;
-      double val = 0.0;
-      if (row0 + r < P.rows) {
-        if (c < p) val = __ldg(P.W + (row0 + r) * P.ldw + (P.colsel ? P.colsel[c] : c));
-        else if (c < p1 && P.tau != nullptr) {
-          const int64_t rr = row0 + r;
-          val = __ldg(P.tau + (P.tau_blk ? (rr / P.tau_blk) * P.tau_ld + rr % P.tau_blk : rr));
+    {
+      const int cb = lane >> 2, rr = lane & 3;
+      for (int b = warp; b < nb; b += CQ_NW) {
+        const int c = b * 8 + cb;
+        const double* src = nullptr;
+        int64_t stride = 0;
+        if (c < p) { src = P.W + (P.colsel ? P.colsel[c] : c); stride = P.ldw; }
+        double* dstb = tile + (size_t)b * GQ_BLK;
+#pragma unroll
+        for (int r0 = 0; r0 < CQ_TR; r0 += 32) {
+          double val[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int64_t r = row0 + r0 + 4 * u + rr;
+            val[u] = 0.0;
+            if (r < P.rows) {
+              if (src != nullptr) val[u] = __ldg(src + r * stride);
+              else if (c == p && P.tau != nullptr) val[u] = __ldg(P.tau + (P.tau_blk ? (r / P.tau_blk) * P.tau_ld + r % P.tau_blk : r));
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) dstb[(size_t)(r0 >> 5) * nb * GQ_BLK + tq_idx(cb, 4 * u + rr)] = val[u];
         }
       }
-      tile[(size_t)(r >> 5) * nb * GQ_BLK + (c >> 3) * GQ_BLK + tq_idx(c & 7, r & 31)] = val;
+      // next tile of this CTA towards L2 while this one is folded
+      const int64_t nrow0 = (tl + gridDim.x) * CQ_TR;
+      if (nrow0 < P.rows) {
+        const int64_t row_bytes = (int64_t)P.ldw * 8;
+        const int lines = (int)((row_bytes + 127) / 128) + 1;
+        for (int e = threadIdx.x; e < CQ_TR * lines; e += blockDim.x) {
+          const int r = e / lines, l = e - r * lines;
+          if (nrow0 + r < P.rows) {
+            const char* ptr = reinterpret_cast<const char*>(P.W + (nrow0 + r) * P.ldw) + (int64_t)l * 128;
+            if (l * 128 < row_bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+          }
+        }
+      }
     }
-    __syncthreads();
+    __syncwarp();  // every warp loaded its OWN blocks: nobody waits for anybody here
     if (warp == 0) {
       cq_panel<RPL>(tile, nb, 0, R, Tb, scr, offs, lane);
-      __threadfence_block();
-      __syncwarp();
-      if (lane == 0) *flag = base + 1;
+      cq_publish(bars, lane);
     }
     const int cq = lane >> 2, rq = lane & 3;
     for (int k = 0; k + 1 < nb; ++k) {
       int j = k + 1 + ((warp - (k + 1)) % CQ_NW + CQ_NW) % CQ_NW;  // my first block to the right of k
       if (j >= nb) continue;
-      cq_wait(flag, base + k + 1);
+      cq_wait(bars + k, parity);
       CqFrag<RPL> f;
       cq_load_frag(f, tile, nb, k, Tb, offs, lane);
       double* Rb = R + (size_t)tq_rblk(nb, k, j) * 64;
@@ -208,9 +243,7 @@ cq_accumulate_dense_kernel(const __grid_constant__ CqParams P) {
         cq_update(f, tile, nb, j, Rb, r0, r1, offs, lane);
         __syncwarp();
         cq_panel<RPL>(tile, nb, j, R, Tb, scr, offs, lane);
-        __threadfence_block();
-        __syncwarp();
-        if (lane == 0) *flag = base + k + 2;
+        cq_publish(bars + j, lane);
         j += CQ_NW;
         if (j >= nb) continue;
         cq_load_frag(f, tile, nb, k, Tb, offs, lane);

@@ -20,7 +20,7 @@ MatzPlan matz_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, 
   std::vector<unsigned> own(nj, 0u), live(nj, 0u);
   for (int g = 0; g < ms; ++g) own[rows[g].joint] |= 1u << g;
   for (int i = 1; i < nj; ++i) live[i] = live[joints[i].parent] | own[i];
-  const RqWalk walk = rq_build_walk(nj, joints, need, own, live, kMaxJoints, 2 * kMaxJoints);
+  const RqWalk walk = rq_build_walk(nj, joints, need, own, live, kMaxJoints, 2 * kMaxJoints, 24);
   if (!walk.ok || (int)walk.order.size() != nb) return mp;
   mp.tab.reset(new MatzTables);
   MatzTables& T = *mp.tab;
@@ -49,13 +49,20 @@ MatzPlan matz_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, 
     }
     T.extra_grp[b] = eg;
   }
-  // walk | patch stage | staged inputs of one tile | mbarrier
-  M.smem_per_warp = (ms * 6 + 12 * (M.nvslots + M.nmslots)) * 32 + MATZ_STAGE + (MATZ_STAGE & 1) + 32 * (P.nq + 2 * P.nv) + 2;
-  M.smem_per_warp += M.smem_per_warp & 1;
+  // walk | patch stage | staged inputs of one tile | mbarrier.  Wide models (Talos: 39 + 2 x 38 inputs and eight saved
+  // transforms per sample) keep their inputs in global memory: staging them would leave two warps per SM.
   const int tab_bytes = (int)((sizeof(MatzTables) + 15) / 16) * 16;
-  int nw = MATZ_WARPS;
-  while (nw > 0 && tab_bytes + nw * M.smem_per_warp * 8 > max_smem) --nw;
-  if (nw < 4) { mp.tab.reset(); return mp; }
+  int nw = 0;
+  for (int stage_in = 1; stage_in >= 0; --stage_in) {
+    M.stage_inputs = stage_in;
+    M.smem_per_warp = (ms * 6 + 12 * (M.nvslots + M.nmslots)) * 32 + MATZ_STAGE + (MATZ_STAGE & 1) +
+                      (stage_in ? 32 * (P.nq + 2 * P.nv) : 0) + 2;
+    M.smem_per_warp += M.smem_per_warp & 1;
+    nw = MATZ_WARPS;
+    while (nw > 0 && tab_bytes + nw * M.smem_per_warp * 8 > max_smem) --nw;
+    if (nw >= (stage_in ? 6 : 1)) break;
+  }
+  if (nw < 1) { mp.tab.reset(); return mp; }
   mp.nw = nw;
   mp.smem = tab_bytes + nw * M.smem_per_warp * 8;
   mp.sm_count = sm_count;

@@ -201,12 +201,13 @@ matz_kernel(const __grid_constant__ MatzParams P, const MatzTables* __restrict__
   const int nb = P.nj - 1;
   // inputs of a tile, staged by the copy engine while the previous tile's patches drain (the per-lane loads at a
   // 48-byte stride were the walk's top stall under the write stream: profiles/ncu_matz_r02_v2.md)
+  const bool stin = P.stage_inputs != 0;
   double* in_q = stage + MATZ_STAGE + (MATZ_STAGE & 1);
   double* in_v = in_q + 32 * P.nq;
   double* in_a = in_v + 32 * P.nv;
   uint64_t* bar = reinterpret_cast<uint64_t*>(in_a + 32 * P.nv);
   const bool in16 = ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(qd) | reinterpret_cast<uintptr_t>(qdd)) & 15) == 0;
-  if (lane == 0) {
+  if (stin && lane == 0) {
     rq_mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -226,12 +227,13 @@ matz_kernel(const __grid_constant__ MatzParams P, const MatzTables* __restrict__
   };
   int buf = 0;
   int64_t tl = (int64_t)blockIdx.x * nw + warp;
-  if (tl < ntiles) request(tl);
+  if (stin && tl < ntiles) request(tl);
   for (; tl < ntiles; tl += (int64_t)gridDim.x * nw) {
     const int64_t s0 = tl * 32, smp = s0 + lane;
     const bool valid = smp < N;
     const int nrows = (int)(N - s0 < 32 ? N - s0 : 32);
-    if (nrows == 32 && in16) {
+    if (!stin) {
+    } else if (nrows == 32 && in16) {
       while (!rq_mbar_try_wait(bar, parity)) {}
       parity ^= 1u;
     } else {
@@ -239,16 +241,19 @@ matz_kernel(const __grid_constant__ MatzParams P, const MatzTables* __restrict__
       for (int i = lane; i < nrows * P.nv; i += 32) { in_v[i] = __ldg(qd + s0 * P.nv + i); in_a[i] = __ldg(qdd + s0 * P.nv + i); }
       __syncwarp();
     }
-    const int sc = valid ? lane : nrows - 1;
+    const int64_t sc = stin ? (valid ? lane : nrows - 1) : (valid ? smp : N - 1);
+    const double* src_v = stin ? in_v : qd;
+    const double* src_a = stin ? in_a : qdd;
     MatzSink sink;
     sink.P = &P; sink.T = T; sink.stage = stage; sink.W = W; sink.ldw = ldw; sink.N = N; sink.s0 = s0;
-    sink.vs = in_v + sc * P.nv; sink.as = in_a + sc * P.nv; sink.valid = valid; sink.lane = lane; sink.done = 0u; sink.body = 1;
+    sink.vs = src_v + sc * P.nv; sink.as = src_a + sc * P.nv; sink.valid = valid; sink.lane = lane; sink.done = 0u; sink.body = 1;
     sink.aligned = (ldw & 3) == 0 && (reinterpret_cast<uintptr_t>(W) & 31) == 0;
     sink.aligned16 = (ldw & 1) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0;
     sink.buf = buf;  // the rotation runs across tiles: one __syncwarp lies between two uses of a buffer
     sink.nrows = nrows;
     sink.mode = 0; sink.eg = sink.egp = -2; sink.vv = sink.aa = sink.pv = 0.0;
-    rq_walk_tile<true>(C, &T->S[0][0], 6, ps, in_q, in_v, in_a, 0, nrows, lane, sink);
+    if (stin) rq_walk_tile<true>(C, &T->S[0][0], 6, ps, in_q, in_v, in_a, 0, nrows, lane, sink);
+    else rq_walk_tile<false>(C, &T->S[0][0], 6, ps, q, qd, qdd, s0, N, lane, sink);
     buf = sink.buf;
     if (P.coupling) {
       // add_coupling_TX40 (regressor.py:216-225): row block 4 <- [a5, v5, sign(v4+v5)], 5 <- [a4, v4, sign(v4+v5)]
@@ -264,11 +269,12 @@ matz_kernel(const __grid_constant__ MatzParams P, const MatzTables* __restrict__
         }
       }
     }
-    // every lane has read its inputs: the next tile may land
-    rq_fence_proxy_async_smem();
-    __syncwarp();
-    const int64_t nx = tl + (int64_t)gridDim.x * nw;
-    if (nx < ntiles) request(nx);
+    if (stin) {  // every lane has read its inputs: the next tile may land
+      rq_fence_proxy_async_smem();
+      __syncwarp();
+      const int64_t nx = tl + (int64_t)gridDim.x * nw;
+      if (nx < ntiles) request(nx);
+    }
   }
 #ifdef MATZ_BULK
   rq_bulk_wait_read<0>();  // the copies read this CTA's shared memory

@@ -9,6 +9,7 @@ struct MatzParams {
   int nvslots, nmslots;
   int coupling;             // 3 extra TX40 columns behind the bodies' blocks
   int smem_per_warp;        // doubles
+  int stage_inputs;         // the tile's (q, qd, qdd) are staged in shared memory by bulk copy (small models)
   double gravity[3];
 };
 

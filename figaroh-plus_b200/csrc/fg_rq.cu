@@ -26,7 +26,7 @@ static int env_int(const char* name, int dflt) {
 // parent's (v, a) is saved before it, the joint transforms inside it are saved as it descends, and it is walked
 // back up (axes transported with the inverse action) when it is done.
 RqWalk rq_build_walk(int nj, const DevJoint* joints, const std::vector<char>& need, const std::vector<unsigned>& own,
-                     const std::vector<unsigned>& live, int max_proc, int max_ops) {
+                     const std::vector<unsigned>& live, int max_proc, int max_ops, int max_slots) {
   RqWalk W;
   std::vector<std::vector<int>> kids(nj);
   std::vector<int> height(nj, 0);
@@ -63,14 +63,14 @@ RqWalk rq_build_walk(int nj, const DevJoint* joints, const std::vector<char>& ne
       op.from_universe = b == 0;
       int my_vslot = 255;
       if (side) {
-        if (vdepth >= RQ_MAXSLOTS) { fail = true; return; }
+        if (vdepth >= max_slots) { fail = true; return; }
         my_vslot = vdepth++;
         W.nvslots = std::max(W.nvslots, vdepth);
         op.vsave = (unsigned char)my_vslot;
       }
       const size_t path_mark = path.size();
       if (trip) {
-        if ((int)path.size() >= RQ_MAXSLOTS) { fail = true; return; }
+        if ((int)path.size() >= max_slots) { fail = true; return; }
         mslot_of[c] = (int)path.size();
         op.msave = (unsigned char)mslot_of[c];
         path.push_back(c);

@@ -107,7 +107,7 @@ struct RqWalk {
   int nvslots = 0, nmslots = 0;
 };
 RqWalk rq_build_walk(int nj, const DevJoint* joints, const std::vector<char>& need, const std::vector<unsigned>& own,
-                     const std::vector<unsigned>& live, int max_proc, int max_ops);
+                     const std::vector<unsigned>& live, int max_proc, int max_ops, int max_slots = RQ_MAXSLOTS);
 
 RqLaunch rq_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, const ColDesc* cols, int sm_count,
                   int max_smem, RqParams* out, const char** why, const RqCost* measured = nullptr);
