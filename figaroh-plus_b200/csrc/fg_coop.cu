@@ -5,7 +5,7 @@
 namespace fg {
 
 static int cq_smem_bytes(int rpl, int nb) {
-  return (int)(((size_t)rpl * nb * GQ_BLK + (size_t)nb * 64 + (size_t)CQ_NW * GQ_SCRATCH + (size_t)nb) * 8);
+  return (int)(((size_t)rpl * nb * GQ_BLK + (size_t)nb * 64 + (size_t)CQ_NW * GQ_SCRATCH + 2 * (size_t)nb) * 8);
 }
 
 int cq_max_p1(int max_smem) {

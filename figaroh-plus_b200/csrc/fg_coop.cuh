@@ -65,9 +65,7 @@ struct CqFrag {
 };
 
 template <int RPL>
-__device__ __forceinline__ void cq_load_frag(CqFrag<RPL>& f, const double* tile, int nb, int k, const double* Tb,
-                                             const GqOffs& o, int lane) {
-  const int cq = lane >> 2, rq = lane & 3;
+__device__ __forceinline__ void cq_load_frag(CqFrag<RPL>& f, const double* tile, int nb, int k, const GqOffs& o) {
   const double* Xk = tile + k * GQ_BLK;
 #pragma unroll
   for (int sl = 0; sl < RPL; ++sl)
@@ -78,15 +76,21 @@ __device__ __forceinline__ void cq_load_frag(CqFrag<RPL>& f, const double* tile,
       f.vb0[sl][nn] = Xk[sl * nb * GQ_BLK + o.ob0[nn]];
       f.vb1[sl][nn] = Xk[sl * nb * GQ_BLK + o.ob1[nn]];
     }
+}
+template <int RPL>
+__device__ __forceinline__ void cq_load_T(CqFrag<RPL>& f, int k, const double* Tb, int lane) {
+  const int cq = lane >> 2, rq = lane & 3;
   const double* TS = Tb + k * 64;
   f.t0 = 2 * rq <= cq ? TS[(2 * rq) * 8 + cq] : 0.0;
   f.t1 = 2 * rq + 1 <= cq ? TS[(2 * rq + 1) * 8 + cq] : 0.0;
 }
 
 // panel k applied to block j of the tile and to R_kj (the trailing update of gq_fold_h)
-template <int RPL>
-__device__ __forceinline__ void cq_update(const CqFrag<RPL>& f, double* tile, int nb, int j, double* Rb, double r0, double r1,
-                                          const GqOffs& o, int lane) {
+// WT: T_k is published after V_k; the first update with a panel waits for it only once Y is under way
+template <int RPL, bool WT>
+__device__ __forceinline__ void cq_update(CqFrag<RPL>& f, double* tile, int nb, int j, double* Rb, double r0, double r1,
+                                          const GqOffs& o, int lane, uint64_t* barT = nullptr, uint32_t parity = 0,
+                                          int k = 0, const double* Tb = nullptr) {
   const int cq = lane >> 2, rq = lane & 3;
   double* Bj = tile + j * GQ_BLK;
   double c0[RPL][4], c1[RPL][4];
@@ -107,6 +111,10 @@ __device__ __forceinline__ void cq_update(const CqFrag<RPL>& f, double* tile, in
     }
   y0 += z0 + r0;
   y1 += z1 + r1;
+  if (WT) {
+    cq_wait(barT, parity);
+    cq_load_T(f, k, Tb, lane);
+  }
   double w0 = 0.0, w1 = 0.0;
   tq_dmma(w0, w1, y0, f.t0);
   tq_dmma(w0, w1, y1, f.t1);
@@ -126,14 +134,15 @@ __device__ __forceinline__ void cq_update(const CqFrag<RPL>& f, double* tile, in
 
 // panel k: Householder factorisation of [R_kk; block k of the tile]; V_k stays in the block, T_k goes to Tb[k]
 template <int RPL>
-__device__ __forceinline__ void cq_panel(double* tile, int nb, int k, double* R, double* Tb, double* scr, const GqOffs& o,
-                                         int lane) {
+// d0, d1: R_kk as loaded by the caller (entries lane, lane + 32), requested before it waited for panel k - 1
+__device__ __forceinline__ void cq_panel(double* tile, int nb, int k, double* R, double d0, double d1, double* Tb, double* scr,
+                                         const GqOffs& o, int lane, uint64_t* barV, uint64_t* barT) {
   double* Rd = R + (size_t)tq_rblk(nb, k, k) * 64;
   double* Xk = tile + k * GQ_BLK;
   double* Rin = scr;
   double* sc = scr + 64;
-  Rin[lane] = __ldcg(Rd + lane);
-  Rin[lane + 32] = __ldcg(Rd + lane + 32);
+  Rin[lane] = d0;
+  Rin[lane + 32] = d1;
   double x[RPL][8];
 #pragma unroll
   for (int sl = 0; sl < RPL; ++sl)
@@ -147,7 +156,7 @@ __device__ __forceinline__ void cq_panel(double* tile, int nb, int k, double* R,
   for (int sl = 0; sl < RPL; ++sl)
 #pragma unroll
     for (int c = 0; c < 8; ++c) Xk[sl * nb * GQ_BLK + tq_idx(c, lane)] = x[sl][c];
-  __syncwarp();
+  cq_publish(barV, lane);  // (fence + __syncwarp inside) the reflectors are out: the others start on Y = R + V^T B
   double vc0[RPL][4], vc1[RPL][4];
 #pragma unroll
   for (int sl = 0; sl < RPL; ++sl)
@@ -157,6 +166,7 @@ __device__ __forceinline__ void cq_panel(double* tile, int nb, int k, double* R,
       vc1[sl][nn] = Xk[sl * nb * GQ_BLK + o.oc1[nn]];
     }
   gq_panel_T<RPL>(vc0, vc1, sc, Tb + k * 64, lane);
+  cq_publish(barT, lane);
 }
 
 template <int RPL>
@@ -168,12 +178,13 @@ cq_accumulate_dense_kernel(const __grid_constant__ CqParams P) {
   double* tile = cq_smem;                               // RPL x nb blocks
   double* Tb = tile + (size_t)RPL * nb * GQ_BLK;     // nb x 64
   double* scr = Tb + (size_t)nb * 64 + (size_t)warp * GQ_SCRATCH;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Tb + (size_t)nb * 64 + (size_t)CQ_NW * GQ_SCRATCH);  // nb of them
+  uint64_t* barsV = reinterpret_cast<uint64_t*>(Tb + (size_t)nb * 64 + (size_t)CQ_NW * GQ_SCRATCH);  // nb: V_k published
+  uint64_t* barsT = barsV + nb;                                                                        // nb: T_k published
   const size_t rsize = (size_t)nb * (nb + 1) / 2 * 64;
   double* R = P.r_all + (size_t)blockIdx.x * rsize;
   if (P.first)
     for (size_t i = threadIdx.x; i < rsize; i += blockDim.x) R[i] = 0.0;
-  for (int i = threadIdx.x; i < nb; i += blockDim.x) rq_mbar_init(bars + i, 1);
+  for (int i = threadIdx.x; i < 2 * nb; i += blockDim.x) rq_mbar_init(barsV + i, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   GqOffs offs;
   gq_make_offs(offs, lane);
@@ -226,36 +237,50 @@ cq_accumulate_dense_kernel(const __grid_constant__ CqParams P) {
       }
     }
     __syncwarp();  // every warp loaded its OWN blocks: nobody waits for anybody here
-    if (warp == 0) {
-      cq_panel<RPL>(tile, nb, 0, R, Tb, scr, offs, lane);
-      cq_publish(bars, lane);
-    }
     const int cq = lane >> 2, rq = lane & 3;
+    if (warp == 0) {
+      const double* Rd = R;
+      cq_panel<RPL>(tile, nb, 0, R, __ldcg(Rd + lane), __ldcg(Rd + lane + 32), Tb, scr, offs, lane, barsV, barsT);
+    }
     for (int k = 0; k + 1 < nb; ++k) {
       int j = k + 1 + ((warp - (k + 1)) % CQ_NW + CQ_NW) % CQ_NW;  // my first block to the right of k
       if (j >= nb) continue;
-      cq_wait(bars + k, parity);
-      CqFrag<RPL> f;
-      cq_load_frag(f, tile, nb, k, Tb, offs, lane);
+      // what the first update needs from L2 is requested BEFORE the wait (R_kj; for the owner of k + 1 also R_jj)
       double* Rb = R + (size_t)tq_rblk(nb, k, j) * 64;
       double r0 = __ldcg(Rb + (2 * rq) * 8 + cq), r1 = __ldcg(Rb + (2 * rq + 1) * 8 + cq);
+      double d0 = 0.0, d1 = 0.0;
+      if (j == k + 1) {
+        const double* Rd = R + (size_t)tq_rblk(nb, j, j) * 64;
+        d0 = __ldcg(Rd + lane);
+        d1 = __ldcg(Rd + lane + 32);
+      }
+      cq_wait(barsV + k, parity);
+      CqFrag<RPL> f;
+      cq_load_frag(f, tile, nb, k, offs);
       if (j == k + 1) {  // look-ahead: this block first, then its panel, then the rest of panel k's updates
-        cq_update(f, tile, nb, j, Rb, r0, r1, offs, lane);
+        cq_update<RPL, true>(f, tile, nb, j, Rb, r0, r1, offs, lane, barsT + k, parity, k, Tb);
         __syncwarp();
-        cq_panel<RPL>(tile, nb, j, R, Tb, scr, offs, lane);
-        cq_publish(bars + j, lane);
+        cq_panel<RPL>(tile, nb, j, R, d0, d1, Tb, scr, offs, lane, barsV + j, barsT + j);
         j += CQ_NW;
         if (j >= nb) continue;
-        cq_load_frag(f, tile, nb, k, Tb, offs, lane);
+        cq_load_frag(f, tile, nb, k, offs);
+        cq_load_T(f, k, Tb, lane);
         Rb = R + (size_t)tq_rblk(nb, k, j) * 64;
         r0 = __ldcg(Rb + (2 * rq) * 8 + cq);
         r1 = __ldcg(Rb + (2 * rq + 1) * 8 + cq);
+      } else {
+        double* Rn = Rb + (size_t)CQ_NW * 64;
+        double nr0 = 0.0, nr1 = 0.0;
+        if (j + CQ_NW < nb) { nr0 = __ldcg(Rn + (2 * rq) * 8 + cq); nr1 = __ldcg(Rn + (2 * rq + 1) * 8 + cq); }
+        cq_update<RPL, true>(f, tile, nb, j, Rb, r0, r1, offs, lane, barsT + k, parity, k, Tb);
+        Rb = Rn; r0 = nr0; r1 = nr1;
+        j += CQ_NW;
       }
       for (; j < nb; j += CQ_NW) {
         double nr0 = 0.0, nr1 = 0.0;
         double* Rn = Rb + (size_t)CQ_NW * 64;  // blocks of one block row are consecutive
         if (j + CQ_NW < nb) { nr0 = __ldcg(Rn + (2 * rq) * 8 + cq); nr1 = __ldcg(Rn + (2 * rq + 1) * 8 + cq); }
-        cq_update(f, tile, nb, j, Rb, r0, r1, offs, lane);
+        cq_update<RPL, false>(f, tile, nb, j, Rb, r0, r1, offs, lane);
         Rb = Rn; r0 = nr0; r1 = nr1;
       }
     }
