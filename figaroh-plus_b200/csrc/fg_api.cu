@@ -88,6 +88,7 @@ struct fg_state {
   double* d_ring = nullptr;     // generation 5: ring of regressor tiles + its control words (L2 resident)
   int64_t ring_cap = 0;         // in doubles
   const void* ring_plan = nullptr;  // the plan whose tile layout the ring currently holds (padding columns stay zero)
+  int cq_grid = 0;              // CTAs (= per-CTA factors in d_gR) of the running cooperative-TSQR sequence
   unsigned* h_rq_err = nullptr; // pinned: error flag of the last generation-5 launch
   double* d_A = nullptr;        // (p1 x p1) dense scratch of the small stage
   double* d_Re = nullptr;       // reduced factor (dense, (nk+1)^2)
@@ -1073,7 +1074,7 @@ static int accumulate_samples_dev(fg_state* s, fg_model* m, const fg_regressor_c
       int ms_full = 0, cols_chk = 0;
       rc = fg_regressor_shape(m, &cfull, &ms_full, &cols_chk);
       if (rc) return rc;
-      if (ms_full == ms && !(phase != (FG_PHASE_FIRST | FG_PHASE_LAST))) {
+      if (ms_full == ms) {
         const int64_t chunk = std::max<int64_t>(32, std::min<int64_t>(N, (int64_t)(768ll << 20) / ((int64_t)ms * ncols_full * 8)));
         const int64_t w_doubles = chunk * ms * ncols_full;
         if (w_doubles > s->ring_cap) {
@@ -1083,10 +1084,17 @@ static int accumulate_samples_dev(fg_state* s, fg_model* m, const fg_regressor_c
           s->ring_cap = w_doubles;
         }
         s->ring_plan = nullptr;
-        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((chunk * ms + 63) / 64, m->sm_count));
+        // a sequence of calls (FIRST ... LAST: the chunks of the host-buffer path) shares the per-CTA factors
+        if (phase & FG_PHASE_FIRST) {
+          s->cq_grid = (int)std::max<int64_t>(1, std::min<int64_t>((std::min(chunk, N) * ms + 63) / 64, m->sm_count));
+          rc = ensure_gR(s, (int64_t)s->cq_grid * cq_r_doubles(pl->P.p1));
+          if (rc) return rc;
+        } else if (s->cq_grid <= 0 || s->gR_cap < (int64_t)s->cq_grid * cq_r_doubles(pl->P.p1)) {
+          return set_err(FG_ERR_INVALID, "internal: continued launch without a first one");
+        }
+        const int grid = s->cq_grid;
+        if (chunkable) *chunkable = true;
         rc = ensure_parts(s, grid + 1);
-        if (rc) return rc;
-        rc = ensure_gR(s, (int64_t)grid * cq_r_doubles(pl->P.p1));
         if (rc) return rc;
         rc = timing_begin(s, st);
         if (rc) return rc;
@@ -1098,17 +1106,17 @@ static int accumulate_samples_dev(fg_state* s, fg_model* m, const fg_regressor_c
           ca.W = s->d_ring; ca.ldw = ncols_full; ca.colsel = pl->ptrs.fullcol;
           ca.tau = tau ? tau + i0 : nullptr; ca.tau_blk = n; ca.tau_ld = ld_tau;
           ca.rows = n * ms; ca.p1 = pl->P.p1;
-          ca.first = i0 == 0; ca.last = i0 + n >= N;
+          ca.first = (phase & FG_PHASE_FIRST) && i0 == 0;
+          ca.last = (phase & FG_PHASE_LAST) && i0 + n >= N;
           cudaError_t ce = cq_launch_dense(ca, s->d_gR, s->d_parts, grid, m->max_smem, st);
           if (ce != cudaSuccess) return set_err(FG_ERR_CUDA, "cooperative dense kernel failed: %s", cudaGetErrorString(ce));
           FG_LAUNCHED();
         }
         rc = timing_end(s, st);
         if (rc) return rc;
-        rc = merge_parts_into_state(s, grid, m->max_smem, st);
-        if (rc) return rc;
         s->rows += N * ms;
-        return FG_OK;
+        if (!(phase & FG_PHASE_LAST)) return FG_OK;
+        return merge_parts_into_state(s, grid, m->max_smem, st);
       }
     }
   }
