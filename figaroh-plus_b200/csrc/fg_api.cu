@@ -781,12 +781,16 @@ extern "C" int fg_state_accumulate_dense(fg_state* s, const double* W, int64_t l
       if (rc) return rc;
       CqArgs ca;
       ca.W = W; ca.ldw = ldw; ca.tau = tau; ca.rows = rows; ca.p1 = s->p1;
-      cudaError_t e = cq_launch_dense(ca, s->d_gR, s->d_parts, grid, max_smem, st);
+      cudaError_t e = cq_launch_dense(ca, s->d_gR, grid, max_smem, st);
       rc = timing_end(s, st);
       if (rc) return rc;
       if (e != cudaSuccess) return set_err(FG_ERR_CUDA, "cooperative dense kernel failed: %s", cudaGetErrorString(e));
       FG_LAUNCHED();
-      rc = merge_parts_into_state(s, grid, max_smem, st);
+      int nl = 0;
+      e = cq_reduce_export(s->d_gR, grid, s->p1, s->d_parts, max_smem, &nl, st);
+      if (e != cudaSuccess) return set_err(FG_ERR_CUDA, "cooperative merge failed: %s", cudaGetErrorString(e));
+      for (int i = 0; i < nl; ++i) FG_LAUNCHED();
+      rc = merge_parts_into_state(s, 1, max_smem, st);
       if (rc) return rc;
       s->rows += rows;
       return FG_OK;
@@ -1107,8 +1111,7 @@ static int accumulate_samples_dev(fg_state* s, fg_model* m, const fg_regressor_c
           ca.tau = tau ? tau + i0 : nullptr; ca.tau_blk = n; ca.tau_ld = ld_tau;
           ca.rows = n * ms; ca.p1 = pl->P.p1;
           ca.first = (phase & FG_PHASE_FIRST) && i0 == 0;
-          ca.last = (phase & FG_PHASE_LAST) && i0 + n >= N;
-          cudaError_t ce = cq_launch_dense(ca, s->d_gR, s->d_parts, grid, m->max_smem, st);
+          cudaError_t ce = cq_launch_dense(ca, s->d_gR, grid, m->max_smem, st);
           if (ce != cudaSuccess) return set_err(FG_ERR_CUDA, "cooperative dense kernel failed: %s", cudaGetErrorString(ce));
           FG_LAUNCHED();
         }
@@ -1116,7 +1119,11 @@ static int accumulate_samples_dev(fg_state* s, fg_model* m, const fg_regressor_c
         if (rc) return rc;
         s->rows += N * ms;
         if (!(phase & FG_PHASE_LAST)) return FG_OK;
-        return merge_parts_into_state(s, grid, m->max_smem, st);
+        int nl = 0;
+        cudaError_t ce = cq_reduce_export(s->d_gR, grid, pl->P.p1, s->d_parts, m->max_smem, &nl, st);
+        if (ce != cudaSuccess) return set_err(FG_ERR_CUDA, "cooperative merge failed: %s", cudaGetErrorString(ce));
+        for (int i = 0; i < nl; ++i) FG_LAUNCHED();
+        return merge_parts_into_state(s, 1, m->max_smem, st);
       }
     }
   }

@@ -1,4 +1,6 @@
 // fg_coop.cu - host side of the cooperative blocked TSQR (fg_coop.cuh).
+#include <cstring>
+
 #include "fg_coop.cuh"
 #include "fg_coop.h"
 
@@ -19,13 +21,7 @@ int64_t cq_r_doubles(int p1) {
   return nb * (nb + 1) / 2 * 64;
 }
 
-cudaError_t cq_launch_dense(const CqArgs& a, double* r_all, double* parts, int grid, int max_smem, cudaStream_t st) {
-  CqParams P;
-  P.W = a.W; P.ldw = a.ldw; P.colsel = a.colsel; P.tau = a.tau; P.rows = a.rows; P.p1 = a.p1;
-  P.nb = (a.p1 + 7) / 8;
-  P.r_all = r_all; P.parts = parts;
-  P.tau_blk = a.tau_blk; P.tau_ld = a.tau_ld;
-  P.first = a.first ? 1 : 0; P.last = a.last ? 1 : 0;
+static cudaError_t cq_launch(const CqParams& P, int grid, int max_smem, cudaStream_t st) {
   const int rpl = cq_smem_bytes(2, P.nb) <= max_smem ? 2 : 1;
   const int smem = cq_smem_bytes(rpl, P.nb);
   if (smem > max_smem) return cudaErrorInvalidValue;
@@ -39,6 +35,33 @@ cudaError_t cq_launch_dense(const CqArgs& a, double* r_all, double* parts, int g
     if (e != cudaSuccess) return e;
     cq_accumulate_dense_kernel<1><<<grid, CQ_NW * 32, smem, st>>>(P);
   }
+  return cudaGetLastError();
+}
+
+cudaError_t cq_launch_dense(const CqArgs& a, double* r_all, int grid, int max_smem, cudaStream_t st) {
+  CqParams P;
+  memset(&P, 0, sizeof P);
+  P.W = a.W; P.ldw = a.ldw; P.colsel = a.colsel; P.tau = a.tau; P.rows = a.rows; P.p1 = a.p1;
+  P.nb = (a.p1 + 7) / 8;
+  P.r_all = r_all;
+  P.tau_blk = a.tau_blk; P.tau_ld = a.tau_ld;
+  P.first = a.first ? 1 : 0;
+  return cq_launch(P, grid, max_smem, st);
+}
+
+cudaError_t cq_reduce_export(double* r_all, int grid, int p1, double* part_out, int max_smem, int* launches, cudaStream_t st) {
+  CqParams P;
+  memset(&P, 0, sizeof P);
+  P.p1 = p1; P.nb = (p1 + 7) / 8; P.r_all = r_all; P.nfac = grid;
+  for (int stride = 1; stride < grid; stride *= 2) {
+    P.merge_stride = stride;
+    const int pairs = (grid + 2 * stride - 1) / (2 * stride);
+    cudaError_t e = cq_launch(P, pairs, max_smem, st);
+    if (e != cudaSuccess) return e;
+    if (launches) ++*launches;
+  }
+  cq_export_kernel<<<32, 256, 0, st>>>(r_all, p1, P.nb, part_out);
+  if (launches) ++*launches;
   return cudaGetLastError();
 }
 

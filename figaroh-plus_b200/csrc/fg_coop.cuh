@@ -40,9 +40,10 @@ struct CqParams {
   int p1;                 // columns incl. the rhs
   int nb;                 // 8-column blocks
   double* r_all;          // grid x nb (nb + 1) / 2 x 64 doubles
-  double* parts;          // grid x part_doubles(p1)
   int64_t tau_blk, tau_ld;  // rhs of row r at tau[(r / tau_blk) * tau_ld + r % tau_blk] (tau_blk = 0: tau[r])
-  int first, last;        // first launch of a sequence zeroes the factors, the last one writes the parts
+  int first;              // first launch of a sequence zeroes the factors
+  // merge mode (merge_stride > 0): CTA b folds factor (2b + 1) * merge_stride into factor 2b * merge_stride; W / tau unused
+  int merge_stride, nfac;
 };
 
 // "panel k is published": one mbarrier per panel (arrival count 1, the owner's lane 0), phase = parity of the CTA's
@@ -182,7 +183,7 @@ cq_accumulate_dense_kernel(const __grid_constant__ CqParams P) {
   uint64_t* barsT = barsV + nb;                                                                        // nb: T_k published
   const size_t rsize = (size_t)nb * (nb + 1) / 2 * 64;
   double* R = P.r_all + (size_t)blockIdx.x * rsize;
-  if (P.first)
+  if (P.first && P.merge_stride == 0)
     for (size_t i = threadIdx.x; i < rsize; i += blockDim.x) R[i] = 0.0;
   for (int i = threadIdx.x; i < 2 * nb; i += blockDim.x) rq_mbar_init(barsV + i, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -190,9 +191,19 @@ cq_accumulate_dense_kernel(const __grid_constant__ CqParams P) {
   gq_make_offs(offs, lane);
   const int ncol = nb * 8;
   constexpr int CQ_TR = 32 * RPL;
-  const int64_t ntiles = (P.rows + CQ_TR - 1) / CQ_TR;
+  const bool merge = P.merge_stride > 0;
+  const double* Rs = nullptr;  // merge mode: the factor that is folded into R, 64 of its rows per tile
+  if (merge) {
+    const int dst = 2 * (int)blockIdx.x * P.merge_stride, src = dst + P.merge_stride;
+    if (src >= P.nfac) return;
+    R = P.r_all + (size_t)dst * rsize;
+    Rs = P.r_all + (size_t)src * rsize;
+  }
+  const int64_t ntiles = merge ? (p1 + CQ_TR - 1) / CQ_TR : (P.rows + CQ_TR - 1) / CQ_TR;
   uint32_t parity = 0;
-  for (int64_t tl = blockIdx.x; tl < ntiles; tl += gridDim.x, parity ^= 1u) {
+  for (int64_t tl = merge ? 0 : blockIdx.x; tl < ntiles; tl += merge ? 1 : gridDim.x, parity ^= 1u) {
+    // rows 64 t .. of an upper-triangular factor are zero left of column 64 t: the panels start there
+    const int k0 = merge ? (int)(tl * CQ_TR / 8) : 0;
     __syncthreads();  // the previous tile is finished with by every warp (and R is zeroed before the first one)
     // ---- the tile: rows row0 .. row0 + 32 RPL - 1 of [W(:, colsel) | tau], zero padded.  One warp instruction moves one
     // column block x 4 rows (lane = (column, row mod 4): 64-byte row segments from HBM, conflict-free stores); eight
@@ -201,6 +212,19 @@ cq_accumulate_dense_kernel(const __grid_constant__ CqParams P) {
     {
       const int cb = lane >> 2, rr = lane & 3;
       for (int b = warp; b < nb; b += CQ_NW) {
+        if (merge) {
+          if (b < k0) continue;
+          double* dstb = tile + (size_t)b * GQ_BLK;
+#pragma unroll 4
+          for (int u = 0; u < CQ_TR / 4; ++u) {
+            const int r = 4 * u + rr;
+            const int sr = (int)row0 + r, br = sr >> 3;
+            double val = 0.0;
+            if (sr < p1 && b >= br) val = __ldcg(Rs + (size_t)tq_rblk(nb, br, b) * 64 + (sr & 7) * 8 + cb);
+            dstb[(size_t)(r >> 5) * nb * GQ_BLK + tq_idx(cb, r & 31)] = val;
+          }
+          continue;
+        }
         const int c = b * 8 + cb;
         const double* src = nullptr;
         int64_t stride = 0;
@@ -224,7 +248,7 @@ cq_accumulate_dense_kernel(const __grid_constant__ CqParams P) {
       }
       // next tile of this CTA towards L2 while this one is folded
       const int64_t nrow0 = (tl + gridDim.x) * CQ_TR;
-      if (nrow0 < P.rows) {
+      if (!merge && nrow0 < P.rows) {
         const int64_t row_bytes = (int64_t)P.ldw * 8;
         const int lines = (int)((row_bytes + 127) / 128) + 1;
         for (int e = threadIdx.x; e < CQ_TR * lines; e += blockDim.x) {
@@ -238,11 +262,11 @@ cq_accumulate_dense_kernel(const __grid_constant__ CqParams P) {
     }
     __syncwarp();  // every warp loaded its OWN blocks: nobody waits for anybody here
     const int cq = lane >> 2, rq = lane & 3;
-    if (warp == 0) {
-      const double* Rd = R;
-      cq_panel<RPL>(tile, nb, 0, R, __ldcg(Rd + lane), __ldcg(Rd + lane + 32), Tb, scr, offs, lane, barsV, barsT);
+    if (warp == k0 % CQ_NW) {
+      const double* Rd = R + (size_t)tq_rblk(nb, k0, k0) * 64;
+      cq_panel<RPL>(tile, nb, k0, R, __ldcg(Rd + lane), __ldcg(Rd + lane + 32), Tb, scr, offs, lane, barsV + k0, barsT + k0);
     }
-    for (int k = 0; k + 1 < nb; ++k) {
+    for (int k = k0; k + 1 < nb; ++k) {
       int j = k + 1 + ((warp - (k + 1)) % CQ_NW + CQ_NW) % CQ_NW;  // my first block to the right of k
       if (j >= nb) continue;
       // what the first update needs from L2 is requested BEFORE the wait (R_kj; for the owner of k + 1 also R_jj)
@@ -285,19 +309,19 @@ cq_accumulate_dense_kernel(const __grid_constant__ CqParams P) {
       }
     }
   }
-  __syncthreads();
-  if (!P.last) return;
-  // ---- packed upper triangle + squared column norms (the part format of merge_pairs / wide merge)
-  double* out = P.parts + (size_t)blockIdx.x * part_doubles(p1);
+}
+
+// factor 0 of r_all as a packed part: upper triangle + squared column norms (the format of merge_pairs / fg_state)
+__global__ void cq_export_kernel(const double* __restrict__ R, int p1, int nb, double* __restrict__ out) {
   const int ntri = p1 * (p1 + 1) / 2;
-  for (int idx = threadIdx.x; idx < p1 * p1; idx += blockDim.x) {
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < p1 * p1; idx += gridDim.x * blockDim.x) {
     const int r = idx / p1, c = idx - r * p1;
-    if (c >= r) out[tri_off(r, p1) + c - r] = __ldcg(R + (size_t)tq_rblk(nb, r >> 3, c >> 3) * 64 + (r & 7) * 8 + (c & 7));
+    if (c >= r) out[tri_off(r, p1) + c - r] = R[(size_t)tq_rblk(nb, r >> 3, c >> 3) * 64 + (r & 7) * 8 + (c & 7)];
   }
-  for (int c = threadIdx.x; c < p1; c += blockDim.x) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < p1; c += gridDim.x * blockDim.x) {
     double sacc = 0.0;
     for (int r = 0; r <= c; ++r) {
-      const double x = __ldcg(R + (size_t)tq_rblk(nb, r >> 3, c >> 3) * 64 + (r & 7) * 8 + (c & 7));
+      const double x = R[(size_t)tq_rblk(nb, r >> 3, c >> 3) * 64 + (r & 7) * 8 + (c & 7)];
       sacc = fma(x, x, sacc);
     }
     out[ntri + c] = sacc;

@@ -18,10 +18,13 @@ struct CqArgs {
   int64_t tau_blk = 0, tau_ld = 0;  // rhs of row r at tau[(r / tau_blk) * tau_ld + r % tau_blk]; tau_blk = 0: tau[r]
   int64_t rows = 0;
   int p1 = 0;
-  bool first = true, last = true;   // a sequence of launches over row chunks shares the per-CTA factors
+  bool first = true;           // a sequence of launches over row chunks shares the per-CTA factors: the first one zeroes them
 };
-// CTA b of `grid` folds tiles b, b + grid, ... into its factor r_all + b * cq_r_doubles(p1); the last launch of a
-// sequence writes parts[b] (packed triangle + squared column norms).
-cudaError_t cq_launch_dense(const CqArgs& a, double* r_all, double* parts, int grid, int max_smem, cudaStream_t st);
+// CTA b of `grid` folds tiles b, b + grid, ... into its factor r_all + b * cq_r_doubles(p1).
+cudaError_t cq_launch_dense(const CqArgs& a, double* r_all, int grid, int max_smem, cudaStream_t st);
+// after the last launch of a sequence: pairwise tree over the `grid` factors (log2 launches of the same kernel: 64
+// rows of the right-hand factor per tile, panels starting at the tile's first non-zero column), then factor 0 as one
+// packed part (upper triangle + squared column norms) in part_out.  *launches += kernels launched.
+cudaError_t cq_reduce_export(double* r_all, int grid, int p1, double* part_out, int max_smem, int* launches, cudaStream_t st);
 
 }  // namespace fg
