@@ -1456,6 +1456,21 @@ static int run_small_qr(double* A, int mrows, int n, const int* d_ext, cudaStrea
   int sm_count, max_smem;
   int rc = device_limits(&sm_count, &max_smem);
   if (rc) return rc;
+  if (n > 128 && scratch != nullptr && n <= cq_max_p1(max_smem)) {
+    // cooperative blocked TSQR with one CTA (fg_coop.cuh); scratch: one part for the result + two for the block factor
+    CqArgs ca;
+    ca.W = A; ca.ldw = n; ca.rhs_in_w = true; ca.rows = mrows; ca.p1 = n;
+    double* Rblk = scratch + part_doubles(n);
+    cudaError_t e = cq_launch_dense(ca, Rblk, 1, max_smem, st);
+    int nl = 1;
+    if (e == cudaSuccess) e = cq_reduce_export(Rblk, 1, n, scratch, max_smem, &nl, st);
+    if (e != cudaSuccess) return set_err(FG_ERR_CUDA, "small stage (cooperative) failed: %s", cudaGetErrorString(e));
+    for (int i = 0; i < nl; ++i) FG_LAUNCHED();
+    tri_to_square_kernel<<<64, 256, 0, st>>>(scratch, n, A);
+    FG_CUDA(cudaGetLastError());
+    FG_LAUNCHED();
+    return FG_OK;
+  }
   if (n > 128 && scratch != nullptr && wide_dense_tile_rows(n) > 0) {
     cudaError_t e = wide_launch_dense(A, n, A + (n - 1), n, mrows, n, scratch, 1, st);
     if (e != cudaSuccess) return set_err(FG_ERR_CUDA, "small stage (wide) failed: %s", cudaGetErrorString(e));
@@ -1493,7 +1508,7 @@ extern "C" int fg_state_reduce(fg_state* s, const int32_t* keep, int32_t nk, dou
   gather_cols_kernel<<<64, 256, 0, st>>>(s->d_part, p1, 1, s->d_idx, p1, n, s->d_A);
   FG_CUDA(cudaGetLastError());
   FG_LAUNCHED();
-  int rc = ensure_parts(s, 2);
+  int rc = ensure_parts(s, 3);
   if (rc) return rc;
   rc = run_small_qr(s->d_A, p1, n, s->d_idx + n, st, s->d_parts);
   if (rc) return rc;
@@ -1634,7 +1649,7 @@ extern "C" int fg_state_regroup_solve(fg_state* s, const int32_t* base, int32_t 
   gather_cols_kernel<<<64, 256, 0, st>>>(s->d_Re, n, 0, s->d_idx, n, n, s->d_A);
   FG_CUDA(cudaGetLastError());
   FG_LAUNCHED();
-  int rc = ensure_parts(s, 2);
+  int rc = ensure_parts(s, 3);
   if (rc) return rc;
   rc = run_small_qr(s->d_A, n, n, s->d_idx + n, st, s->d_parts);
   if (rc) return rc;

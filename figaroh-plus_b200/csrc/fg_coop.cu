@@ -46,6 +46,7 @@ cudaError_t cq_launch_dense(const CqArgs& a, double* r_all, int grid, int max_sm
   P.r_all = r_all;
   P.tau_blk = a.tau_blk; P.tau_ld = a.tau_ld;
   P.first = a.first ? 1 : 0;
+  P.rhs_in_w = a.rhs_in_w ? 1 : 0;
   return cq_launch(P, grid, max_smem, st);
 }
 

@@ -44,6 +44,7 @@ struct CqParams {
   int first;              // first launch of a sequence zeroes the factors
   // merge mode (merge_stride > 0): CTA b folds factor (2b + 1) * merge_stride into factor 2b * merge_stride; W / tau unused
   int merge_stride, nfac;
+  int rhs_in_w;           // all p1 columns come from W (the small stage: the rhs is the last column of the matrix)
 };
 
 // "panel k is published": one mbarrier per panel (arrival count 1, the owner's lane 0), phase = parity of the CTA's
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(CQ_NW * 32, 1)
 cq_accumulate_dense_kernel(const __grid_constant__ CqParams P) {
   extern __shared__ __align__(16) double cq_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nb = P.nb, p1 = P.p1, p = p1 - 1;  // the last column is the rhs (zero without tau)
+  const int nb = P.nb, p1 = P.p1, p = P.rhs_in_w ? p1 : p1 - 1;  // the last column is the rhs (zero without tau)
   double* tile = cq_smem;                               // RPL x nb blocks
   double* Tb = tile + (size_t)RPL * nb * GQ_BLK;     // nb x 64
   double* scr = Tb + (size_t)nb * 64 + (size_t)warp * GQ_SCRATCH;

@@ -18,6 +18,7 @@ struct CqArgs {
   int64_t tau_blk = 0, tau_ld = 0;  // rhs of row r at tau[(r / tau_blk) * tau_ld + r % tau_blk]; tau_blk = 0: tau[r]
   int64_t rows = 0;
   int p1 = 0;
+  bool rhs_in_w = false;       // all p1 columns (incl. the rhs) are columns 0 .. p1 - 1 of W
   bool first = true;           // a sequence of launches over row chunks shares the per-CTA factors: the first one zeroes them
 };
 // CTA b of `grid` folds tiles b, b + grid, ... into its factor r_all + b * cq_r_doubles(p1).
