@@ -525,9 +525,10 @@ def main():
         kernel = ("rq_accumulate_kernel (producer SMs walk the kinematic tree once per 32-sample tile and write every row group's "
                   "tile into an L2-resident ring; consumer SMs: one Householder TSQR stream per (warp, row group), cp.async.bulk "
                   "tile refill, 8-column panels, DMMA trailing updates)") if plan.get("ring_kernel") else \
-                 ("wide_accumulate_samples_kernel (CTA-wide register tile, one column per thread and slot, Householder column "
-                  "steps through one named barrier, factor row streamed from L2; forward kinematics by a thread-per-sample "
-                  "pre-kernel, staged per tile by cp.async.bulk)")
+                 ("matz_kernel + cq_accumulate_dense_kernel (kernel (1) materialises W a chunk of samples at a time: one sample "
+                  "per lane, one walk of the tree for all row blocks, sector-aligned 14-column patches; kernel (2) is a "
+                  "cooperative blocked Householder TSQR: 64-row tiles in shared memory, column blocks owned by warps, panel "
+                  "look-ahead, DMMA trailing updates, factor in an L2-resident scratch); timed together")
         diag = np.asarray(sol.diag[:len(sol.keep)])
         base_diag = diag[diag > 1e-8]
         line = {
