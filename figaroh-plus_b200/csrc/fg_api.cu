@@ -43,6 +43,16 @@ static std::atomic<long long> g_launches{0};
 #define FG_LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
 
 // ------------------------------------------------------------------------------------ objects
+// Row blocks with the same set of structurally non-zero columns (cooperative path): blocks = positions in the
+// materialised W, d_colsel = the group's columns as indices into the full W, d_colmap = local column -> column of group 0
+// (the group that sees every column), both with the rhs as last entry (d_colsel[p1-1] unused).
+struct CqGroup {
+  std::vector<int> blocks;
+  int p1 = 0;
+  int* d_colsel = nullptr;
+  int* d_colmap = nullptr;
+};
+
 struct DevPlan {
   Plan P;
   std::vector<ColDesc> cols;
@@ -50,6 +60,9 @@ struct DevPlan {
   std::vector<int> nact, fullcol;
   void* d_blob = nullptr;  // one allocation holding everything
   DevPlanPtrs ptrs{};
+  // row-block groups of the cooperative path (build_cq_groups)
+  bool cqg_built = false;
+  std::vector<CqGroup> cqg;
   // materialising kernel, second version (fg_matz.cuh)
   bool matz_tried = false;
   MatzPlan matz;
@@ -60,7 +73,8 @@ struct DevPlan {
   RqLaunch rql;
   std::unique_ptr<RqParams> rq;
   void* d_rq_tab = nullptr;
-  ~DevPlan() { if (d_blob) cudaFree(d_blob); if (d_rq_tab) cudaFree(d_rq_tab); if (d_matz_tab) cudaFree(d_matz_tab); }
+  ~DevPlan() { if (d_blob) cudaFree(d_blob); if (d_rq_tab) cudaFree(d_rq_tab); if (d_matz_tab) cudaFree(d_matz_tab);
+    for (auto& g : cqg) { if (g.d_colsel) cudaFree(g.d_colsel); if (g.d_colmap) cudaFree(g.d_colmap); } }
 };
 
 struct fg_model {
@@ -1037,6 +1051,75 @@ static int launch_rq(fg_state* s, fg_model* m, DevPlan* pl, const double* q, con
   return merge_parts_into_state(s, 1, m->max_smem, st);
 }
 
+static int build_cq_groups(DevPlan* pl) {
+  const int ms = pl->P.ms, ncols = pl->P.ncols;
+  std::vector<std::vector<char>> mask(ms, std::vector<char>(ncols, 1));
+  bool split_ok = ms <= 32 && getenv("FG_CQ_NOSPLIT") == nullptr;
+  for (int g = 0; g < ms && split_ok; ++g) {
+    if (pl->rows[g].rowblock != g) split_ok = false;  // tau rows and W row blocks must line up
+    const double* S = pl->rows[g].S;
+    const bool no_ang = S[3] == 0.0 && S[4] == 0.0 && S[5] == 0.0;
+    for (int c = 0; c < ncols; ++c) {
+      const ColDesc& cd = pl->cols[c];
+      bool nz = true;
+      if (cd.kind == COL_INERTIAL) nz = ((col_ancmask(cd) >> g) & 1ull) && !(cd.k >= 4 && no_ang);
+      else if (cd.kind == COL_EXTRA) nz = cd.grp == -1 || cd.grp == g;
+      else if (cd.kind == COL_COUPLING) nz = pl->rows[g].rowblock == 4 || pl->rows[g].rowblock == 5;
+      mask[g][c] = nz ? 1 : 0;
+    }
+  }
+  std::vector<int> grp_of(ms, 0);
+  std::vector<int> rep;  // representative row block of every group
+  if (split_ok) {
+    for (int g = 0; g < ms; ++g) {
+      int k = 0;
+      for (; k < (int)rep.size(); ++k)
+        if (mask[rep[k]] == mask[g]) break;
+      if (k == (int)rep.size()) rep.push_back(g);
+      grp_of[g] = k;
+    }
+    // group 0 must see every column; a narrower group must save at least a quarter of the columns to pay for itself
+    int full = -1;
+    for (int k = 0; k < (int)rep.size(); ++k)
+      if (std::count(mask[rep[k]].begin(), mask[rep[k]].end(), 1) == ncols) full = k;
+    if (full < 0) split_ok = false;
+    else {
+      for (int k = 0; k < (int)rep.size(); ++k)
+        if (k != full && std::count(mask[rep[k]].begin(), mask[rep[k]].end(), 1) * 4 > ncols * 3)
+          for (int g = 0; g < ms; ++g)
+            if (grp_of[g] == k) grp_of[g] = full;
+      std::vector<int> order{full};
+      for (int k = 0; k < (int)rep.size(); ++k)
+        if (k != full && std::count(grp_of.begin(), grp_of.end(), k) > 0) order.push_back(k);
+      std::vector<int> renum(rep.size(), -1);
+      for (size_t i = 0; i < order.size(); ++i) renum[order[i]] = (int)i;
+      std::vector<int> nrep(order.size());
+      for (size_t i = 0; i < order.size(); ++i) nrep[i] = rep[order[i]];
+      for (int g = 0; g < ms; ++g) grp_of[g] = renum[grp_of[g]];
+      rep = nrep;
+    }
+  }
+  if (!split_ok) { rep.assign(1, 0); std::fill(grp_of.begin(), grp_of.end(), 0); for (auto& v : mask[0]) v = 1; }
+  pl->cqg.assign(rep.size(), CqGroup());
+  for (size_t k = 0; k < rep.size(); ++k) {
+    CqGroup& G = pl->cqg[k];
+    for (int g = 0; g < ms; ++g)
+      if (grp_of[g] == (int)k) G.blocks.push_back(pl->rows[g].rowblock);
+    std::sort(G.blocks.begin(), G.blocks.end());
+    std::vector<int> colsel, colmap;
+    for (int c = 0; c < ncols; ++c)
+      if (k == 0 || mask[rep[k]][c]) { colsel.push_back(pl->fullcol[c]); colmap.push_back(c); }
+    colsel.push_back(0);
+    colmap.push_back(ncols);  // rhs
+    G.p1 = (int)colsel.size();
+    FG_CUDA(cudaMalloc(&G.d_colsel, sizeof(int) * colsel.size()));
+    FG_CUDA(cudaMalloc(&G.d_colmap, sizeof(int) * colmap.size()));
+    FG_CUDA(cudaMemcpy(G.d_colsel, colsel.data(), sizeof(int) * colsel.size(), cudaMemcpyHostToDevice));
+    FG_CUDA(cudaMemcpy(G.d_colmap, colmap.data(), sizeof(int) * colmap.size(), cudaMemcpyHostToDevice));
+  }
+  return FG_OK;
+}
+
 static int accumulate_samples_dev(fg_state* s, fg_model* m, const fg_regressor_cfg* cfg, const double* q,
                                   const double* v, const double* a, const double* tau, int64_t ld_tau, int64_t N,
                                   cudaStream_t st, int phase = FG_PHASE_FIRST | FG_PHASE_LAST, bool* chunkable = nullptr) {
@@ -1079,6 +1162,16 @@ static int accumulate_samples_dev(fg_state* s, fg_model* m, const fg_regressor_c
       rc = fg_regressor_shape(m, &cfull, &ms_full, &cols_chk);
       if (rc) return rc;
       if (ms_full == ms) {
+        // Row blocks that see the same set of columns form a group with its own (narrower) problem: the three force
+        // rows of a free-flyer never see the inertia-tensor columns (133 of Talos' 331 columns).  The widest group
+        // must see every column; the others are folded into its factor at the end.
+        if (!pl->cqg_built) {
+          pl->cqg_built = true;
+          rc = build_cq_groups(pl);
+          if (rc) return rc;
+        }
+        const std::vector<CqGroup>& G = pl->cqg;
+        const int ng = (int)G.size();
         const int64_t chunk = std::max<int64_t>(32, std::min<int64_t>(N, (int64_t)(768ll << 20) / ((int64_t)ms * ncols_full * 8)));
         const int64_t w_doubles = chunk * ms * ncols_full;
         if (w_doubles > s->ring_cap) {
@@ -1089,16 +1182,20 @@ static int accumulate_samples_dev(fg_state* s, fg_model* m, const fg_regressor_c
         }
         s->ring_plan = nullptr;
         // a sequence of calls (FIRST ... LAST: the chunks of the host-buffer path) shares the per-CTA factors
+        std::vector<int64_t> roff(ng + 1, 0);
+        if (phase & FG_PHASE_FIRST)
+          s->cq_grid = (int)std::max<int64_t>(1, std::min<int64_t>((std::min(chunk, N) + 63) / 64, m->sm_count));
+        if (s->cq_grid <= 0) return set_err(FG_ERR_INVALID, "internal: continued launch without a first one");
+        const int grid = s->cq_grid;
+        for (int k = 0; k < ng; ++k) roff[k + 1] = roff[k] + (int64_t)grid * cq_r_doubles(G[k].p1);
         if (phase & FG_PHASE_FIRST) {
-          s->cq_grid = (int)std::max<int64_t>(1, std::min<int64_t>((std::min(chunk, N) * ms + 63) / 64, m->sm_count));
-          rc = ensure_gR(s, (int64_t)s->cq_grid * cq_r_doubles(pl->P.p1));
+          rc = ensure_gR(s, roff[ng]);
           if (rc) return rc;
-        } else if (s->cq_grid <= 0 || s->gR_cap < (int64_t)s->cq_grid * cq_r_doubles(pl->P.p1)) {
+        } else if (s->gR_cap < roff[ng]) {
           return set_err(FG_ERR_INVALID, "internal: continued launch without a first one");
         }
-        const int grid = s->cq_grid;
         if (chunkable) *chunkable = true;
-        rc = ensure_parts(s, grid + 1);
+        rc = ensure_parts(s, 2);
         if (rc) return rc;
         rc = timing_begin(s, st);
         if (rc) return rc;
@@ -1106,21 +1203,46 @@ static int accumulate_samples_dev(fg_state* s, fg_model* m, const fg_regressor_c
           const int64_t n = std::min(chunk, N - i0);
           rc = materialize_dev(m, &cfull, q + i0 * m->nq, v + i0 * m->nv, a + i0 * m->nv, n, s->d_ring, ncols_full, st);
           if (rc) return rc;
-          CqArgs ca;
-          ca.W = s->d_ring; ca.ldw = ncols_full; ca.colsel = pl->ptrs.fullcol;
-          ca.tau = tau ? tau + i0 : nullptr; ca.tau_blk = n; ca.tau_ld = ld_tau;
-          ca.rows = n * ms; ca.p1 = pl->P.p1;
-          ca.first = (phase & FG_PHASE_FIRST) && i0 == 0;
-          cudaError_t ce = cq_launch_dense(ca, s->d_gR, grid, m->max_smem, st);
-          if (ce != cudaSuccess) return set_err(FG_ERR_CUDA, "cooperative dense kernel failed: %s", cudaGetErrorString(ce));
-          FG_LAUNCHED();
+          for (int k = 0; k < ng; ++k) {
+            bool first_run = true;
+            for (size_t r0 = 0; r0 < G[k].blocks.size();) {  // runs of consecutive row blocks
+              size_t r1 = r0 + 1;
+              while (r1 < G[k].blocks.size() && G[k].blocks[r1] == G[k].blocks[r1 - 1] + 1) ++r1;
+              const int b0 = G[k].blocks[r0], nblk = (int)(r1 - r0);
+              CqArgs ca;
+              ca.W = s->d_ring + (int64_t)b0 * n * ncols_full; ca.ldw = ncols_full; ca.colsel = G[k].d_colsel;
+              ca.tau = tau ? tau + (int64_t)b0 * ld_tau + i0 : nullptr; ca.tau_blk = n; ca.tau_ld = ld_tau;
+              ca.rows = n * nblk; ca.p1 = G[k].p1;
+              ca.first = (phase & FG_PHASE_FIRST) && i0 == 0 && first_run;
+              cudaError_t ce = cq_launch_dense(ca, s->d_gR + roff[k], grid, m->max_smem, st);
+              if (ce != cudaSuccess) return set_err(FG_ERR_CUDA, "cooperative dense kernel failed: %s", cudaGetErrorString(ce));
+              FG_LAUNCHED();
+              first_run = false;
+              r0 = r1;
+            }
+          }
         }
         rc = timing_end(s, st);
         if (rc) return rc;
         s->rows += N * ms;
         if (!(phase & FG_PHASE_LAST)) return FG_OK;
         int nl = 0;
-        cudaError_t ce = cq_reduce_export(s->d_gR, grid, pl->P.p1, s->d_parts, m->max_smem, &nl, st);
+        cudaError_t ce = cq_reduce(s->d_gR + roff[0], grid, G[0].p1, m->max_smem, &nl, st);
+        for (int k = 1; k < ng && ce == cudaSuccess; ++k) {  // narrower groups: tree, rows scattered to full width, folded
+          ce = cq_reduce(s->d_gR + roff[k], grid, G[k].p1, m->max_smem, &nl, st);
+          if (ce != cudaSuccess) break;
+          const int64_t dd = (int64_t)G[k].p1 * G[0].p1;
+          if (dd > s->ring_cap) { ce = cudaErrorMemoryAllocation; break; }
+          ce = cudaMemsetAsync(s->d_ring, 0, sizeof(double) * dd, st);
+          if (ce != cudaSuccess) break;
+          ce = cq_scatter_rows(s->d_gR + roff[k], G[k].p1, G[k].d_colmap, G[0].p1, s->d_ring, st);
+          if (ce != cudaSuccess) break;
+          CqArgs ca;
+          ca.W = s->d_ring; ca.ldw = G[0].p1; ca.rhs_in_w = true; ca.rows = G[k].p1; ca.p1 = G[0].p1; ca.first = false;
+          ce = cq_launch_dense(ca, s->d_gR + roff[0], 1, m->max_smem, st);
+          nl += 2;
+        }
+        if (ce == cudaSuccess) { ce = cq_export(s->d_gR + roff[0], G[0].p1, s->d_parts, st); ++nl; }
         if (ce != cudaSuccess) return set_err(FG_ERR_CUDA, "cooperative merge failed: %s", cudaGetErrorString(ce));
         for (int i = 0; i < nl; ++i) FG_LAUNCHED();
         return merge_parts_into_state(s, 1, m->max_smem, st);

@@ -50,7 +50,7 @@ cudaError_t cq_launch_dense(const CqArgs& a, double* r_all, int grid, int max_sm
   return cq_launch(P, grid, max_smem, st);
 }
 
-cudaError_t cq_reduce_export(double* r_all, int grid, int p1, double* part_out, int max_smem, int* launches, cudaStream_t st) {
+cudaError_t cq_reduce(double* r_all, int grid, int p1, int max_smem, int* launches, cudaStream_t st) {
   CqParams P;
   memset(&P, 0, sizeof P);
   P.p1 = p1; P.nb = (p1 + 7) / 8; P.r_all = r_all; P.nfac = grid;
@@ -61,9 +61,24 @@ cudaError_t cq_reduce_export(double* r_all, int grid, int p1, double* part_out, 
     if (e != cudaSuccess) return e;
     if (launches) ++*launches;
   }
-  cq_export_kernel<<<32, 256, 0, st>>>(r_all, p1, P.nb, part_out);
-  if (launches) ++*launches;
+  return cudaSuccess;
+}
+
+cudaError_t cq_export(const double* r_all, int p1, double* part_out, cudaStream_t st) {
+  cq_export_kernel<<<32, 256, 0, st>>>(r_all, p1, (p1 + 7) / 8, part_out);
   return cudaGetLastError();
+}
+
+cudaError_t cq_scatter_rows(const double* R, int p1g, const int* colmap, int p1, double* D, cudaStream_t st) {
+  cq_scatter_rows_kernel<<<32, 256, 0, st>>>(R, p1g, (p1g + 7) / 8, colmap, p1, D);
+  return cudaGetLastError();
+}
+
+cudaError_t cq_reduce_export(double* r_all, int grid, int p1, double* part_out, int max_smem, int* launches, cudaStream_t st) {
+  cudaError_t e = cq_reduce(r_all, grid, p1, max_smem, launches, st);
+  if (e != cudaSuccess) return e;
+  if (launches) ++*launches;
+  return cq_export(r_all, p1, part_out, st);
 }
 
 }  // namespace fg

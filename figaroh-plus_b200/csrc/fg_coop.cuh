@@ -329,4 +329,15 @@ __global__ void cq_export_kernel(const double* __restrict__ R, int p1, int nb, d
   }
 }
 
+
+// rows of a (narrower) block-triangular factor as dense rows of width p1: D[r][colmap[c]] = R(r, c); D is zeroed by
+// the caller.  Used to fold the factor of a row-block group with fewer columns into the full-width factor.
+__global__ void cq_scatter_rows_kernel(const double* __restrict__ R, int p1g, int nbg, const int* __restrict__ colmap, int p1,
+                                       double* __restrict__ D) {
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < p1g * p1g; idx += gridDim.x * blockDim.x) {
+    const int r = idx / p1g, c = idx - r * p1g;
+    if (c >= r) D[(size_t)r * p1 + colmap[c]] = R[(size_t)tq_rblk(nbg, r >> 3, c >> 3) * 64 + (r & 7) * 8 + (c & 7)];
+  }
+}
+
 }  // namespace fg

@@ -26,6 +26,11 @@ cudaError_t cq_launch_dense(const CqArgs& a, double* r_all, int grid, int max_sm
 // after the last launch of a sequence: pairwise tree over the `grid` factors (log2 launches of the same kernel: 64
 // rows of the right-hand factor per tile, panels starting at the tile's first non-zero column), then factor 0 as one
 // packed part (upper triangle + squared column norms) in part_out.  *launches += kernels launched.
+// the two halves of cq_reduce_export, and the scatter of a narrower factor's rows into dense rows of width p1 (D must
+// be zeroed; colmap: p1g device ints, local column -> column of the wide problem)
+cudaError_t cq_reduce(double* r_all, int grid, int p1, int max_smem, int* launches, cudaStream_t st);
+cudaError_t cq_export(const double* r_all, int p1, double* part_out, cudaStream_t st);
+cudaError_t cq_scatter_rows(const double* R, int p1g, const int* colmap, int p1, double* D, cudaStream_t st);
 cudaError_t cq_reduce_export(double* r_all, int grid, int p1, double* part_out, int max_smem, int* launches, cudaStream_t st);
 
 }  // namespace fg
