@@ -47,16 +47,18 @@ struct CqParams {
   int rhs_in_w;           // all p1 columns come from W (the small stage: the rhs is the last column of the matrix)
 };
 
-// "panel k is published": one mbarrier per panel (arrival count 1, the owner's lane 0), phase = parity of the CTA's
-// tile counter.  Waiting warps sit in mbarrier.try_wait (the hardware suspends them) instead of polling a flag in
-// shared memory (first version: the polls were 42 % of all executed instructions, profiles/ncu_cq_talos_r02_v1.md).
+// "panel k is published": one mbarrier per panel and stage (V_k, T_k), arrival count 32: EVERY lane of the owner warp
+// arrives (release of its own shared-memory writes), phase = parity of the CTA's tile counter.  Waiting warps sit in
+// mbarrier.try_wait (the hardware suspends them) instead of polling a flag in shared memory (first version: the polls
+// were 42 % of all executed instructions, profiles/ncu_cq_talos_r02_v1.md).  The owner also observes the completed
+// phase before it goes on (one try_wait that succeeds as soon as its 32 lanes have arrived): every thread that
+// arrives also waits, which is the pattern compute-sanitizer's racecheck / synccheck can follow.
 __device__ __forceinline__ void cq_wait(uint64_t* bar, uint32_t parity) {
   while (!rq_mbar_try_wait(bar, parity)) {}
 }
-__device__ __forceinline__ void cq_publish(uint64_t* bar, int lane) {
-  __threadfence_block();
-  __syncwarp();
-  if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rq_smem_u32(bar)) : "memory");
+__device__ __forceinline__ void cq_publish(uint64_t* bar, uint32_t parity) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rq_smem_u32(bar)) : "memory");
+  while (!rq_mbar_try_wait(bar, parity)) {}
 }
 
 // reflector fragments of panel k (kept in registers for the updates that follow)
@@ -138,7 +140,7 @@ __device__ __forceinline__ void cq_update(CqFrag<RPL>& f, double* tile, int nb, 
 template <int RPL>
 // d0, d1: R_kk as loaded by the caller (entries lane, lane + 32), requested before it waited for panel k - 1
 __device__ __forceinline__ void cq_panel(double* tile, int nb, int k, double* R, double d0, double d1, double* Tb, double* scr,
-                                         const GqOffs& o, int lane, uint64_t* barV, uint64_t* barT) {
+                                         const GqOffs& o, int lane, uint64_t* barV, uint64_t* barT, uint32_t parity) {
   double* Rd = R + (size_t)tq_rblk(nb, k, k) * 64;
   double* Xk = tile + k * GQ_BLK;
   double* Rin = scr;
@@ -158,7 +160,7 @@ __device__ __forceinline__ void cq_panel(double* tile, int nb, int k, double* R,
   for (int sl = 0; sl < RPL; ++sl)
 #pragma unroll
     for (int c = 0; c < 8; ++c) Xk[sl * nb * GQ_BLK + tq_idx(c, lane)] = x[sl][c];
-  cq_publish(barV, lane);  // (fence + __syncwarp inside) the reflectors are out: the others start on Y = R + V^T B
+  cq_publish(barV, parity);  // the reflectors are out: the others start on Y = R + V^T B (all lanes pass the wait: warp-wide order)
   double vc0[RPL][4], vc1[RPL][4];
 #pragma unroll
   for (int sl = 0; sl < RPL; ++sl)
@@ -168,7 +170,7 @@ __device__ __forceinline__ void cq_panel(double* tile, int nb, int k, double* R,
       vc1[sl][nn] = Xk[sl * nb * GQ_BLK + o.oc1[nn]];
     }
   gq_panel_T<RPL>(vc0, vc1, sc, Tb + k * 64, lane);
-  cq_publish(barT, lane);
+  cq_publish(barT, parity);
 }
 
 template <int RPL>
@@ -186,7 +188,7 @@ cq_accumulate_dense_kernel(const __grid_constant__ CqParams P) {
   double* R = P.r_all + (size_t)blockIdx.x * rsize;
   if (P.first && P.merge_stride == 0)
     for (size_t i = threadIdx.x; i < rsize; i += blockDim.x) R[i] = 0.0;
-  for (int i = threadIdx.x; i < 2 * nb; i += blockDim.x) rq_mbar_init(barsV + i, 1);
+  for (int i = threadIdx.x; i < 2 * nb; i += blockDim.x) rq_mbar_init(barsV + i, 32);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   GqOffs offs;
   gq_make_offs(offs, lane);
@@ -265,7 +267,7 @@ cq_accumulate_dense_kernel(const __grid_constant__ CqParams P) {
     const int cq = lane >> 2, rq = lane & 3;
     if (warp == k0 % CQ_NW) {
       const double* Rd = R + (size_t)tq_rblk(nb, k0, k0) * 64;
-      cq_panel<RPL>(tile, nb, k0, R, __ldcg(Rd + lane), __ldcg(Rd + lane + 32), Tb, scr, offs, lane, barsV + k0, barsT + k0);
+      cq_panel<RPL>(tile, nb, k0, R, __ldcg(Rd + lane), __ldcg(Rd + lane + 32), Tb, scr, offs, lane, barsV + k0, barsT + k0, parity);
     }
     for (int k = k0; k + 1 < nb; ++k) {
       int j = k + 1 + ((warp - (k + 1)) % CQ_NW + CQ_NW) % CQ_NW;  // my first block to the right of k
@@ -285,7 +287,7 @@ cq_accumulate_dense_kernel(const __grid_constant__ CqParams P) {
       if (j == k + 1) {  // look-ahead: this block first, then its panel, then the rest of panel k's updates
         cq_update<RPL, true>(f, tile, nb, j, Rb, r0, r1, offs, lane, barsT + k, parity, k, Tb);
         __syncwarp();
-        cq_panel<RPL>(tile, nb, j, R, d0, d1, Tb, scr, offs, lane, barsV + j, barsT + j);
+        cq_panel<RPL>(tile, nb, j, R, d0, d1, Tb, scr, offs, lane, barsV + j, barsT + j, parity);
         j += CQ_NW;
         if (j >= nb) continue;
         cq_load_frag(f, tile, nb, k, offs);

@@ -115,7 +115,9 @@ __device__ __forceinline__ double gq_rcp(double x) {
 // (Measured and rejected: skipping the column steps of a padded last block behind uniform branches, and taking
 // sigma by shuffle instead of through the scratch - both break the compiler's interleaving of the unrolled
 // column steps and cost more than they save: 4.92 ms and 4.20 ms against 4.15 ms.)
-template <int RPL>
+// NC: real columns of the block (the columns NC..7 are zero padding: the last block of a row group; their column
+// steps are skipped - 21 of UR10's 248 column steps per tile are padding)
+template <int RPL, int NC = 8>
 __device__ __forceinline__ void gq_panel_factor(double (&x)[RPL][8], const double* Rin, double* Rout, double* sc,
                                                 double* Pb, int lane) {
   const int ci = lane >> 2, part = lane & 3;
@@ -125,9 +127,12 @@ __device__ __forceinline__ void gq_panel_factor(double (&x)[RPL][8], const doubl
   double* dbuf = sc + 8;
   double rw[8];  // updated row j - 1 of the diagonal block (lane-uniform), stored once every lane has read it
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int c = NC; c < 8; ++c) rw[c] = 0.0;
+  if (NC < 8 && lane >= NC && lane < 8) sc[lane] = 0.0;
 #pragma unroll
-    for (int c = j; c < 8; ++c) {
+  for (int j = 0; j < NC; ++j) {
+#pragma unroll
+    for (int c = j; c < NC; ++c) {
       double pr = x[0][j] * x[0][c];
 #pragma unroll
       for (int sl = 1; sl < RPL; ++sl) pr = fma(x[sl][j], x[sl][c], pr);
@@ -152,7 +157,7 @@ __device__ __forceinline__ void gq_panel_factor(double (&x)[RPL][8], const doubl
     __syncwarp();
     double d[8];
 #pragma unroll
-    for (int c = (j & ~1); c < 8; c += 2) {
+    for (int c = (j & ~1); c < NC; c += 2) {
       const double2 t = *reinterpret_cast<const double2*>(dbuf + c);
       d[c] = t.x;
       d[c + 1] = t.y;
@@ -172,7 +177,7 @@ __device__ __forceinline__ void gq_panel_factor(double (&x)[RPL][8], const doubl
     if (lane == 0) sc[j] = tauh;
     rw[j] = beta;
 #pragma unroll
-    for (int c = j + 1; c < 8; ++c) {
+    for (int c = j + 1; c < NC; ++c) {
       const double rho = Rin[j * 8 + c];
       const double w = tauh * fma(d[c], inv, rho);  // tau * v^T [rho; b]  (0 when the reflector is skipped)
       const double coef = w * inv;
@@ -184,7 +189,10 @@ __device__ __forceinline__ void gq_panel_factor(double (&x)[RPL][8], const doubl
     for (int sl = 0; sl < RPL; ++sl) x[sl][j] *= inv;  // H = I (dlarfg with xnorm == 0) leaves v = 0
   }
   __syncwarp();
-  if (lane == 0) Rout[63] = rw[7];
+  if (lane == 0) {
+#pragma unroll
+    for (int c = NC - 1; c < 8; ++c) Rout[(NC - 1) * 8 + c] = rw[c];
+  }
   __syncwarp();
 }
 
@@ -225,6 +233,9 @@ __device__ __forceinline__ void gq_fold_h(double* tile, int nb, double* Rg, int 
     double r0 = 0.0, r1 = 0.0;
     if (k + 1 < nb) { r0 = gq_ld<CG>(Rb + (2 * rq) * 8 + cq); r1 = gq_ld<CG>(Rb + (2 * rq + 1) * 8 + cq); }
     __syncwarp();
+    // (measured and rejected in round 2: a second instantiation gq_panel_factor<RPL, 4> for last blocks with <= 4 real
+    // columns - 21 of UR10's 248 column steps per tile are padding - 4.51 ms against 3.44 ms: the extra code evicts
+    // the panel from the instruction cache, as the round-1 attempt with uniform branches did)
     gq_panel_factor<RPL>(x, Rin, Rout, sc, Xk, lane);
     if ((lane >> 3) <= (lane & 7)) Rd[lane] = Rout[lane];            // rows 0..3 of the upper triangle
     if ((lane >> 3) + 4 <= (lane & 7)) Rd[lane + 32] = Rout[lane + 32];  // rows 4..7
