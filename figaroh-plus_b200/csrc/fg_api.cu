@@ -102,6 +102,7 @@ struct fg_state {
   double* d_ring = nullptr;     // generation 5: ring of regressor tiles + its control words (L2 resident)
   int64_t ring_cap = 0;         // in doubles
   const void* ring_plan = nullptr;  // the plan whose tile layout the ring currently holds (padding columns stay zero)
+  int64_t hint_total = 0;       // host-buffer path: samples of the whole call (the chunks are shorter)
   int cq_grid = 0;              // CTAs (= per-CTA factors in d_gR) of the running cooperative-TSQR sequence
   unsigned* h_rq_err = nullptr; // pinned: error flag of the last generation-5 launch
   double* d_A = nullptr;        // (p1 x p1) dense scratch of the small stage
@@ -117,7 +118,8 @@ struct fg_state {
   // staging for the host-buffer path
   double* d_stage = nullptr;
   int64_t stage_cap = 0;
-  cudaStream_t copy_stream = nullptr;
+  cudaStream_t copy_streams[4] = {nullptr, nullptr, nullptr, nullptr};   // host-buffer path: one per input array
+  cudaEvent_t ev_copy[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   // optional timing of the dominant (fold) kernel
   bool timing = false;
@@ -581,7 +583,8 @@ extern "C" void fg_state_destroy(fg_state* s) {
   cudaFree(s->d_part); cudaFree(s->d_parts); cudaFree(s->d_gR); cudaFree(s->d_A); cudaFree(s->d_Re);
   cudaFree(s->d_X); cudaFree(s->d_idx); cudaFree(s->d_stage); cudaFree(s->d_solve); cudaFree(s->d_ring);
   if (s->h_rq_err) cudaFreeHost(s->h_rq_err);
-  if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+  for (auto& cs : s->copy_streams) if (cs) cudaStreamDestroy(cs);
+  for (auto& e : s->ev_copy) if (e) cudaEventDestroy(e);
   for (auto& e : s->ev) if (e) cudaEventDestroy(e);
   if (s->t0) cudaEventDestroy(s->t0);
   if (s->t1) cudaEventDestroy(s->t1);
@@ -870,13 +873,32 @@ static int launch_rq(fg_state* s, fg_model* m, DevPlan* pl, const double* q, con
 // instead of 26, -2 % kernel time; UR10: the model's 26 confirmed).  A launch of the profiling instantiation of the
 // kernel also measures the warp cycles of a fold per row group and of a produced tile (diagnosis).  One-off per plan,
 // ~10 ms; FG_RQ_CALIBRATE=0 keeps the instruction-count model, FG_RQ_CALIBRATE=2 prints what was measured.
+// pseudo-random doubles in (-3, 3) (calibration inputs only)
+__global__ void synth_inputs_kernel(double* x, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    unsigned long long h = (unsigned long long)i * 0x9E3779B97F4A7C15ull;
+    h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
+    x[i] = ((double)(h >> 11) * (1.0 / 9007199254740992.0) - 0.5) * 6.0;
+  }
+}
+
 static int rq_calibrate(fg_state* s, fg_model* m, DevPlan* pl, const double* q, const double* v, const double* a,
                         const double* tau, int64_t ld_tau, int64_t N, cudaStream_t st) {
   const char* e = getenv("FG_RQ_CALIBRATE");
   const int mode = e && *e ? atoi(e) : 1;
   pl->rq_calibrated = true;
   if (mode == 0 || getenv("FG_RQ_NPCTA") || getenv("FG_RQ_COST")) return FG_OK;
-  const int64_t ncal = std::min<int64_t>(N, 1 << 18);
+  int64_t ncal = std::min<int64_t>(N, 1 << 18);
+  // a short first chunk (host-buffer path) cannot carry timed trials: synthetic inputs then (what a tile costs does not
+  // depend on the values)
+  double* synth = nullptr;
+  if (N < (1 << 17)) {
+    ncal = 1 << 18;
+    const int64_t per = m->nq + 2 * m->nv + pl->P.ms;
+    FG_CUDA(cudaMalloc(&synth, sizeof(double) * ncal * per));
+    synth_inputs_kernel<<<1024, 256, 0, st>>>(synth, ncal * per);
+    q = synth; v = q + ncal * m->nq; a = v + ncal * m->nv; tau = a + ncal * m->nv; ld_tau = ncal;
+  }
   unsigned long long* d_prof = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   FG_CUDA(cudaMalloc(&d_prof, sizeof(unsigned long long) * RQ_PROF_WORDS));
@@ -937,7 +959,8 @@ static int rq_calibrate(fg_state* s, fg_model* m, DevPlan* pl, const double* q, 
     if (!mc.have) break;
     mc.prod = (double)h[24] / (double)h[25];
     if (mode >= 2) {
-      fprintf(stderr, "[fg] rq calibration (%lld samples, %d producer SMs):", (long long)ncal, pl->rq->npc);
+      fprintf(stderr, "[fg] rq calibration (%lld samples, %d producer SMs, ring %d slots of %d KB):", (long long)ncal, pl->rq->npc,
+              pl->rq->ring, pl->rq->slot_doubles / 128);
       for (int g = 0; g < ms_; ++g)
         fprintf(stderr, " g%d[%d warps] fold %.0f wait %.0f |", g, pl->rq->gq.gen.grp[g].ninst, mc.grp[g],
                 (double)h[16 + g] / (double)h[8 + g]);
@@ -982,13 +1005,14 @@ static int rq_calibrate(fg_state* s, fg_model* m, DevPlan* pl, const double* q, 
   cudaEventDestroy(ev0);
   cudaEventDestroy(ev1);
   cudaFree(d_prof);
+  if (synth) { cudaStreamSynchronize(st); cudaFree(synth); }
   if (rc == FG_OK) rc = check_rq_error(s);
   return rc;
 }
 
 static int launch_rq(fg_state* s, fg_model* m, DevPlan* pl, const double* q, const double* v, const double* a,
                      const double* tau, int64_t ld_tau, int64_t N, int phase, cudaStream_t st) {
-  if ((phase & FG_PHASE_FIRST) && !pl->rq_calibrated && N >= (1 << 15)) {
+  if ((phase & FG_PHASE_FIRST) && !pl->rq_calibrated && std::max<int64_t>(N, s->hint_total) >= (1 << 17)) {
     if (!pl->d_rq_tab) { int rc0 = rq_upload_tables(pl); if (rc0) return rc0; }
     int rc0 = rq_calibrate(s, m, pl, q, v, a, tau, ld_tau, N, st);
     if (rc0) return rc0;
@@ -1306,7 +1330,16 @@ extern "C" int fg_state_accumulate_samples_host(fg_state* s, const fg_model* mc,
   if (rc) return rc;
   if (N <= 0) return FG_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t chunk = std::min<int64_t>(N, 1 << 17);  // the copies are the bottleneck (PCIe): a short last chunk keeps the un-overlapped compute tail short
+  // The copies are the bottleneck (PCIe: 192 B per UR10 sample against 12 B/ns of kernel appetite; tools/probe_h2d.py on
+  // this pool, pinned memory: 1 MB copies 30 GB/s, 6 MB 40, 25 MB 42, 192 MB 55).  Chunk sizes ramp up at the start (the
+  // first copy, which nothing can overlap, is short) and down at the end (so is the last kernel, which overlaps nothing).
+  // Measured and rejected (UR10, 1 M samples, end to end 5.70 ms = 33.7 GB/s): chunks of 256 Ki / 512 Ki samples (6.2 /
+  // 6.9 ms), the four arrays on two / four copy streams (6.2 / 6.1 ms); FG_H2D_CAP / FG_H2D_STREAMS keep the A/B.
+  const char* ecap = getenv("FG_H2D_CAP");      // log2 of the largest chunk (A/B)
+  const char* estr = getenv("FG_H2D_STREAMS");  // 1 .. 4 copy streams (A/B)
+  const int64_t cap = 1ll << (ecap && *ecap ? std::max(15, std::min(22, atoi(ecap))) : 17);
+  const int nstr = estr && *estr ? std::max(1, std::min(4, atoi(estr))) : 1;
+  const int64_t chunk = std::min<int64_t>(N, cap);
   const int64_t per_sample = m->nq + 2 * m->nv + ms;
   const int64_t need = 2 * chunk * per_sample;
   if (need > s->stage_cap) {
@@ -1315,19 +1348,28 @@ extern "C" int fg_state_accumulate_samples_host(fg_state* s, const fg_model* mc,
     FG_CUDA(cudaMalloc(&s->d_stage, sizeof(double) * need));
     s->stage_cap = need;
   }
-  if (!s->copy_stream) FG_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+  for (auto& cs : s->copy_streams) if (!cs) FG_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
   for (auto& e : s->ev) if (!e) FG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  // ev[b]: copies into buffer b done; ev[2+b]: compute on buffer b done
+  for (auto& e : s->ev_copy) if (!e) FG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  // ev_copy[4 b + k]: copy k into buffer b done; ev[2 + b]: compute on buffer b done
   FG_CUDA(cudaEventRecord(s->ev[2], st));
   FG_CUDA(cudaEventRecord(s->ev[3], st));
+  std::vector<int64_t> sizes;
+  {
+    int64_t left = N;
+    std::vector<int64_t> down;
+    for (int64_t d = cap / 2; d >= (1 << 15) && left > 2 * d; d /= 2) { down.push_back(d); left -= d; }
+    for (int64_t u = 1 << 15; u < cap && left > u; u *= 2) { sizes.push_back(u); left -= u; }
+    if (left % cap) { sizes.push_back(left % cap); left -= left % cap; }
+    for (; left > 0; left -= cap) sizes.push_back(cap);
+    sizes.insert(sizes.end(), down.begin(), down.end());
+  }
+  s->hint_total = N;
   int b = 0;
-  bool chunkable = false;  // set by the first chunk when the tile-QR kernel took it: later chunks continue its factors
-  // Chunk sizes ramp up (32 Ki, 64 Ki, ... samples) to the staging size: the first copy, which nothing can
-  // overlap, is short, and the kernel of chunk k runs in the shadow of the copy of chunk k + 1.
-  int64_t ramp = std::min<int64_t>(chunk, 1 << 15);
-  for (int64_t i0 = 0, n = 0; i0 < N; i0 += n, b ^= 1) {
-    n = std::min(ramp, N - i0);
-    ramp = std::min(chunk, 2 * ramp);
+  bool chunkable = false;  // set by the first chunk when a chunk-continuing kernel took it: later chunks continue its factors
+  int64_t i0 = 0;
+  for (size_t ci = 0; ci < sizes.size(); ++ci, b ^= 1) {
+    const int64_t n = sizes[ci];
     int phase = FG_PHASE_FIRST | FG_PHASE_LAST;
     if (i0 == 0) phase = N > n ? FG_PHASE_FIRST : phase;
     else if (chunkable) phase = i0 + n >= N ? FG_PHASE_LAST : 0;
@@ -1336,19 +1378,23 @@ extern "C" int fg_state_accumulate_samples_host(fg_state* s, const fg_model* mc,
     double* dv = dq + chunk * m->nq;
     double* da = dv + chunk * m->nv;
     double* dt = da + chunk * m->nv;
-    FG_CUDA(cudaStreamWaitEvent(s->copy_stream, s->ev[2 + b], 0));
-    FG_CUDA(cudaMemcpyAsync(dq, q + i0 * m->nq, sizeof(double) * n * m->nq, cudaMemcpyHostToDevice, s->copy_stream));
-    FG_CUDA(cudaMemcpyAsync(dv, v + i0 * m->nv, sizeof(double) * n * m->nv, cudaMemcpyHostToDevice, s->copy_stream));
-    FG_CUDA(cudaMemcpyAsync(da, a + i0 * m->nv, sizeof(double) * n * m->nv, cudaMemcpyHostToDevice, s->copy_stream));
+    for (int k = 0; k < 4; ++k) FG_CUDA(cudaStreamWaitEvent(s->copy_streams[k], s->ev[2 + b], 0));
+    FG_CUDA(cudaMemcpyAsync(dq, q + i0 * m->nq, sizeof(double) * n * m->nq, cudaMemcpyHostToDevice, s->copy_streams[0]));
+    FG_CUDA(cudaMemcpyAsync(dv, v + i0 * m->nv, sizeof(double) * n * m->nv, cudaMemcpyHostToDevice, s->copy_streams[1 % nstr]));
+    FG_CUDA(cudaMemcpyAsync(da, a + i0 * m->nv, sizeof(double) * n * m->nv, cudaMemcpyHostToDevice, s->copy_streams[2 % nstr]));
     if (tau)
       FG_CUDA(cudaMemcpy2DAsync(dt, sizeof(double) * chunk, tau + i0, sizeof(double) * ld_tau, sizeof(double) * n, ms,
-                                cudaMemcpyHostToDevice, s->copy_stream));
-    FG_CUDA(cudaEventRecord(s->ev[b], s->copy_stream));
-    FG_CUDA(cudaStreamWaitEvent(st, s->ev[b], 0));
+                                cudaMemcpyHostToDevice, s->copy_streams[3 % nstr]));
+    for (int k = 0; k < 4; ++k) {
+      FG_CUDA(cudaEventRecord(s->ev_copy[4 * b + k], s->copy_streams[k]));
+      FG_CUDA(cudaStreamWaitEvent(st, s->ev_copy[4 * b + k], 0));
+    }
     rc = accumulate_samples_dev(s, m, cfg, dq, dv, da, tau ? dt : nullptr, chunk, n, st, phase, i0 == 0 ? &chunkable : nullptr);
     if (rc) return rc;
     FG_CUDA(cudaEventRecord(s->ev[2 + b], st));
+    i0 += n;
   }
+  s->hint_total = 0;
   return FG_OK;
 }
 

@@ -354,7 +354,11 @@ RqLaunch rq_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, co
     break;
   }
   if (rl.nw < 1) { rq_fail(why, "tile does not fit shared memory"); return rl; }
-  R.ring = std::max(8, env_int("FG_RQ_RING", 512));
+  // ring + per-warp factors must stay inside the 126 MB L2 (TIAGo at 512 slots of 170 KB: 8.4 GB of DRAM traffic per
+  // 1 M samples, profiles/ncu_rq_tiago_r02_final.md): 40 MB of ring, between 256 and 512 slots (A/B on B200: UR10 512 of
+  // 62 KB; TIAGo, slots of 132 KB: 256..320 slots 10.70 ms, 384 10.86 ms, 512 10.95 ms)
+  const int ring_auto = (int)std::min<int64_t>(512, std::max<int64_t>(256, (40ll << 20) / std::max<int64_t>(1, (int64_t)R.slot_doubles * 8)));
+  R.ring = std::max(8, env_int("FG_RQ_RING", ring_auto));
   R.sleep_ns = std::max(0, env_int("FG_RQ_SLEEP", 400));
   rl.ring_doubles = (int64_t)R.ring * R.slot_doubles;
   rl.rfull_doubles = (int64_t)T.nbf * (T.nbf + 1) / 2 * 64;
