@@ -1570,6 +1570,21 @@ extern "C" int fg_state_merge_packed(fg_state* s, const double* packed, int32_t 
     FG_CUDA(cudaMalloc(&s->d_rows_pending, sizeof(double)));
     FG_CUDA(cudaMemsetAsync(s->d_rows_pending, 0, sizeof(double), st));
   }
+  {  // pairwise tree with the cooperative blocked TSQR (fg_coop.cuh): 40 us per level against 95 us (UR10, 74 columns)
+     // and 0.7 ms against 2.4 ms (Talos, 331 columns) with the column-owner merge kernels
+    const char* ecq = getenv("FG_USE_CQ");
+    if (n >= 2 && !(ecq && ecq[0] == '0') && s->p1 <= cq_max_p1(max_smem)) {
+      rc = ensure_gR(s, (int64_t)n * cq_r_doubles(s->p1));
+      if (rc) return rc;
+      cudaError_t e = cq_import_dense(packed, n, s->p1, s->d_gR, s->d_rows_pending, st);
+      int nl = 1;
+      if (e == cudaSuccess) e = cq_reduce_export(s->d_gR, n, s->p1, s->d_parts, max_smem, &nl, st);
+      if (e != cudaSuccess) return set_err(FG_ERR_CUDA, "merge of packed factors failed: %s", cudaGetErrorString(e));
+      for (int i = 0; i < nl; ++i) FG_LAUNCHED();
+      s->rows_pending = true;
+      return merge_parts_into_state(s, 1, max_smem, st);
+    }
+  }
   dense_to_tri_kernel<<<dim3(16, n), 256, 0, st>>>(packed, n, s->p1, s->d_parts, s->d_rows_pending);
   FG_CUDA(cudaGetLastError());
   FG_LAUNCHED();

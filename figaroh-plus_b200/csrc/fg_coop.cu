@@ -74,6 +74,13 @@ cudaError_t cq_scatter_rows(const double* R, int p1g, const int* colmap, int p1,
   return cudaGetLastError();
 }
 
+cudaError_t cq_import_dense(const double* packed, int n, int p1, double* r_all, double* rows_acc, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(r_all, 0, sizeof(double) * (size_t)n * cq_r_doubles(p1), st);
+  if (e != cudaSuccess) return e;
+  cq_import_dense_kernel<<<dim3(16, n), 256, 0, st>>>(packed, n, p1, (p1 + 7) / 8, r_all, rows_acc);
+  return cudaGetLastError();
+}
+
 cudaError_t cq_reduce_export(double* r_all, int grid, int p1, double* part_out, int max_smem, int* launches, cudaStream_t st) {
   cudaError_t e = cq_reduce(r_all, grid, p1, max_smem, launches, st);
   if (e != cudaSuccess) return e;

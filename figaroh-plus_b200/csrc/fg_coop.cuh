@@ -332,6 +332,27 @@ __global__ void cq_export_kernel(const double* __restrict__ R, int p1, int nb, d
 }
 
 
+// n dense upper-triangular factors (fg_state_export layout: p1 x p1 row-major R | p1 norms | rows | p1 - 1 perm entries)
+// into block layout (r_all zeroed by the caller); the row counts are summed into rows_acc
+__global__ void cq_import_dense_kernel(const double* __restrict__ packed, int n, int p1, int nb, double* __restrict__ r_all,
+                                       double* __restrict__ rows_acc) {
+  const int64_t pk = (int64_t)p1 * p1 + 2 * (int64_t)p1;
+  const size_t rsize = (size_t)nb * (nb + 1) / 2 * 64;
+  for (int k = blockIdx.y; k < n; k += gridDim.y) {
+    const double* src = packed + (size_t)k * pk;
+    double* R = r_all + (size_t)k * rsize;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < p1 * p1; idx += gridDim.x * blockDim.x) {
+      const int r = idx / p1, c = idx - r * p1;
+      if (c >= r) R[(size_t)tq_rblk(nb, r >> 3, c >> 3) * 64 + (r & 7) * 8 + (c & 7)] = src[idx];
+    }
+  }
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    double acc = 0.0;
+    for (int k = 0; k < n; ++k) acc += packed[(size_t)k * pk + (size_t)p1 * p1 + p1];
+    *rows_acc += acc;
+  }
+}
+
 // rows of a (narrower) block-triangular factor as dense rows of width p1: D[r][colmap[c]] = R(r, c); D is zeroed by
 // the caller.  Used to fold the factor of a row-block group with fewer columns into the full-width factor.
 __global__ void cq_scatter_rows_kernel(const double* __restrict__ R, int p1g, int nbg, const int* __restrict__ colmap, int p1,

@@ -31,6 +31,8 @@ cudaError_t cq_launch_dense(const CqArgs& a, double* r_all, int grid, int max_sm
 cudaError_t cq_reduce(double* r_all, int grid, int p1, int max_smem, int* launches, cudaStream_t st);
 cudaError_t cq_export(const double* r_all, int p1, double* part_out, cudaStream_t st);
 cudaError_t cq_scatter_rows(const double* R, int p1g, const int* colmap, int p1, double* D, cudaStream_t st);
+// n gathered factors in the fg_state_export layout -> block layout in r_all (zeroed here), row counts added to *rows_acc
+cudaError_t cq_import_dense(const double* packed, int n, int p1, double* r_all, double* rows_acc, cudaStream_t st);
 cudaError_t cq_reduce_export(double* r_all, int grid, int p1, double* part_out, int max_smem, int* launches, cudaStream_t st);
 
 }  // namespace fg
