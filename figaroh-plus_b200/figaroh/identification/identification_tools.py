@@ -138,8 +138,19 @@ def weigthed_least_squares(robot, phi_b, W_b, tau_meas, tau_est, param):
         diff = tau_meas[start_idx:stop] - tau_est[start_idx:stop]
         sigma = np.linalg.norm(diff) / (len(diff) - len(phi_b))
         start_idx = stop
+        if sigma == 0.0:  # the reference divides by it: infinite weights, np.linalg.pinv then fails in the SVD
+            raise np.linalg.LinAlgError("SVD did not converge")
         w[ii * nb_samples:(ii + 1) * nb_samples] = 1 / sigma
     Wd = _eng.as_device(W_b)
     wd = torch.from_numpy(w).to(Wd.device)
-    R1, z, _, _ = _factor_of(Wd * wd[:, None], torch.from_numpy(tau_meas).to(Wd.device) * wd)
-    return np.around(np.linalg.solve(R1, z), 6)
+    Ws, ts = Wd * wd[:, None], torch.from_numpy(tau_meas).to(Wd.device) * wd
+    try:
+        R1, z, _, _ = _factor_of(Ws, ts)
+        return np.around(np.linalg.solve(R1, z), 6)
+    except np.linalg.LinAlgError:
+        # rank-deficient weighted system: the reference's pinv(P W_b) (P tau) is the minimum-norm solution;
+        # with P W_b = Q R (Q with orthonormal columns) it is pinv(R) Q^T (P tau), all on the small factor
+        r = Ws.shape[1]
+        st = _eng.TsqrState(r).accumulate_dense(Ws, ts)
+        R = st.export().cpu().numpy()[:(r + 1) * (r + 1)].reshape(r + 1, r + 1)
+        return np.around(np.linalg.pinv(R[:r, :r]) @ R[:r, r], 6)

@@ -300,6 +300,12 @@ def test_statistics_on_the_factor_match_reference():
     out = weigthed_least_squares(R, phi_ls, W_b, tau, tau_est, param)
     ref = pre.weigthed_least_squares(nq, phi_ls, W_b, tau, tau_est, param)
     np.testing.assert_allclose(out, ref, atol=2e-6)
+    # rank-deficient weighted system: the reference's pinv gives the minimum-norm solution
+    W_d = np.c_[W_b, 2.0 * W_b[:, 0]]
+    phi_d = np.r_[phi_ls, 0.0]
+    out_d = weigthed_least_squares(R, phi_d, W_d, tau, tau_est, param)
+    ref_d = pre.weigthed_least_squares(nq, phi_d, W_d, tau, tau_est, param)
+    np.testing.assert_allclose(out_d, ref_d, atol=5e-6)
 
 
 def test_human_free_flyer_560_columns_drop_in():
