@@ -55,6 +55,16 @@ __device__ __forceinline__ unsigned long long rq_policy_evict_first() {
   asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
+__device__ __forceinline__ unsigned long long rq_policy_evict_last() {
+  unsigned long long p;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+// 16-byte store that asks L2 to keep the line (rows of W that are still being completed by later patches)
+__device__ __forceinline__ void rq_st_keep(double2* p, double2 v) {
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(rq_policy_evict_last())
+               : "memory");
+}
 __device__ __forceinline__ double rq_ldg_stream(const double* p) {
   double v;
   asm("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(rq_policy_evict_first()));

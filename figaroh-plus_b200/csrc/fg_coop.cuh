@@ -9,18 +9,22 @@
 // Householder work per row, i.e. the detour through HBM is 5 % of the FP64 time.
 //
 // What the column-at-a-time register-tile kernel of fg_wide.cuh showed (profiles/ncu_wide_talos_r02.md: 6.8 % of the
-// FP64 roofline): one CTA-wide barrier per column, 331 of them per tile, and no tensor-core work.  Here:
+// FP64 roofline): one CTA-wide barrier per column, 331 of them per tile, and no tensor-core work.  Here (Talos:
+// 40 % of the roofline, profiles/ncu_cq_talos_r02_final.md):
 //   * the tile (64 rows x nb 8-column blocks, fg_tile.cuh layout) lives in shared memory, the CTA's
 //     block-upper-triangular factor R in an L2-resident scratch (nb (nb + 1) / 2 blocks of 8 x 8);
 //   * warp w OWNS the column blocks j = w (mod NW): nobody else ever touches block j of the tile or column j of R,
-//     so there is no barrier inside a tile - only one flag, "panel k is published";
+//     so there is no CTA barrier inside a tile - only two mbarriers per panel, "V_k is published" and "T_k is published";
 //   * panel k (8 columns, two rows per lane) is factored by its owner with the row-group streams' Householder panel
 //     (gq_panel_factor: LAPACK dlarfg reflectors, compact-WY T from a DMMA); the owner leaves V_k in place of the
-//     block, T_k in a per-panel slot and raises the flag;
+//     block and publishes it, then T_k in a per-panel slot (the others start Y = R_kj + V^T B_j while T_k is computed);
 //   * every warp then applies panel k to its own blocks j > k with DMMA (Y = R_kj + V^T B_j, W = T^T Y,
 //     R_kj -= W, B_j -= V W: gq_fold_h's trailing update).  The owner of block k + 1 does that block FIRST and
 //     factors panel k + 1 at once (look-ahead), so the serial chain of a tile is nb x (one update + one panel)
-//     while the other nb (nb - 1) / 2 updates fill the FP64 pipe around it.
+//     while the other nb (nb - 1) / 2 updates fill the FP64 pipe around it; the R blocks a warp needs after a wait
+//     are requested from L2 before it;
+//   * merge mode: the same kernel folds one per-CTA factor into another, 64 of its rows per tile, the panels
+//     starting at the tile's first non-zero column (pairwise tree over the factors, multi-GPU exchange, small stage).
 #pragma once
 #define FG_GQ_DEVICE_ONLY
 #include "fg_groupqr.cuh"

@@ -74,7 +74,13 @@ struct MatzSink {
     if (c2 < NC2) {
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
+        // L2 evict-last: the row is completed by the patches of the bodies that follow; lines that leave L2 half
+        // written cost DRAM efficiency (A/B, 6 warps: 0.99 ms with the hint, 1.09 ms without)
+#ifndef MATZ_NO_EVICT_LAST
+        if (4 * it + r0 < nrows) rq_st_keep(p, zero ? make_double2(0.0, 0.0) : sp[it * (4 * MATZ_ROW / 2)]);
+#else
         if (4 * it + r0 < nrows) *p = zero ? make_double2(0.0, 0.0) : sp[it * (4 * MATZ_ROW / 2)];
+#endif
         p += step;
       }
     }
@@ -172,7 +178,9 @@ struct MatzSink {
 };
 
 #ifndef MATZ_WARPS
-#define MATZ_WARPS 8   // 205 registers, no spills (A/B on B200: 16 warps at 128 registers with spills 2.26 ms, 12: 1.63, 8: 1.09)
+#define MATZ_WARPS 6   // spill-free (A/B on B200, UR10 1 M samples: 16 warps at 128 registers with spills 2.26 ms, 12: 1.63, 8: 1.09;
+                       // with evict-last stores 4: 1.27, 5: 1.23, 6: 0.99, 7: 1.04, 8: 1.04, 10: 1.18 - the rows of a tile are
+                       // completed over six patch passes: warps x 148 SMs x 129 KB of partially written rows must fit L2)
 #endif
 __global__ void __launch_bounds__(MATZ_WARPS * 32, 1)
 matz_kernel(const __grid_constant__ MatzParams P, const MatzTables* __restrict__ tab, const double* __restrict__ q,

@@ -4,6 +4,5 @@ mkdir -p gpurun_out
 for f in figaroh-plus_b200/lib/libfigaroh_b200.so figaroh-plus_b200/lib/variants/lib_matz_*.so; do
   echo "== $f"
   FG_B200_LIB=$PWD/$f timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k golden 2>&1 | tail -1
-  for rep in 1 2; do FG_B200_LIB=$PWD/$f timeout 300 python tools/probe_materialize.py 1000000 2>&1 | tail -1; done
+  for rep in 1 2; do FG_B200_LIB=$PWD/$f timeout 300 python tools/probe_materialize.py 1000000 2>&1 | tail -1 | cut -c1-200; done
 done
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:matz_kernel -s 3 -c 1 -f -o gpurun_out/prof_matz2 python tools/probe_materialize.py 1000000 > /dev/null 2>&1; echo "rc=$?"
