@@ -83,7 +83,7 @@ __device__ __forceinline__ void rq_emit(double* gslot, int ed, const double* sl,
 #pragma unroll
   for (int k = 0; k < 10; ++k) {
     if ((ed >> k) & 1) {  // uniform
-      dst[lane ^ tq_sw(slot & 7)] = valid ? val[k] : 0.0;
+      dst[lane ^ tq_sw(slot & 7)] = valid ? val[k] : 0.0;  // (measured and rejected: L2 evict-last on the ring stores)
       ++slot;
       dst += 32;
     }

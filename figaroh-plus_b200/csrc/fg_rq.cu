@@ -263,7 +263,7 @@ RqLaunch rq_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, co
     cost[g] = c_base + c_panel * G.nb + c_trail * G.nb * (G.nb - 1) / 2;
     csum += cost[g];
   }
-  double pcost = 1.07 * (400.0 + 420.0 * nproc + 45.0 * n_transports + 190.0 * n_emits + 25.0 * n_simple + 60.0 * (nops - nproc));  // 1.07: A/B on UR10 (26 producer SMs of 148)
+  double pcost = 0.97 * (400.0 + 420.0 * nproc + 45.0 * n_transports + 190.0 * n_emits + 25.0 * n_simple + 60.0 * (nops - nproc));  // 0.97: the timed calibration's pick on UR10 (22 producer SMs of 148) and TIAGo (21..22)
   if (measured && measured->have) {  // warp cycles per tile, measured on this device with this plan
     csum = 0.0;
     for (int g = 0; g < ms; ++g) { cost[g] = std::max(1.0, measured->grp[g]); csum += cost[g]; }
