@@ -144,13 +144,9 @@ def weigthed_least_squares(robot, phi_b, W_b, tau_meas, tau_est, param):
     Wd = _eng.as_device(W_b)
     wd = torch.from_numpy(w).to(Wd.device)
     Ws, ts = Wd * wd[:, None], torch.from_numpy(tau_meas).to(Wd.device) * wd
-    try:
-        R1, z, _, _ = _factor_of(Ws, ts)
-        return np.around(np.linalg.solve(R1, z), 6)
-    except np.linalg.LinAlgError:
-        # rank-deficient weighted system: the reference's pinv(P W_b) (P tau) is the minimum-norm solution;
-        # with P W_b = Q R (Q with orthonormal columns) it is pinv(R) Q^T (P tau), all on the small factor
-        r = Ws.shape[1]
-        st = _eng.TsqrState(r).accumulate_dense(Ws, ts)
-        R = st.export().cpu().numpy()[:(r + 1) * (r + 1)].reshape(r + 1, r + 1)
-        return np.around(np.linalg.pinv(R[:r, :r]) @ R[:r, r], 6)
+    # The reference's pinv(P W_b) (P tau) - the minimum-norm solution when the weighted system is rank-deficient -
+    # on the small factor: with P W_b = Q R (Q with orthonormal columns) it is pinv(R) Q^T (P tau)
+    r = Ws.shape[1]
+    st = _eng.TsqrState(r).accumulate_dense(Ws, ts)
+    R = st.export().cpu().numpy()[:(r + 1) * (r + 1)].reshape(r + 1, r + 1)
+    return np.around(np.linalg.pinv(R[:r, :r]) @ R[:r, r], 6)
