@@ -1,9 +1,11 @@
 // fg_matz.cu - host side of the materialising kernel (fg_matz.cuh): tables of the walk over the whole tree for all row
 // blocks, launch.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "fg_matz.cuh"
+#include "fg_matzg.cuh"
 #include "fg_matz.h"
 
 namespace fg {
@@ -63,6 +65,25 @@ MatzPlan matz_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, 
     if (nw >= (stage_in ? 6 : 1)) break;
   }
   if (nw < 1) { mp.tab.reset(); return mp; }
+  {  // serial chain of single-dof joints, one row block per joint, no coupling columns: the row-block-major kernel
+    bool chain = P.mode == 0 && ms == nb && !M.coupling && !(getenv("FG_USE_MATZG") && getenv("FG_USE_MATZG")[0] == '0');
+    for (int t = 0; t < nb && chain; ++t) {
+      const DevJoint& jt = joints[t + 1];
+      chain = walk.order[t] == t + 1 && jt.parent == t && jt.jtype >= 1 && jt.jtype <= 3 && rows[t].joint == t + 1 &&
+              rows[t].rowblock == t && T.extra_grp[t + 1] == t;
+    }
+    if (chain) {
+      MatzgParams& Gp = mp.gprm;
+      memset(&Gp, 0, sizeof Gp);
+      Gp.nb = nb; Gp.ms = ms; Gp.nq = P.nq; Gp.nv = P.nv; Gp.flags = P.flags; Gp.ncols = 14 * nb; Gp.pitch = 14 * nb + 2;
+      for (int k = 0; k < 3; ++k) Gp.gravity[k] = P.gravity[k];
+      Gp.smem_per_warp = nb * MZG_KIN * 32 + 32 * Gp.pitch;
+      Gp.smem_per_warp += Gp.smem_per_warp & 1;
+      int gw = MATZG_WARPS;
+      while (gw > 0 && tab_bytes + gw * Gp.smem_per_warp * 8 > max_smem) --gw;
+      if (gw >= 4) { mp.g_ok = true; mp.g_nw = gw; mp.g_smem = tab_bytes + gw * Gp.smem_per_warp * 8; }
+    }
+  }
   mp.nw = nw;
   mp.smem = tab_bytes + nw * M.smem_per_warp * 8;
   mp.sm_count = sm_count;
@@ -72,6 +93,14 @@ MatzPlan matz_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, 
 
 cudaError_t matz_launch(const MatzPlan& mp, const MatzTables* d_tab, const double* q, const double* v, const double* a,
                         int64_t N, double* W, int64_t ldw, cudaStream_t st) {
+  if (mp.g_ok && ldw == mp.gprm.ncols && (reinterpret_cast<uintptr_t>(W) & 15) == 0) {
+    cudaError_t e = cudaFuncSetAttribute(matzg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mp.g_smem);
+    if (e != cudaSuccess) return e;
+    const int64_t ntiles = (N + 31) / 32;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((ntiles + mp.g_nw - 1) / mp.g_nw, mp.sm_count));
+    matzg_kernel<<<grid, mp.g_nw * 32, mp.g_smem, st>>>(mp.gprm, d_tab, q, v, a, N, W, ldw);
+    return cudaGetLastError();
+  }
   cudaError_t e = cudaFuncSetAttribute(matz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mp.smem);
   if (e != cudaSuccess) return e;
   const int64_t ntiles = (N + 31) / 32;

@@ -177,6 +177,9 @@ struct MatzSink {
   }
 };
 
+#ifndef MATZG_WARPS
+#define MATZG_WARPS 5   // fg_matzg.cuh: 42 KB of kinematics + stage per warp
+#endif
 #ifndef MATZ_WARPS
 #define MATZ_WARPS 6   // spill-free (A/B on B200, UR10 1 M samples: 16 warps at 128 registers with spills 2.26 ms, 12: 1.63, 8: 1.09;
                        // with evict-last stores 4: 1.27, 5: 1.23, 6: 0.99, 7: 1.04, 8: 1.04, 10: 1.18 - the rows of a tile are

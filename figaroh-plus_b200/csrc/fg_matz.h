@@ -13,6 +13,7 @@ struct MatzTables;
 }  // namespace fg
 
 #include "fg_matz_params.h"
+#include "fg_matzg_params.h"
 
 namespace fg {
 
@@ -21,6 +22,10 @@ struct MatzPlan {
   int nw = 0, smem = 0, sm_count = 0;
   MatzParams prm;
   std::shared_ptr<MatzTables> tab;   // host copy; the caller uploads it (matz_tables_bytes() bytes)
+  // row-block-major kernel for serial chains (fg_matzg.cuh); it needs contiguous 16-byte aligned rows (checked per launch)
+  bool g_ok = false;
+  int g_nw = 0, g_smem = 0;
+  MatzgParams gprm;
 };
 
 size_t matz_tables_bytes();
