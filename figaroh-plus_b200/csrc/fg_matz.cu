@@ -75,7 +75,7 @@ MatzPlan matz_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, 
     if (chain) {
       MatzgParams& Gp = mp.gprm;
       memset(&Gp, 0, sizeof Gp);
-      Gp.nb = nb; Gp.ms = ms; Gp.nq = P.nq; Gp.nv = P.nv; Gp.flags = P.flags; Gp.ncols = 14 * nb; Gp.pitch = 14 * nb + 2;
+      Gp.nb = nb; Gp.ms = ms; Gp.nq = P.nq; Gp.nv = P.nv; Gp.flags = P.flags; Gp.ncols = 14 * nb; Gp.pitch = 14 * nb;  // dense rows: the block leaves as ONE bulk copy
       for (int k = 0; k < 3; ++k) Gp.gravity[k] = P.gravity[k];
       Gp.smem_per_warp = nb * MZG_KIN * 32 + 32 * Gp.pitch;
       Gp.smem_per_warp += Gp.smem_per_warp & 1;

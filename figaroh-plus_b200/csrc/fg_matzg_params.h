@@ -4,7 +4,7 @@
 namespace fg {
 
 struct MatzgParams {
-  int nb, ms, nq, nv, flags, ncols, pitch;   // pitch: doubles per staged row (ncols + 2: bank spread)
+  int nb, ms, nq, nv, flags, ncols, pitch;   // pitch: doubles per staged row (= ncols: dense, one bulk copy per block)
   int smem_per_warp;                         // doubles
   double gravity[3];
 };
