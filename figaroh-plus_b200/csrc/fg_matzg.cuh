@@ -46,6 +46,14 @@ matzg_kernel(const __grid_constant__ MatzgParams P, const MatzTables* __restrict
     const double* qs = q + sc * P.nq;
     const double* vs = qd + sc * P.nv;
     const double* as = qdd + sc * P.nv;
+    {  // the next tile of this warp towards L2
+      const int64_t sn = (tl + (int64_t)gridDim.x * nw) * 32 + lane;
+      if (sn < N) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(q + sn * P.nq));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(qd + sn * P.nv));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(qdd + sn * P.nv));
+      }
+    }
     // ---- forward pass down the chain (same recursion as rq_walk_tile; joints 1 .. nb in walk order)
     {
       double v[6] = {0, 0, 0, 0, 0, 0}, a[6] = {-P.gravity[0], -P.gravity[1], -P.gravity[2], 0, 0, 0};
@@ -104,13 +112,6 @@ matzg_kernel(const __grid_constant__ MatzgParams P, const MatzTables* __restrict
     // ---- row block by row block: this lane's row of the block, then out through the copy engine
     for (int g = 0; g < P.ms; ++g) {
       const int tg = T->rowjoint[g] - 1;   // walk index of the row block's joint (chain: joint j at walk index j - 1)
-      if (lane == 0) rq_bulk_wait_read<0>();   // the previous block has left the stage
-      __syncwarp();
-      if (tg >= 1) {                       // the body above the joint had entries in the pass before: zero them
-        double2* z = reinterpret_cast<double2*>(stage + 14 * (tg - 1));
-#pragma unroll
-        for (int c2 = 0; c2 < 7; ++c2) z[c2] = make_double2(0.0, 0.0);
-      }
       double sl[3] = {T->S[g][0], T->S[g][1], T->S[g][2]}, sa[3] = {T->S[g][3], T->S[g][4], T->S[g][5]};
       for (int t = tg; t < nb; ++t) {
         const double* K = kin + (size_t)t * MZG_KIN * 32;
@@ -154,6 +155,15 @@ matzg_kernel(const __grid_constant__ MatzgParams P, const MatzTables* __restrict
           if (P.flags & 2) e10 = aa;
           if (P.flags & 1) { e11 = vv; e12 = sgn(vv); }
           if (P.flags & 4) e13 = 1.0;
+        }
+        if (t == tg) {  // first write of the pass (its values are in registers by now): the previous block must have left
+          if (lane == 0) rq_bulk_wait_read<0>();
+          __syncwarp();
+          if (tg >= 1) {  // the body above the joint had entries in the pass before: zero them
+            double2* z = reinterpret_cast<double2*>(stage + 14 * (tg - 1));
+#pragma unroll
+            for (int c2 = 0; c2 < 7; ++c2) z[c2] = make_double2(0.0, 0.0);
+          }
         }
         double2* row = reinterpret_cast<double2*>(stage + 14 * t);
 #pragma unroll
