@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round-2 multi-GPU call: usage tools/gpu_r2t.sh N   (run under gpurun --gpus N)
+# Round-2 multi-GPU call: usage tools/gpu_multi_gpu.sh N   (run under gpurun --gpus N)
 # weak scaling (1 M samples per GPU), the north-star strong-scaling run (10 M UR10 samples over N GPUs), Talos weak,
 # the 2-rank NCCL parity test.
 N=${1:-2}
