@@ -966,9 +966,10 @@ static int rq_calibrate(fg_state* s, fg_model* m, DevPlan* pl, const double* q, 
                 (double)h[16 + g] / (double)h[8 + g]);
       fprintf(stderr, " producer tile %.0f wait %.0f\n", mc.prod, (double)h[26] / (double)h[25]);
     }
-    // Measured and rejected as the apportionment of the consumer warps (UR10: 3.54 ms against 3.48 ms with the
-    // instruction-count model): a fold's cycles depend on what its neighbours on the SM are doing.  The numbers are
-    // printed for diagnosis (mode 2) and only used with FG_RQ_CALIBRATE=3.
+    // The measured fold cycles are not reliably the better apportionment of the consumer warps (a fold's cycles depend
+    // on what its neighbours on the SM are doing: UR10 3.53 ms against 3.45 ms with the instruction-count model, TIAGo
+    // 10.73 ms against 11.0 ms), so both are TIMED below and the faster one is kept (mode 3 forces the measured one).
+    const bool have_meas = mc.have;
     if (mode < 3) mc.have = false;
     // (2) producer SMs: timed trials, downhill from the model's count
     const int start = pl->rq->npc;
@@ -998,9 +999,24 @@ static int rq_calibrate(fg_state* s, fg_model* m, DevPlan* pl, const double* q, 
       float t = 0.f;
       if (eval(best_n + dir, &t) && t < best_ms) { best_ms = t; best_n += dir; break; }
     }
+    bool use_meas = mc.have;
+    if (have_meas && !mc.have) {  // (3) row groups by measured fold cycles at the chosen producer count: kept if >= 1 % faster
+      mc.have = true;
+      float t = 0.f;
+      if (eval(best_n, &t) && t < 0.99f * best_ms) {
+        best_ms = t; use_meas = true;
+        for (int dir = -1; dir <= 1; dir += 2) {  // the producer count once more around the new apportionment
+          float t2 = 0.f;
+          if (eval(best_n + dir, &t2) && t2 < best_ms) { best_ms = t2; best_n += dir; break; }
+        }
+      }
+      mc.have = use_meas;
+    }
     mc.force_npcta = best_n;
     if (!rebuild(mc)) rc = set_err(FG_ERR_INVALID, "internal: calibrated split could not be rebuilt");
-    if (mode >= 2) fprintf(stderr, "[fg] rq calibration: %d producer SMs (model %d)\n", best_n, start);
+    if (mode >= 2)
+      fprintf(stderr, "[fg] rq calibration: %d producer SMs (model %d), row groups by %s\n", best_n, start,
+              use_meas ? "measured fold cycles" : "the instruction-count model");
   } while (false);
   cudaEventDestroy(ev0);
   cudaEventDestroy(ev1);
