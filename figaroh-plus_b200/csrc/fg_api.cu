@@ -979,9 +979,9 @@ static int rq_calibrate(fg_state* s, fg_model* m, DevPlan* pl, const double* q, 
       if (n < 1 || n > m->sm_count - 1) return false;
       mc.force_npcta = n;
       if (!rebuild(mc)) return false;
-      float t1 = 0.f, t2 = 0.f;
-      if (trial(nullptr, &t1) || trial(nullptr, &t2)) return false;
-      *ms = std::min(t1, t2);
+      float t1 = 0.f, t2 = 0.f, t3 = 0.f;   // the fastest of three: a trial is ~1 ms and one outlier must not decide
+      if (trial(nullptr, &t1) || trial(nullptr, &t2) || trial(nullptr, &t3)) return false;
+      *ms = std::min(t1, std::min(t2, t3));
       if (mode >= 2) fprintf(stderr, "[fg]   %d producer SMs: %.4f ms\n", n, *ms);
       return true;
     };
@@ -990,20 +990,20 @@ static int rq_calibrate(fg_state* s, fg_model* m, DevPlan* pl, const double* q, 
       bool moved = false;
       for (int n = best_n + 2 * dir;; n += 2 * dir) {
         float t = 0.f;
-        if (!eval(n, &t) || t >= best_ms) break;
+        if (!eval(n, &t) || t >= 0.998f * best_ms) break;   // a little hysteresis: the model's count is tuned
         best_ms = t; best_n = n; moved = true;
       }
       if (moved) break;
     }
     for (int dir = -1; dir <= 1; dir += 2) {  // odd neighbours
       float t = 0.f;
-      if (eval(best_n + dir, &t) && t < best_ms) { best_ms = t; best_n += dir; break; }
+      if (eval(best_n + dir, &t) && t < 0.998f * best_ms) { best_ms = t; best_n += dir; break; }
     }
     bool use_meas = mc.have;
-    if (have_meas && !mc.have) {  // (3) row groups by measured fold cycles at the chosen producer count: kept if >= 1 % faster
+    if (have_meas && !mc.have) {  // (3) row groups by measured fold cycles at the chosen producer count: kept if >= 0.5 % faster
       mc.have = true;
       float t = 0.f;
-      if (eval(best_n, &t) && t < 0.99f * best_ms) {
+      if (eval(best_n, &t) && t < 0.995f * best_ms) {
         best_ms = t; use_meas = true;
         for (int dir = -1; dir <= 1; dir += 2) {  // the producer count once more around the new apportionment
           float t2 = 0.f;
