@@ -1170,7 +1170,7 @@ static int accumulate_samples_dev(fg_state* s, fg_model* m, const fg_regressor_c
     return set_err(FG_ERR_INVALID, "state has p=%d but the regressor has %d columns", s->p, pl->P.ncols);
   if (N <= 0) return FG_OK;
   if (tau && ld_tau < N) return set_err(FG_ERR_INVALID, "ld_tau=%lld smaller than N=%lld", (long long)ld_tau, (long long)N);
-  const int ms = pl->P.ms, nslot = (pl->P.p1 + 31) / 32;
+  const int ms = pl->P.ms;
   {
     const char* e = getenv("FG_USE_RQ");
     const bool use_rq = !(e && e[0] == '0');

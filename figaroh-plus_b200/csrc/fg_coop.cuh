@@ -196,7 +196,6 @@ cq_accumulate_dense_kernel(const __grid_constant__ CqParams P) {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   GqOffs offs;
   gq_make_offs(offs, lane);
-  const int ncol = nb * 8;
   constexpr int CQ_TR = 32 * RPL;
   const bool merge = P.merge_stride > 0;
   const double* Rs = nullptr;  // merge mode: the factor that is folded into R, 64 of its rows per tile
