@@ -102,6 +102,7 @@ struct fg_state {
   double* d_ring = nullptr;     // generation 5: ring of regressor tiles + its control words (L2 resident)
   int64_t ring_cap = 0;         // in doubles
   const void* ring_plan = nullptr;  // the plan whose tile layout the ring currently holds (padding columns stay zero)
+  int ring_slots = 0;               // ... and its slot count (the control words sit behind the last slot)
   int64_t hint_total = 0;       // host-buffer path: samples of the whole call (the chunks are shorter)
   int cq_grid = 0;              // CTAs (= per-CTA factors in d_gR) of the running cooperative-TSQR sequence
   unsigned* h_rq_err = nullptr; // pinned: error flag of the last generation-5 launch
@@ -919,9 +920,10 @@ static int rq_calibrate(fg_state* s, fg_model* m, DevPlan* pl, const double* q, 
       if (cudaMalloc(&s->d_ring, sizeof(double) * ring_need) != cudaSuccess) return set_err(FG_ERR_CUDA, "ring allocation failed");
       s->ring_cap = ring_need;
     }
-    if (s->ring_plan != (const void*)pl) {
+    if (s->ring_plan != (const void*)pl || s->ring_slots != prm.ring) {
       cudaMemsetAsync(s->d_ring, 0, sizeof(double) * s->ring_cap, st);
       s->ring_plan = (const void*)pl;
+      s->ring_slots = prm.ring;
     }
     unsigned* ctl = reinterpret_cast<unsigned*>(s->d_ring + rl.ring_doubles);
     if (prof) cudaMemsetAsync(prof, 0, sizeof(unsigned long long) * RQ_PROF_WORDS, st);
@@ -1061,9 +1063,12 @@ static int launch_rq(fg_state* s, fg_model* m, DevPlan* pl, const double* q, con
     FG_CUDA(cudaMalloc(&s->d_ring, sizeof(double) * ring_need));
     s->ring_cap = ring_need;
   }
-  if (s->ring_plan != (const void*)pl) {  // the padding columns of a slot are never written: they must read as zero
+  // the padding columns of a slot are never written: they must read as zero; the control words (error flag) sit behind the
+  // last slot, so a different slot count (the calibration changes the producer count) also means a fresh ring
+  if (s->ring_plan != (const void*)pl || s->ring_slots != prm.ring) {
     FG_CUDA(cudaMemsetAsync(s->d_ring, 0, sizeof(double) * s->ring_cap, st));
     s->ring_plan = (const void*)pl;
+    s->ring_slots = prm.ring;
   }
   if (!s->h_rq_err) {
     FG_CUDA(cudaMallocHost(&s->h_rq_err, sizeof(unsigned)));

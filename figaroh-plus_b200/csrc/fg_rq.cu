@@ -354,10 +354,12 @@ RqLaunch rq_build(const Plan& P, const DevJoint* joints, const RowDesc* rows, co
     break;
   }
   if (rl.nw < 1) { rq_fail(why, "tile does not fit shared memory"); return rl; }
-  // ring + per-warp factors must stay inside the 126 MB L2 (TIAGo at 512 slots of 170 KB: 8.4 GB of DRAM traffic per
-  // 1 M samples, profiles/ncu_rq_tiago_r02_final.md): 40 MB of ring, between 256 and 512 slots (A/B on B200: UR10 512 of
-  // 62 KB; TIAGo, slots of 132 KB: 256..320 slots 10.70 ms, 384 10.86 ms, 512 10.95 ms)
-  const int ring_auto = (int)std::min<int64_t>(512, std::max<int64_t>(256, (40ll << 20) / std::max<int64_t>(1, (int64_t)R.slot_doubles * 8)));
+  // Ring size: every producer warp holds one slot while it fills it, so the ring needs the producer warps plus a little
+  // slack; beyond that, slots only cost L2 (ring + per-warp factors must stay inside the 126 MB).  A/B on B200 - UR10
+  // (352 producer warps, slots of 62 KB): 320 slots 3.90 ms, 352 3.59, 384 3.39, 416 3.42, 448 3.45, 512 3.46; TIAGo
+  // (220 producer warps, slots of 132 KB): 192 11.22 ms, 256..320 10.70, 384 10.86, 512 10.95 (8.4 GB of DRAM traffic
+  // per 1 M samples at 512 slots, profiles/ncu_rq_tiago_r02_final.md).
+  const int ring_auto = std::min(512, std::max(64, (R.nprod + 32 + 31) / 32 * 32));
   R.ring = std::max(8, env_int("FG_RQ_RING", ring_auto));
   R.sleep_ns = std::max(0, env_int("FG_RQ_SLEEP", 400));
   rl.ring_doubles = (int64_t)R.ring * R.slot_doubles;
